@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — Davidson H.C FP64 throughput on the Cr2/SVP M=4000 pair list.
+
+One "step" = one matvec sigma = H_eff.c: zero sigma, replay every recorded GEMM pair of the
+site through libb2g (block2 BatchGEMMSeq::operator(), core/batch_gemm.hpp:1570), and for N > 1
+all-reduce the partial sigma over NCCL (ParallelTensorFunctions::operator(),
+core/parallel_tensor_functions.hpp:51-55).  The pair list (shapes, windows, factors) was
+recorded by the reference itself for data/CR2.SVP.FCIDUMP, SU2, two-site, M = 4000, site 20
+(workloads/README.md); operator values are synthetic (seeded normal), as the contract allows.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    torchrun --nproc-per-node N bench.py --gpus N ...
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+WORKLOAD = os.path.join(ROOT, "workloads", "cr2_svp_m4000_site20.b2seq.gz")
+WORKLOAD_NAME = "Cr2 SVP (data/CR2.SVP.FCIDUMP) SU2 two-site DMRG, M=4000, site 20 H_eff pair list"
+METRIC = "Davidson H.C FP64 TFLOP/s at M=4000 (Cr2 SVP)"
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def reference_replay(max_gflop: float, reps: int, warmup: int, threads: int) -> dict:
+    """Times the reference's own BatchGEMMSeq::operator() (oracle/_ref/b2ref_su2 replay) on a
+    bounded, seeded sample of the same pair list.  The only place bench.py executes oracle/."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "b2ref_su2")
+    if not os.path.exists(exe):
+        raise FileNotFoundError(f"{exe} missing (built by __graft_entry__.build() where /root/reference exists)")
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS=str(threads))
+    scratch = "/tmp/b2ref_bench_scratch"
+    os.makedirs(scratch, exist_ok=True)
+    cmd = [exe, "replay", "--fcidump", WORKLOAD, "--threads", str(threads), "--reps", str(reps),
+           "--warmup", str(warmup), "--scratch", scratch]
+    if max_gflop > 0:
+        cmd += ["--max-gflop", str(max_gflop)]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, check=True).stdout
+    line = [ln for ln in out.splitlines() if ln.startswith("{")][-1]
+    return json.loads(line)
+
+
+def cpu_sample_gflop(threads: int) -> float:
+    # ~40 GFLOP of pair work per host thread: 10-30 s of CPU time at the 2-10 GFLOP/s per core
+    # the reference reaches on these shapes, for warmup + reps = 3 passes
+    return 40.0 * threads
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    r = reference_replay(cpu_sample_gflop(threads), max(args.steps, 1), max(args.warmup, 1), threads)
+    sample = (f"{r['pairs']} of {r['pairs_total']} GEMM pairs ({r['flops'] / 1e9:.0f} GFLOP, seeded random subset) "
+              f"through the reference BatchGEMMSeq::operator() (Tasked), OpenBLAS 1 thread x {threads} OpenMP threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["tflops"], "unit": "TFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds_per_matvec"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAME, "sample": sample},
+        "cpu_baseline": {"value": r["tflops"], "unit": "TFLOP/s", "cores": threads, "kind": "reference",
+                         "sample": sample},
+        "e2e": {"value": r["tflops"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons during the timed region (pynvml)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self) -> dict:
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def fp64_gemm_peak(torch, dev) -> float:
+    """cuBLAS DGEMM 8192^3 TFLOP/s on this GPU, best of 5: the FP64 roofline denominator
+    (MEASURED_PEAKS.json carries only HBM and bf16 figures)."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / (best * 1e-3) * 1e-12
+
+
+def run_b200(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import b2gpkg
+    b2g = b2gpkg.load()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = b2g.Context(local)
+    if world > 1:
+        uid = [b2g.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(world, rank, uid[0])
+
+    full = b2g.load_seqfile(WORKLOAD)
+    sf = full.shard(rank, world) if world > 1 else full
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    ops = torch.empty(max(sf.operand_doubles, 1), dtype=torch.float64, device=dev)
+    ops.normal_(0.0, 1.0, generator=gen)
+    plan = b2g.SeqPlan.from_seqfile(ctx, sf, ops.data_ptr(), b2g.OPERANDS_DEVICE)
+    gc = torch.Generator(device=dev).manual_seed(99)  # same c on every rank
+    c = torch.randn(sf.csize, dtype=torch.float64, device=dev, generator=gc)
+    v = torch.zeros(sf.vsize, dtype=torch.float64, device=dev)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        with torch.cuda.stream(stream):
+            v.zero_()
+        plan.matvec_dev(c.data_ptr(), v.data_ptr(), 1.0)
+        if world > 1:
+            ctx.allreduce_sum(v.data_ptr(), sf.vsize)
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    peak = fp64_gemm_peak(torch, dev) if rank == 0 else 0.0
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    sampler.stop_flag = True
+    sampler.join()
+    launches = ctx.launches - launches0
+    # kernel-only duration of the matvec launches (no memset / all-reduce), same stream
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = 0.0
+    for _ in range(args.steps):
+        with torch.cuda.stream(stream):
+            v.zero_()
+        k0.record(stream)
+        plan.matvec_dev(c.data_ptr(), v.data_ptr(), 1.0)
+        k1.record(stream)
+        ctx.synchronize()
+        kms += k0.elapsed_time(k1)
+    kms /= args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    fl = torch.tensor([sf.flops], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(fl, op=dist.ReduceOp.SUM)
+    ms_step = float(t.item()) / args.steps
+    total_flops = float(fl.item())
+    value = total_flops / (ms_step * 1e-3) * 1e-12
+
+    # end to end through the host-buffer C-ABI call (drop-in for BatchGEMMSeq::operator()):
+    # c from host memory, sigma back to host, every step
+    c_host = c.cpu().numpy().copy()
+    v_host = np.zeros(sf.vsize)
+    plan(c_host, v_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v_host[:] = 0.0
+        plan(c_host, v_host)
+    t_e2e = (time.perf_counter() - t0) / args.steps
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = total_flops / float(te.item()) * 1e-12
+    # cross-check of the two paths (same pair list, same c)
+    chk = float((torch.from_numpy(v_host).to(dev) - v).norm() / v.norm())
+
+    if rank == 0:
+        st = plan.stats
+        kernel_tflops = sf.flops / (kms * 1e-3) * 1e-12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        alg_bytes = 8.0 * (sf.operand_doubles + sf.csize + sf.vsize)
+        line = {
+            "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME, "pairs": full.npairs, "wavefunction_doubles": full.csize,
+                       "operator_bytes": 8 * full.operand_doubles, "flop_per_step": full.flops,
+                       "l2": "inputs (operator blocks, %.1f GB per rank) larger than L2" % (8e-9 * sf.operand_doubles),
+                       "parallelism": "terms sharded over %d rank(s) by left-operator index, NCCL all-reduce of sigma"
+                                      % world},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": 8 * sf.csize,
+                    "d2h_bytes_per_step": 8 * sf.vsize, "path_check_rel": chk},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": kernel_tflops, "peak": peak, "unit": "TFLOP/s",
+                         "frac": kernel_tflops / peak if peak else None, "traffic": None,
+                         "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (FP64 tensor pipe); "
+                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "kernel_ms": kms, "algorithmic_bytes": alg_bytes,
+                         "hbm_gbs_if_streamed_once": alg_bytes / (kms * 1e-3) * 1e-9,
+                         "hbm_peak_gbs": peaks.get("hbm_gbs")},
+            "plan": {"pairs": int(st.pairs), "arenas": int(st.arenas), "launches_per_matvec": int(st.launches),
+                     "n_small": int(st.n_small), "n_large": int(st.n_large)},
+        }
+        if world == 1 and not args.no_cpu:
+            try:
+                threads = host_threads()
+                r = reference_replay(cpu_sample_gflop(threads), 2, 1, threads)
+                line["cpu_baseline"] = {
+                    "value": r["tflops"], "unit": "TFLOP/s", "cores": threads, "kind": "reference",
+                    "sample": f"{r['pairs']} of {r['pairs_total']} pairs ({r['flops'] / 1e9:.0f} GFLOP, seeded random "
+                              f"subset), reference BatchGEMMSeq::operator() Tasked, {r['seconds_per_matvec']:.2f} s/pass"}
+            except Exception as exc:  # the baseline is reported, never needed by the GPU path
+                line["cpu_baseline"] = {"value": None, "unit": "TFLOP/s", "cores": host_threads(), "kind": "reference",
+                                        "sample": f"unavailable: {exc}"}
+        print(json.dumps(line), flush=True)
+    plan.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,356 @@
+// b2g_core.cu — context, plan construction and the host entry points of libb2g.so.
+//
+// The plan is the device-side form of what EffectiveHamiltonian::precompute()
+// records into BatchGEMMSeq (block2 src/dmrg/effective_hamiltonian.hpp:226-246,
+// src/core/batch_gemm.hpp:893-902, 952-1022): a flat list of GEMM pairs whose
+// wavefunction operands are null-based offsets and whose operator operands are
+// raw pointers.  Nothing of the reference is compiled into this library.
+#include "b2g_internal.h"
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <mutex>
+
+static thread_local std::string g_err;
+void b2g_set_error(const std::string &msg) { g_err = msg; }
+
+extern "C" const char *b2g_last_error(void) { return g_err.c_str(); }
+
+extern "C" int b2g_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+        return 0;
+    return n;
+}
+
+extern "C" int b2g_context_create(int device, b2g_context **out) {
+    if (!out) {
+        b2g_set_error("b2g_context_create: null out");
+        return 1;
+    }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        b2g_set_error(std::string("b2g_context_create: no CUDA device (") +
+                      (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0") +
+                      "); libb2g has no CPU fallback");
+        return 2;
+    }
+    B2G_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    B2G_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        b2g_set_error("b2g_context_create: device is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                      ", libb2g is built for sm_100a only");
+        return 3;
+    }
+    b2g_context *ctx = new b2g_context();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    B2G_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    *out = ctx;
+    return 0;
+}
+
+extern "C" int b2g_context_destroy(b2g_context *ctx) {
+    if (!ctx)
+        return 0;
+    cudaSetDevice(ctx->device);
+    if (ctx->nccl_comm)
+        b2g_comm_destroy(ctx);
+    if (ctx->h_stage)
+        cudaFreeHost(ctx->h_stage);
+    if (ctx->d_c)
+        cudaFree(ctx->d_c);
+    if (ctx->d_v)
+        cudaFree(ctx->d_v);
+    if (ctx->stream)
+        cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+extern "C" int64_t b2g_context_launches(const b2g_context *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void *b2g_context_stream(const b2g_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" int b2g_context_synchronize(b2g_context *ctx) {
+    B2G_CUDA(cudaSetDevice(ctx->device));
+    B2G_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int b2g_malloc(b2g_context *ctx, size_t bytes, void **dev) {
+    B2G_CUDA(cudaSetDevice(ctx->device));
+    B2G_CUDA(cudaMalloc(dev, bytes));
+    return 0;
+}
+extern "C" int b2g_free(b2g_context *ctx, void *dev) {
+    B2G_CUDA(cudaSetDevice(ctx->device));
+    B2G_CUDA(cudaFree(dev));
+    return 0;
+}
+extern "C" int b2g_memcpy_h2d(b2g_context *ctx, void *dev, const void *host, size_t bytes) {
+    B2G_CUDA(cudaSetDevice(ctx->device));
+    B2G_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    B2G_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int b2g_memcpy_d2h(b2g_context *ctx, void *host, const void *dev, size_t bytes) {
+    B2G_CUDA(cudaSetDevice(ctx->device));
+    B2G_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    B2G_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int b2g_memset_zero(b2g_context *ctx, void *dev, size_t bytes) {
+    B2G_CUDA(cudaSetDevice(ctx->device));
+    B2G_CUDA(cudaMemsetAsync(dev, 0, bytes, ctx->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------ plan
+
+static inline bool is_trans(int32_t t) { return t == B2G_TRANS || t == 1; }
+static inline bool valid_trans(int32_t t) { return t == B2G_TRANS || t == B2G_NOTRANS || t == 0 || t == 1; }
+
+// elements spanned by a row-major rows x cols matrix with leading dimension ld
+static inline size_t extent(int rows, int cols, int ld) {
+    return (rows <= 0 || cols <= 0) ? 0 : (size_t)(rows - 1) * (size_t)ld + (size_t)cols;
+}
+
+struct Range {
+    uintptr_t lo, hi;
+    size_t dev_off; // doubles
+};
+
+extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_batch *b1, int64_t max_work,
+                               int64_t csize, int64_t vsize, int operand_space, b2g_plan **out) {
+    if (!ctx || !b0 || !b1 || !out) {
+        b2g_set_error("b2g_plan_create: null argument");
+        return 1;
+    }
+    if (b0->count != b1->count) {
+        b2g_set_error("b2g_plan_create: batch[0] and batch[1] differ in length (gp[i] must be 1, acidxs empty)");
+        return 1;
+    }
+    if (csize >= ((int64_t)1 << 31) || vsize >= ((int64_t)1 << 31)) {
+        b2g_set_error("b2g_plan_create: wavefunction larger than 2^31 doubles");
+        return 1;
+    }
+    B2G_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = b0->count;
+    b2g_plan *p = new b2g_plan();
+    p->ctx = ctx, p->npairs = n, p->csize = csize, p->vsize = vsize, p->max_work = max_work;
+    std::vector<B2GPair> &hp = p->h_pairs;
+    hp.resize((size_t)n);
+    std::vector<Range> rg;
+    rg.reserve((size_t)2 * n);
+    int64_t nflop = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (!valid_trans(b0->ta[i]) || !valid_trans(b0->tb[i]) || !valid_trans(b1->ta[i]) ||
+            !valid_trans(b1->tb[i])) {
+            b2g_set_error("b2g_plan_create: pair " + std::to_string(i) + ": transpose flag is not N/T");
+            delete p;
+            return 1;
+        }
+        const bool ta0 = is_trans(b0->ta[i]), tb0 = is_trans(b0->tb[i]), ta1 = is_trans(b1->ta[i]),
+                   tb1 = is_trans(b1->tb[i]);
+        const int m0 = b0->m[i], n0 = b0->n[i], k0 = b0->k[i], m1 = b1->m[i], n1 = b1->n[i], k1 = b1->k[i];
+        // the chained form recorded by AdvancedGEMM<real>::rotate / BatchGEMMSeq::three_rotate:
+        // GEMM 1 consumes the contiguous work matrix of GEMM 0 as its untransposed B operand
+        if ((const void *)b0->c[i] != (const void *)b1->b[i] || tb1 || k1 != m0 || n1 != n0 ||
+            b0->ldc[i] != n0 || b1->ldb[i] != n0 || b0->beta[i] != 0.0 || b1->beta[i] != 1.0) {
+            b2g_set_error("b2g_plan_create: pair " + std::to_string(i) +
+                          " is not a chained W = A0*B0, C1 += A1*W pair");
+            delete p;
+            return 1;
+        }
+        const uintptr_t a0 = (uintptr_t)b0->a[i], c1 = (uintptr_t)b1->c[i];
+        if (a0 % sizeof(double) || c1 % sizeof(double)) {
+            b2g_set_error("b2g_plan_create: misaligned wavefunction offset");
+            delete p;
+            return 1;
+        }
+        const size_t a0_off = a0 / sizeof(double), c1_off = c1 / sizeof(double);
+        const size_t ea = extent(ta0 ? k0 : m0, ta0 ? m0 : k0, b0->lda[i]);
+        const size_t ec = extent(m1, n1, b1->ldc[i]);
+        if (a0_off + ea > (size_t)csize || c1_off + ec > (size_t)vsize) {
+            b2g_set_error("b2g_plan_create: pair " + std::to_string(i) +
+                          ": wavefunction window outside [0, size) - operands must be recorded null-based");
+            delete p;
+            return 1;
+        }
+        B2GPair &q = hp[(size_t)i];
+        q.b0 = b0->b[i], q.a1 = b1->a[i];
+        q.alpha0 = b0->alpha[i], q.alpha1 = b1->alpha[i];
+        q.a0_off = (int32_t)a0_off, q.c1_off = (int32_t)c1_off;
+        q.m0 = m0, q.n0 = n0, q.k0 = k0, q.m1 = m1;
+        q.lda0 = b0->lda[i], q.ldb0 = b0->ldb[i], q.lda1 = b1->lda[i], q.ldc1 = b1->ldc[i];
+        q.flags = (ta0 ? B2G_F_TA0 : 0) | (tb0 ? B2G_F_TB0 : 0) | (ta1 ? B2G_F_TA1 : 0);
+        q.pad = 0;
+        nflop += (int64_t)m0 * n0 * k0 + (int64_t)m1 * n1 * k1;
+        const size_t eb0 = extent(tb0 ? n0 : k0, tb0 ? k0 : n0, q.ldb0);
+        const size_t ea1 = extent(ta1 ? k1 : m1, ta1 ? m1 : k1, q.lda1);
+        const uintptr_t pb = (uintptr_t)q.b0, pa = (uintptr_t)q.a1;
+        if (eb0)
+            rg.push_back(Range{pb, pb + eb0 * sizeof(double), 0});
+        if (ea1)
+            rg.push_back(Range{pa, pa + ea1 * sizeof(double), 0});
+    }
+    // merge the referenced operator ranges into arenas
+    std::sort(rg.begin(), rg.end(), [](const Range &x, const Range &y) { return x.lo < y.lo; });
+    std::vector<Range> ar;
+    for (const Range &r : rg) {
+        if (!ar.empty() && r.lo <= ar.back().hi)
+            ar.back().hi = std::max(ar.back().hi, r.hi);
+        else
+            ar.push_back(r);
+    }
+    size_t total = 0;
+    for (Range &r : ar) {
+        r.dev_off = total;
+        total += (r.hi - r.lo) / sizeof(double);
+        total = (total + 1) & ~(size_t)1; // keep every arena 16-byte aligned relative to its host alignment
+    }
+    p->stats.pairs = n, p->stats.csize = csize, p->stats.vsize = vsize, p->stats.nflop_mnk = nflop;
+    p->stats.arenas = (int64_t)ar.size();
+    size_t op_doubles = 0;
+    for (const Range &r : ar)
+        op_doubles += (r.hi - r.lo) / sizeof(double);
+    p->stats.operand_doubles = (int64_t)op_doubles;
+
+    auto t0 = std::chrono::steady_clock::now();
+    if (operand_space == B2G_OPERANDS_HOST && total > 0) {
+        if (cudaMalloc(&p->d_operands, total * sizeof(double)) != cudaSuccess) {
+            b2g_set_error("b2g_plan_create: cudaMalloc of " + std::to_string(total * 8) + " operand bytes failed");
+            delete p;
+            return 1;
+        }
+        for (const Range &r : ar) {
+            // preserve the 16-byte phase of the host address so vector loads keep their alignment
+            cudaError_t e = cudaMemcpyAsync(p->d_operands + r.dev_off, (const void *)r.lo, r.hi - r.lo,
+                                            cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) {
+                b2g_set_error(std::string("b2g_plan_create: operand upload failed: ") + cudaGetErrorString(e));
+                cudaFree(p->d_operands);
+                delete p;
+                return 1;
+            }
+        }
+        auto locate = [&ar](uintptr_t ptr) -> const Range & {
+            size_t lo = 0, hi = ar.size();
+            while (hi - lo > 1) {
+                size_t mid = (lo + hi) / 2;
+                if (ar[mid].lo <= ptr)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            return ar[lo];
+        };
+        for (B2GPair &q : hp) {
+            const Range &rb = locate((uintptr_t)q.b0);
+            q.b0 = p->d_operands + rb.dev_off + ((uintptr_t)q.b0 - rb.lo) / sizeof(double);
+            const Range &ra = locate((uintptr_t)q.a1);
+            q.a1 = p->d_operands + ra.dev_off + ((uintptr_t)q.a1 - ra.lo) / sizeof(double);
+        }
+    }
+    // order: pairs writing the same sigma window become neighbours (locality of the accumulation)
+    std::stable_sort(hp.begin(), hp.end(), [](const B2GPair &x, const B2GPair &y) {
+        if (x.c1_off != y.c1_off)
+            return x.c1_off < y.c1_off;
+        return x.a0_off < y.a0_off;
+    });
+    if (n > 0) {
+        B2G_CUDA(cudaMalloc(&p->d_pairs, (size_t)n * sizeof(B2GPair)));
+        B2G_CUDA(cudaMemcpyAsync(p->d_pairs, hp.data(), (size_t)n * sizeof(B2GPair), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    }
+    B2G_CUDA(cudaStreamSynchronize(ctx->stream));
+    p->stats.upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    p->n_generic = n;
+    p->stats.n_small = 0, p->stats.n_large = n;
+    p->stats.launches = n > 0 ? 1 : 0;
+    *out = p;
+    return 0;
+}
+
+extern "C" int b2g_plan_destroy(b2g_plan *p) {
+    if (!p)
+        return 0;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    if (p->d_operands)
+        cudaFree(p->d_operands);
+    if (p->d_pairs)
+        cudaFree(p->d_pairs);
+    if (p->d_work)
+        cudaFree(p->d_work);
+    delete p;
+    return 0;
+}
+
+extern "C" int b2g_plan_get_stats(const b2g_plan *p, b2g_plan_stats *out) {
+    if (!p || !out) {
+        b2g_set_error("b2g_plan_get_stats: null argument");
+        return 1;
+    }
+    *out = p->stats;
+    return 0;
+}
+
+extern "C" int b2g_seq_matvec_dev(b2g_plan *p, const double *c_dev, double *v_dev, double scale) {
+    if (!p) {
+        b2g_set_error("b2g_seq_matvec_dev: null plan");
+        return 1;
+    }
+    B2G_CUDA(cudaSetDevice(p->ctx->device));
+    return b2g_launch_matvec(p, c_dev, v_dev, scale);
+}
+
+static int ensure_staging(b2g_context *ctx, size_t csize, size_t vsize) {
+    const size_t need = std::max(csize, vsize);
+    if (ctx->h_stage_doubles < need) {
+        if (ctx->h_stage)
+            cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr, ctx->h_stage_doubles = 0;
+        B2G_CUDA(cudaMallocHost(&ctx->h_stage, need * sizeof(double)));
+        ctx->h_stage_doubles = need;
+    }
+    if (ctx->d_cv_doubles < need) {
+        if (ctx->d_c)
+            cudaFree(ctx->d_c);
+        if (ctx->d_v)
+            cudaFree(ctx->d_v);
+        ctx->d_c = ctx->d_v = nullptr, ctx->d_cv_doubles = 0;
+        B2G_CUDA(cudaMalloc(&ctx->d_c, need * sizeof(double)));
+        B2G_CUDA(cudaMalloc(&ctx->d_v, need * sizeof(double)));
+        ctx->d_cv_doubles = need;
+    }
+    return 0;
+}
+
+// Host-buffer drop-in for BatchGEMMSeq::operator()(c, v, scale): the reference accumulates
+// into v (beta = 1 on every second GEMM), so the device result is added to the caller's v.
+extern "C" int b2g_seq_matvec(b2g_plan *p, const double *c_host, double *v_host, double scale) {
+    if (!p || !c_host || !v_host) {
+        b2g_set_error("b2g_seq_matvec: null argument");
+        return 1;
+    }
+    b2g_context *ctx = p->ctx;
+    B2G_CUDA(cudaSetDevice(ctx->device));
+    if (ensure_staging(ctx, (size_t)p->csize, (size_t)p->vsize))
+        return 1;
+    memcpy(ctx->h_stage, c_host, (size_t)p->csize * sizeof(double));
+    B2G_CUDA(cudaMemcpyAsync(ctx->d_c, ctx->h_stage, (size_t)p->csize * sizeof(double), cudaMemcpyHostToDevice,
+                             ctx->stream));
+    B2G_CUDA(cudaMemsetAsync(ctx->d_v, 0, (size_t)p->vsize * sizeof(double), ctx->stream));
+    if (b2g_launch_matvec(p, ctx->d_c, ctx->d_v, scale))
+        return 1;
+    if (ctx->nccl_comm && b2g_allreduce_sum(ctx, ctx->d_v, p->vsize))
+        return 1;
+    B2G_CUDA(cudaMemcpyAsync(ctx->h_stage, ctx->d_v, (size_t)p->vsize * sizeof(double), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    B2G_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int64_t i = 0; i < p->vsize; i++)
+        v_host[i] += ctx->h_stage[i];
+    return 0;
+}

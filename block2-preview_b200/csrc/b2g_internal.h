@@ -1,0 +1,65 @@
+// b2g_internal.h — internal types of libb2g.so (not part of the C ABI).
+#pragma once
+#include "../../include/b2g.h"
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+// One GEMM pair of the H.C replay list, device layout (80 bytes).
+//   W[m0 x n0]        = alpha0 * op(c + a0_off)[m0 x k0] * op(b0)[k0 x n0]
+//   v + c1_off [m1 x n0] += alpha1 * op(a1)[m1 x m0] * W          (k1 == m0, n1 == n0)
+struct B2GPair {
+    const double *b0; // operator block of GEMM 0 (device)
+    const double *a1; // operator block of GEMM 1 (device)
+    double alpha0, alpha1;
+    int32_t a0_off, c1_off; // |psi| < 2^31 is asserted by the reference (effective_hamiltonian.hpp:413)
+    int32_t m0, n0, k0, m1;
+    int32_t lda0, ldb0, lda1, ldc1;
+    uint32_t flags; // bit0 ta0, bit1 tb0, bit2 ta1
+    uint32_t pad;
+};
+static_assert(sizeof(B2GPair) == 80, "B2GPair layout");
+
+#define B2G_F_TA0 1u
+#define B2G_F_TB0 2u
+#define B2G_F_TA1 4u
+
+struct b2g_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    int64_t launches = 0;
+    // pinned staging for the host-buffer entry points
+    double *h_stage = nullptr;
+    size_t h_stage_doubles = 0;
+    double *d_c = nullptr, *d_v = nullptr;
+    size_t d_cv_doubles = 0;
+    void *nccl_comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+struct b2g_plan {
+    b2g_context *ctx = nullptr;
+    int64_t npairs = 0, csize = 0, vsize = 0, max_work = 0;
+    b2g_plan_stats stats{};
+    double *d_operands = nullptr; // mirrored operator arenas (operand_space == HOST)
+    B2GPair *d_pairs = nullptr;   // sorted by kernel class, then by output window
+    int64_t n_generic = 0;        // pairs [0, n_generic) run through the generic kernel
+    double *d_work = nullptr;     // spill space for W of pairs too large for shared memory
+    size_t work_doubles = 0;
+    std::vector<B2GPair> h_pairs; // host copy (debug / stats)
+};
+
+void b2g_set_error(const std::string &msg);
+#define B2G_CUDA(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t e__ = (expr);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            b2g_set_error(std::string(#expr) + ": " + cudaGetErrorString(e__));          \
+            return 1;                                                                    \
+        }                                                                                \
+    } while (0)
+
+// kernels (b2g_kernels.cu)
+int b2g_launch_matvec(b2g_plan *plan, const double *c_dev, double *v_dev, double scale);

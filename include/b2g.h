@@ -1,0 +1,122 @@
+/* include/b2g.h — C ABI of libb2g.so, the sm_100a CUDA executor for block2's
+ * Davidson H.C hot path.  Plain pointers and sizes only; no torch, no
+ * reference types.  Every entry point returns 0 on success and a non-zero
+ * code on failure (b2g_last_error() holds the message); nothing here falls
+ * back to the CPU.
+ *
+ * Reference interfaces replaced (paths under block2 src/):
+ *   b2g_batch            <- BatchGEMM<double> SoA arrays      core/batch_gemm.hpp:237-247
+ *   b2g_plan_create      <- EffectiveHamiltonian::precompute  dmrg/effective_hamiltonian.hpp:226-246
+ *                           (consumes seq->batch[0], seq->batch[1], seq->max_work)
+ *   b2g_seq_matvec       <- BatchGEMMSeq<double>::operator()(c, v, scale), Tasked branch
+ *                           core/batch_gemm.hpp:1570-1691 (= TensorFunctions::operator(),
+ *                           core/tensor_functions.hpp:59-62)
+ *   b2g_plan_destroy     <- EffectiveHamiltonian::post_precompute  :247-253
+ *   b2g_dgemm_batch      <- cblas_xgemm_batch / BatchGEMM::perform  core/batch_gemm.hpp:81-111, 339-357
+ *   b2g_davidson         <- IterativeMatrixFunctions<double>::davidson (k = 1, Normal type,
+ *                           Olsen preconditioner)  core/iterative_matrix_functions.hpp:864-1173, 93-108
+ *   b2g_comm_* / b2g_allreduce_sum
+ *                        <- MPICommunicator::allreduce_sum(double*, size_t)  core/parallel_mpi.hpp:300-309
+ *                           as used by ParallelTensorFunctions::operator()  core/parallel_tensor_functions.hpp:51-55
+ */
+#ifndef B2G_H
+#define B2G_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2G_NOTRANS 111 /* CblasNoTrans; 0 is accepted too */
+#define B2G_TRANS 112   /* CblasTrans;   1 is accepted too */
+
+#define B2G_OPERANDS_HOST 0   /* a/b operator pointers are host addresses: mirrored to HBM by the plan */
+#define B2G_OPERANDS_DEVICE 1 /* a/b operator pointers already are device addresses (resident environments) */
+
+typedef struct b2g_context b2g_context;
+typedef struct b2g_plan b2g_plan;
+
+/* One recorded GEMM list, entry i = one row-major GEMM
+ *   C_i[m x n] = alpha_i * op(A_i) * op(B_i) + beta_i * C_i,   lda >= (ta ? m : k), ldb >= (tb ? k : n), ldc >= n
+ * exactly as BatchGEMM<double> stores it with gp[i] == 1. */
+typedef struct b2g_batch {
+    int64_t count;
+    const int32_t *ta, *tb;
+    const int32_t *m, *n, *k;
+    const int32_t *lda, *ldb, *ldc;
+    const double *alpha, *beta;
+    const double *const *a;
+    const double *const *b;
+    double *const *c;
+} b2g_batch;
+
+typedef struct b2g_plan_stats {
+    int64_t pairs;          /* GEMM pairs per matvec */
+    int64_t csize, vsize;   /* |c|, |sigma| in doubles */
+    int64_t nflop_mnk;      /* sum m*n*k over both GEMMs (reference units, batch_gemm.hpp:307) */
+    int64_t operand_doubles;/* distinct operator doubles referenced (mirrored or resident) */
+    int64_t arenas;         /* merged contiguous operand ranges */
+    int64_t launches;       /* kernel launches per matvec */
+    int64_t n_small, n_large; /* pairs routed to the warp-per-pair / CTA-tiled kernels */
+    double upload_seconds;  /* host->device mirror time of the operands */
+} b2g_plan_stats;
+
+const char *b2g_last_error(void);
+int b2g_device_count(void);
+int b2g_context_create(int device, b2g_context **ctx);
+int b2g_context_destroy(b2g_context *ctx);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+int64_t b2g_context_launches(const b2g_context *ctx);
+/* the CUDA stream all work of this context is ordered on (cudaStream_t) */
+void *b2g_context_stream(const b2g_context *ctx);
+int b2g_context_synchronize(b2g_context *ctx);
+
+/* Build the replay plan of one H_eff from the two recorded lists.
+ * Pair i:  W = alpha0 * op(c + a0_i) * op(B0_i);   sigma + c1_i += alpha1 * scale * op(A1_i) * W
+ * batch0->a[i] and batch1->c[i] are null-based offsets into c / sigma (the reference records
+ * them with cmat->data = vmat->data = 0), batch0->c[i] == batch1->b[i] is the work slot. */
+int b2g_plan_create(b2g_context *ctx, const b2g_batch *batch0, const b2g_batch *batch1,
+                    int64_t max_work, int64_t csize, int64_t vsize, int operand_space,
+                    b2g_plan **plan);
+int b2g_plan_destroy(b2g_plan *plan);
+int b2g_plan_get_stats(const b2g_plan *plan, b2g_plan_stats *out);
+
+/* sigma += scale * H.c, host buffers (drop-in for BatchGEMMSeq::operator()). Synchronous. */
+int b2g_seq_matvec(b2g_plan *plan, const double *c_host, double *v_host, double scale);
+/* same with device-resident c and sigma; asynchronous on the context stream */
+int b2g_seq_matvec_dev(b2g_plan *plan, const double *c_dev, double *v_dev, double scale);
+
+/* Grouped GEMM list with the cblas_dgemm_batch signature (device pointers), asynchronous. */
+int b2g_dgemm_batch(b2g_context *ctx, int64_t group_count, const int32_t *ta, const int32_t *tb,
+                    const int32_t *m, const int32_t *n, const int32_t *k, const double *alpha,
+                    const double *const *a, const int32_t *lda, const double *const *b,
+                    const int32_t *ldb, const double *beta, double *const *c, const int32_t *ldc,
+                    const int32_t *group_size);
+
+/* Davidson ground state with device-resident vectors; H applied through the plan.
+ * ket_host: in = initial guess, out = eigenvector.  diag_host: H_eff diagonal.
+ * Returns the eigenvalue (without const_e) and the number of matvecs, like
+ * EffectiveHamiltonian::eigs (effective_hamiltonian.hpp:480-566). */
+int b2g_davidson(b2g_plan *plan, const double *diag_host, double *ket_host, double conv_thrd,
+                 double rel_conv_thrd, int max_iter, int soft_max_iter, int deflation_min_size,
+                 int deflation_max_size, double *eigenvalue, int *ndav);
+
+/* Multi-GPU: one process per GPU, sigma summed with an NCCL all-reduce on the context stream. */
+int b2g_comm_unique_id(void *id128);               /* rank 0: fill a 128-byte ncclUniqueId */
+int b2g_comm_init(b2g_context *ctx, int nranks, int rank, const void *id128);
+int b2g_comm_destroy(b2g_context *ctx);
+int b2g_allreduce_sum(b2g_context *ctx, double *dev, int64_t count); /* in place, async */
+
+/* device memory helpers for hosts without a CUDA runtime binding of their own */
+int b2g_malloc(b2g_context *ctx, size_t bytes, void **dev);
+int b2g_free(b2g_context *ctx, void *dev);
+int b2g_memcpy_h2d(b2g_context *ctx, void *dev, const void *host, size_t bytes);
+int b2g_memcpy_d2h(b2g_context *ctx, void *host, const void *dev, size_t bytes);
+int b2g_memset_zero(b2g_context *ctx, void *dev, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2G_H */

@@ -17,8 +17,10 @@
  *           H_eff diagonal, the initial ket and the reference Davidson
  *           answer (EffectiveHamiltonian::eigs, :480).  File layout is
  *           documented in oracle/seqdump.py.
- *   time  : same stop, then time N replays of the reference matvec on the
- *           host cores (cpu_baseline / --impl reference of bench.py).
+ *   replay: load a .b2seq pair list (with or without operand data), rebuild the
+ *           reference's BatchGEMMSeq from it and time the reference's own
+ *           BatchGEMMSeq::operator() on the host threads (cpu_baseline and
+ *           --impl reference of bench.py; --max-gflop bounds the sample).
  *
  * Structure-only mode (--struct) records the pair list of a large bond
  * dimension without doing (or storing) any numerics: every TensorFunctions
@@ -42,7 +44,8 @@ struct Args {
     int bond = 250, site = -1, sweeps = 0, n_sweeps = 8, threads = 8, reps = 3,
         dav_max = 4000, seed = 0;
     bool with_data = true, structure_only = false, run_eigs = true;
-    double conv = 1e-7, noise = 1e-5;
+    double conv = 1e-7, noise = 1e-5, max_gflop = 0;
+    int warmup = 1;
     size_t dsize_gb = 8;
 };
 
@@ -82,6 +85,8 @@ static Args parse(int argc, char **argv) {
         else if (k == "--dsize") a.dsize_gb = (size_t)atol(nxt().c_str());
         else if (k == "--conv") a.conv = atof(nxt().c_str());
         else if (k == "--noise") a.noise = atof(nxt().c_str());
+        else if (k == "--max-gflop") a.max_gflop = atof(nxt().c_str());
+        else if (k == "--warmup") a.warmup = atoi(nxt().c_str());
         else if (k == "--nodata") a.with_data = false;
         else if (k == "--noeigs") a.run_eigs = false;
         else if (k == "--struct") a.structure_only = true, a.with_data = false, a.run_eigs = false;
@@ -150,29 +155,41 @@ struct StructTensorFunctions : TensorFunctions<S, FL> {
         m->alloc = nullptr;
         m->data = n == 0 ? nullptr : g_varena.take(n);
     }
+    // which operators of the blocked tensor get storage: the non-delayed
+    // entries of c->lmat / c->rmat that are not already cached
+    // (tensor_functions.hpp:2842-2885, 2941-2984)
+    static void alloc_named(const shared_ptr<Symbolic<S>> &names,
+                            const shared_ptr<OperatorTensor<S, FL>> &c,
+                            OpNamesSet delayed) {
+        for (size_t i = 0; i < names->data.size(); i++) {
+            shared_ptr<OpElement<S, FL>> cop =
+                dynamic_pointer_cast<OpElement<S, FL>>(names->data[i]);
+            if (cop == nullptr || delayed(cop->name))
+                continue;
+            shared_ptr<OpExpr<S>> op = abs_value(names->data[i]);
+            if (c->ops.count(op))
+                valloc(c->ops.at(op));
+        }
+    }
     void left_contract(const shared_ptr<OperatorTensor<S, FL>> &a,
                        const shared_ptr<OperatorTensor<S, FL>> &b,
                        shared_ptr<OperatorTensor<S, FL>> &c,
                        const shared_ptr<Symbolic<S>> &cexprs = nullptr,
                        OpNamesSet delayed = OpNamesSet()) const override {
-        for (auto &p : c->ops) {
-            shared_ptr<OpElement<S, FL>> op =
-                dynamic_pointer_cast<OpElement<S, FL>>(p.first);
-            if (a == nullptr || !delayed(op->name))
-                valloc(p.second);
-        }
+        if (a == nullptr) // first site: tiny site operators, stock code
+            TensorFunctions<S, FL>::left_assign(b, c);
+        else
+            alloc_named(c->lmat, c, delayed);
     }
     void right_contract(const shared_ptr<OperatorTensor<S, FL>> &a,
                         const shared_ptr<OperatorTensor<S, FL>> &b,
                         shared_ptr<OperatorTensor<S, FL>> &c,
                         const shared_ptr<Symbolic<S>> &cexprs = nullptr,
                         OpNamesSet delayed = OpNamesSet()) const override {
-        for (auto &p : c->ops) {
-            shared_ptr<OpElement<S, FL>> op =
-                dynamic_pointer_cast<OpElement<S, FL>>(p.first);
-            if (a == nullptr || !delayed(op->name))
-                valloc(p.second);
-        }
+        if (a == nullptr)
+            TensorFunctions<S, FL>::right_assign(b, c);
+        else
+            alloc_named(c->rmat, c, delayed);
     }
     void left_rotate(const shared_ptr<OperatorTensor<S, FL>> &a,
                      const shared_ptr<SparseMatrix<S, FL>> &mpst_bra,
@@ -188,19 +205,54 @@ struct StructTensorFunctions : TensorFunctions<S, FL> {
         for (auto &p : c->ops)
             valloc(p.second);
     }
+    // new intermediate operators (the SumProd pre-sums H.C reads) get an
+    // entry + storage exactly when the stock code creates them
+    // (tensor_functions.hpp:2404-2440)
     void intermediates(const shared_ptr<Symbolic<S>> &names,
                        const shared_ptr<Symbolic<S>> &exprs,
                        const shared_ptr<OperatorTensor<S, FL>> &a,
-                       bool left) const override {}
+                       bool left) const override {
+        for (size_t i = 0; i < exprs->data.size(); i++) {
+            if (exprs->data[i] == nullptr ||
+                exprs->data[i]->get_type() != OpTypes::Sum)
+                continue;
+            shared_ptr<OpSum<S, FL>> expr =
+                dynamic_pointer_cast<OpSum<S, FL>>(exprs->data[i]);
+            for (auto &str : expr->strings) {
+                if (str->get_type() != OpTypes::SumProd)
+                    continue;
+                shared_ptr<OpSumProd<S, FL>> ex =
+                    dynamic_pointer_cast<OpSumProd<S, FL>>(str);
+                if ((left && ex->b == nullptr) || (!left && ex->a == nullptr) ||
+                    ex->c == nullptr || a->ops.count(ex->c) != 0)
+                    continue;
+                shared_ptr<SparseMatrix<S, FL>> tmp =
+                    make_shared<SparseMatrix<S, FL>>();
+                tmp->info = a->ops.at(abs_value((shared_ptr<OpExpr<S>>)ex->ops[0]))->info;
+                valloc(tmp);
+                a->ops[ex->c] = tmp;
+            }
+        }
+    }
     void numerical_transform(const shared_ptr<OperatorTensor<S, FL>> &a,
                              const shared_ptr<Symbolic<S>> &names,
                              const shared_ptr<Symbolic<S>> &exprs) const override {
-        // the transformed operators (names) need storage like the stock code
-        for (size_t i = 0; i < names->data.size(); i++) {
-            shared_ptr<OpExpr<S>> op = abs_value(names->data[i]);
-            if (a->ops.count(op))
-                valloc(a->ops.at(op));
-        }
+        if (a->lmat == nullptr)
+            a->rmat = names;
+        else
+            a->lmat = names;
+    }
+    void post_numerical_transform(const shared_ptr<OperatorTensor<S, FL>> &a,
+                                  const shared_ptr<Symbolic<S>> &names,
+                                  const shared_ptr<Symbolic<S>> &new_names) const override {
+        set<shared_ptr<OpExpr<S>>, op_expr_less<S>> del_ops;
+        for (auto &x : names->data)
+            del_ops.insert(x);
+        for (auto &x : new_names->data)
+            del_ops.erase(x);
+        for (auto &p : a->ops)
+            if (del_ops.count(p.first))
+                p.second->data = nullptr, p.second->total_memory = 0;
     }
     void tensor_product_diagonal(const shared_ptr<OpExpr<S>> &expr,
                                  const shared_ptr<OpExpr<S>> &stacked_expr,
@@ -442,6 +494,146 @@ template <typename S> struct StopDMRG : DMRG<S, double, double> {
     }
 };
 
+
+/* ---------- replay mode: the reference's own executor on a recorded list ----------
+ * Rebuilds a BatchGEMMSeq<double> (batch_gemm.hpp:847) from a .b2seq file through the
+ * reference's recording calls (BatchGEMM::xgemm_group / xgemm_array, :287-312), fills the
+ * operator arenas with seeded synthetic data when the file carries none, and times
+ * BatchGEMMSeq::operator()(c, v, 1.0) (:1570, Tasked branch) on the host threads.
+ * --max-gflop bounds the sample: pairs are taken in a seeded random order until the budget
+ * is reached, and only the arenas they reference are allocated. */
+struct SeqFileRaw {
+    vector<uint64_t> hdr;
+    vector<double> dh;
+    vector<int32_t> i32[16];
+    vector<double> f64[4];
+    vector<int64_t> i64[7];
+    vector<uint64_t> asz;
+    vector<double> arenas, c;
+};
+
+static bool read_seqfile(const string &path, SeqFileRaw &r) {
+    FILE *f = nullptr;
+    bool piped = false;
+    if (path.size() > 3 && path.substr(path.size() - 3) == ".gz") {
+        f = popen(("gzip -dc '" + path + "'").c_str(), "r");
+        piped = true;
+    } else
+        f = fopen(path.c_str(), "rb");
+    if (!f)
+        return false;
+    char magic[8];
+    bool ok = fread(magic, 1, 8, f) == 8 && magic[0] == 'B' && magic[7] == 2;
+    r.hdr.resize(16), r.dh.resize(8);
+    ok = ok && fread(r.hdr.data(), 8, 16, f) == 16 && fread(r.dh.data(), 8, 8, f) == 8;
+    size_t n = ok ? r.hdr[0] : 0, na = ok ? r.hdr[1] : 0;
+    for (auto &v : r.i32) { v.resize(n); ok = ok && fread(v.data(), 4, n, f) == n; }
+    for (auto &v : r.f64) { v.resize(n); ok = ok && fread(v.data(), 8, n, f) == n; }
+    for (auto &v : r.i64) { v.resize(n); ok = ok && fread(v.data(), 8, n, f) == n; }
+    r.asz.resize(na);
+    ok = ok && fread(r.asz.data(), 8, na, f) == na;
+    if (ok && r.hdr[6]) {
+        size_t tot = 0;
+        for (auto x : r.asz) tot += x;
+        r.arenas.resize(tot), r.c.resize(r.hdr[2]);
+        ok = fread(r.arenas.data(), 8, tot, f) == tot && fread(r.c.data(), 8, r.hdr[2], f) == r.hdr[2];
+    }
+    piped ? pclose(f) : fclose(f);
+    return ok;
+}
+
+static int run_replay(const Args &args) {
+    SeqFileRaw r;
+    if (!read_seqfile(args.fcidump, r)) {
+        fprintf(stderr, "cannot read %s\n", args.fcidump.c_str());
+        return 1;
+    }
+    frame_<double>() = make_shared<DataFrame<double>>((size_t)1 << 24, (size_t)1 << 24, args.scratch);
+    threading_() = make_shared<Threading>(
+        ThreadingTypes::OperatorBatchedGEMM | ThreadingTypes::Global, args.threads, args.threads, 1);
+    threading_()->seq_type = SeqTypes::Tasked;
+    const size_t n = r.hdr[0], na = r.hdr[1], csize = r.hdr[2], vsize = r.hdr[3];
+    // choose the sample
+    vector<size_t> order(n);
+    for (size_t i = 0; i < n; i++) order[i] = i;
+    Random::rand_seed(args.seed);
+    if (args.max_gflop > 0)
+        for (size_t i = n; i > 1; i--)
+            swap(order[i - 1], order[Random::rand_int(0, (int)i)]);
+    vector<size_t> pick;
+    double fl = 0;
+    for (size_t z = 0; z < n; z++) {
+        size_t i = order[z];
+        double f = 2.0 * ((double)r.i32[2][i] * r.i32[3][i] * r.i32[4][i] +
+                          (double)r.i32[10][i] * r.i32[11][i] * r.i32[12][i]);
+        if (args.max_gflop > 0 && fl + f > args.max_gflop * 1e9 && !pick.empty())
+            continue;
+        pick.push_back(i), fl += f;
+    }
+    sort(pick.begin(), pick.end());
+    // arenas referenced by the sample
+    vector<char> used(na, 0);
+    for (size_t i : pick) used[r.i64[1][i]] = used[r.i64[3][i]] = 1;
+    vector<size_t> file_start(na + 1, 0);
+    for (size_t a = 0; a < na; a++) file_start[a + 1] = file_start[a] + r.asz[a];
+    vector<vector<double>> store(na);
+    size_t op_doubles = 0;
+    for (size_t a = 0; a < na; a++)
+        if (used[a]) {
+            store[a].resize(r.asz[a]);
+            op_doubles += r.asz[a];
+            if (r.arenas.size())
+                memcpy(store[a].data(), r.arenas.data() + file_start[a], 8 * r.asz[a]);
+            else {
+                uint64_t s = 88172645463325252ULL + a * 7919 + (uint64_t)args.seed;
+                for (auto &x : store[a]) { // xorshift, uniform in [-1, 1)
+                    s ^= s << 13, s ^= s >> 7, s ^= s << 17;
+                    x = (double)(int64_t)s * (1.0 / 9223372036854775808.0);
+                }
+            }
+        }
+    vector<double> c(csize), v(vsize, 0.0);
+    if (r.c.size()) c = r.c;
+    else { Random::rand_seed(args.seed + 1); Random::fill<double>(c.data(), csize); }
+    shared_ptr<BatchGEMMSeq<double>> seq = make_shared<BatchGEMMSeq<double>>(0, SeqTypes::Tasked);
+    size_t max_work = 0;
+    for (size_t i : pick) {
+        const int m0 = r.i32[2][i], n0 = r.i32[3][i];
+        double *w = (double *)0 + seq->batch[0]->work;
+        seq->batch[0]->xgemm_group(r.i32[0][i], r.i32[1][i], m0, n0, r.i32[4][i], r.f64[0][i],
+                                   r.i32[5][i], r.i32[6][i], r.f64[1][i], r.i32[7][i], 1);
+        seq->batch[0]->xgemm_array((const double *)0 + r.i64[0][i],
+                                   store[r.i64[1][i]].data() + r.i64[2][i], w);
+        seq->batch[1]->xgemm_group(r.i32[8][i], r.i32[9][i], r.i32[10][i], r.i32[11][i], r.i32[12][i],
+                                   r.f64[2][i], r.i32[13][i], r.i32[14][i], r.f64[3][i], r.i32[15][i], 1);
+        seq->batch[1]->xgemm_array(store[r.i64[3][i]].data() + r.i64[4][i], w,
+                                   (double *)0 + r.i64[5][i]);
+        max_work = max(max_work, (size_t)m0 * n0);
+        seq->batch[0]->work += (size_t)m0 * n0, seq->batch[1]->work += (size_t)m0 * n0;
+    }
+    seq->max_work = max_work;
+    GMatrix<double> cm(c.data(), (MKL_INT)csize, 1), vm(v.data(), (MKL_INT)vsize, 1);
+    Timer t;
+    vector<double> times;
+    for (int w = 0; w < args.warmup + args.reps; w++) {
+        memset(v.data(), 0, 8 * vsize);
+        t.get_time();
+        seq->operator()(cm, vm, 1.0);
+        double dt = t.get_time();
+        if (w >= args.warmup) times.push_back(dt);
+    }
+    double tot = 0, chk = 0;
+    for (double x : times) tot += x;
+    for (double x : v) chk += x * x;
+    printf("{\"mode\": \"replay\", \"pairs\": %zu, \"pairs_total\": %zu, \"flops\": %.6e, \"operand_doubles\": %zu, "
+           "\"threads\": %d, \"reps\": %d, \"warmup\": %d, \"seconds_per_matvec\": %.6e, \"tflops\": %.6e, "
+           "\"sigma_norm2\": %.10e}\n",
+           pick.size(), n, fl, op_doubles, args.threads, args.reps, args.warmup, tot / times.size(),
+           fl / (tot / times.size()) * 1e-12, chk);
+    fflush(stdout);
+    _exit(0);
+}
+
 template <typename S> static int run(const Args &args) {
     typedef double FL;
     Random::rand_seed(args.seed);
@@ -505,8 +697,8 @@ template <typename S> static int run(const Args &args) {
 
     shared_ptr<MovingEnvironment<S, FL, FL>> me =
         make_shared<MovingEnvironment<S, FL, FL>>(mpo, mps, mps, "DMRG");
-    if (args.structure_only)
-        me->save_environments = false;
+    // --struct keeps save_environments on: operator storage is outside the
+    // frame stacks, so the per-site scratch files only hold the (small) infos
     me->init_environments(false);
     me->delayed_contraction = OpNamesSet::normal_ops();
     me->cached_contraction = true;
@@ -539,7 +731,10 @@ template <typename S> static int run(const Args &args) {
 
 int main(int argc, char **argv) {
     Args args = parse(argc, argv);
+    setvbuf(stdout, nullptr, _IOLBF, 0);
     // one quantum-number type per binary (halves the 4-minute compile):
     // -DB2REF_S=SU2 -> _ref/b2ref_su2, -DB2REF_S=SZ -> _ref/b2ref_sz
+    if (args.mode == "replay") // --fcidump names the .b2seq(.gz) file here
+        return run_replay(args);
     return run<B2REF_S>(args);
 }

@@ -22,6 +22,7 @@
 #include <stddef.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
@@ -107,6 +108,69 @@ void b2o_seq_matvec(int64_t npairs, const int32_t *ta0, const int32_t *tb0,
                     lda1[i], work, ldb1[i], beta1[i], vts[tid] + c1_off[i],
                     ldc1[i]);
         }
+        free(work);
+    }
+    for (int t = 1; t < nthreads; t++) {
+        for (int64_t j = 0; j < vsize; j++)
+            v[j] += vts[t][j];
+        free(vts[t]);
+    }
+    free(vts);
+}
+
+/* Same replay with every GEMM handed to a Fortran-ABI dgemm (the reference's
+ * xgemm<double>, matrix_functions.hpp:335-351; row-major through the
+ * (B, A) operand swap of single_xgemm, batch_gemm.hpp:219-235).  The caller
+ * passes the dgemm_ entry of the BLAS the reference would link (OpenBLAS here);
+ * used for the CPU baseline timing, on all the host threads it is given. */
+typedef void (*b2o_dgemm_fn)(const char *, const char *, const int *, const int *,
+                             const int *, const double *, const double *,
+                             const int *, const double *, const int *,
+                             const double *, double *, const int *);
+
+void b2o_seq_matvec_blas(b2o_dgemm_fn dgemm, int64_t npairs, const int32_t *ta0,
+                         const int32_t *tb0, const int32_t *m0, const int32_t *n0,
+                         const int32_t *k0, const int32_t *lda0, const int32_t *ldb0,
+                         const int32_t *ldc0, const double *alpha0,
+                         const double *beta0, const int64_t *a0_off,
+                         const double *const *b0, const int32_t *ta1,
+                         const int32_t *tb1, const int32_t *m1, const int32_t *n1,
+                         const int32_t *k1, const int32_t *lda1, const int32_t *ldb1,
+                         const int32_t *ldc1, const double *alpha1,
+                         const double *beta1, const double *const *a1,
+                         const int64_t *c1_off, int64_t max_work, const double *c,
+                         double *v, int64_t vsize, double scale, int nthreads) {
+    if (npairs == 0)
+        return;
+    if (nthreads < 1)
+        nthreads = 1;
+    double **vts = (double **)calloc((size_t)nthreads, sizeof(double *));
+    vts[0] = v;
+    for (int t = 1; t < nthreads; t++)
+        vts[t] = (double *)calloc((size_t)vsize, sizeof(double));
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nthreads)
+#endif
+    {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        double *work = (double *)malloc(sizeof(double) * (size_t)(max_work > 0 ? max_work : 1));
+        double t0 = omp_get_wtime();
+#ifdef _OPENMP
+#pragma omp for schedule(static) nowait
+#endif
+        for (int64_t i = 0; i < npairs; i++) {
+            int m = m0[i], n = n0[i], k = k0[i], la = lda0[i], lb = ldb0[i], lc = ldc0[i];
+            dgemm(tb0[i] ? "t" : "n", ta0[i] ? "t" : "n", &n, &m, &k, &alpha0[i], b0[i], &lb,
+                  c + a0_off[i], &la, &beta0[i], work, &lc);
+            double al = alpha1[i] * scale;
+            m = m1[i], n = n1[i], k = k1[i], la = lda1[i], lb = ldb1[i], lc = ldc1[i];
+            dgemm(tb1[i] ? "t" : "n", ta1[i] ? "t" : "n", &n, &m, &k, &al, work, &lb, a1[i], &la,
+                  &beta1[i], vts[tid] + c1_off[i], &lc);
+        }
+        if (getenv("B2O_DEBUG")) printf("tid %d loop %.4f s\n", tid, omp_get_wtime() - t0);
         free(work);
     }
     for (int t = 1; t < nthreads; t++) {

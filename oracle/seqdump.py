@@ -166,6 +166,54 @@ def replay(d: SeqDump, c: np.ndarray | None = None, scale: float = 1.0,
     return v
 
 
+def _openblas_dgemm():
+    """Address of dgemm_ in the OpenBLAS copied next to the reference binaries
+    (oracle/_ref) or the scipy-bundled one (same library)."""
+    import glob
+    cands = glob.glob(os.path.join(_HERE, "_ref", "libscipy_openblas*.so"))
+    if not cands:
+        import scipy
+        cands = glob.glob(os.path.join(os.path.dirname(scipy.__file__), "..", "scipy.libs", "libscipy_openblas*.so"))
+    L = ctypes.CDLL(cands[0], mode=ctypes.RTLD_GLOBAL)
+    try:
+        L.scipy_openblas_set_num_threads(1)   # one BLAS thread per OpenMP thread, like the reference runs
+    except AttributeError:
+        pass
+    return ctypes.cast(L.scipy_dgemm_, ctypes.c_void_p), L
+
+
+def replay_blas(d: SeqDump, c: np.ndarray | None = None, scale: float = 1.0, nthreads: int = 1,
+                arenas: np.ndarray | None = None, v: np.ndarray | None = None) -> np.ndarray:
+    """sigma = H.c with every GEMM done by OpenBLAS dgemm_, OpenMP over pairs with private
+    sigma replicas - the reference's Tasked executor (batch_gemm.hpp:1613-1688). CPU baseline."""
+    c = np.ascontiguousarray(d.c if c is None else c, dtype=np.float64)
+    ar = np.ascontiguousarray(d.arenas if arenas is None else arenas, dtype=np.float64)
+    b0o, a1o = d.operand_offsets()
+    base = ar.ctypes.data
+    b0 = (base + 8 * b0o).astype(np.uint64)
+    a1 = (base + 8 * a1o).astype(np.uint64)
+    if v is None:
+        v = np.zeros(d.vsize, dtype=np.float64)
+    P = d.p
+    i32, f64, i64 = ctypes.c_int32, ctypes.c_double, ctypes.c_int64
+    vpp = ctypes.POINTER(ctypes.c_void_p)
+    fn, keep = _openblas_dgemm()
+    L = lib()
+    L.b2o_seq_matvec_blas.restype = None
+    L.b2o_seq_matvec_blas(
+        fn, i64(d.npairs),
+        _ptr(P["ta0"], i32), _ptr(P["tb0"], i32), _ptr(P["m0"], i32), _ptr(P["n0"], i32),
+        _ptr(P["k0"], i32), _ptr(P["lda0"], i32), _ptr(P["ldb0"], i32), _ptr(P["ldc0"], i32),
+        _ptr(P["alpha0"], f64), _ptr(P["beta0"], f64), _ptr(P["a0_off"], i64),
+        b0.ctypes.data_as(vpp),
+        _ptr(P["ta1"], i32), _ptr(P["tb1"], i32), _ptr(P["m1"], i32), _ptr(P["n1"], i32),
+        _ptr(P["k1"], i32), _ptr(P["lda1"], i32), _ptr(P["ldb1"], i32), _ptr(P["ldc1"], i32),
+        _ptr(P["alpha1"], f64), _ptr(P["beta1"], f64), a1.ctypes.data_as(vpp),
+        _ptr(P["c1_off"], i64), i64(max(d.max_work, 1)), _ptr(c, f64), _ptr(v, f64),
+        i64(d.vsize), f64(scale), ctypes.c_int(nthreads))
+    return v
+
+
 def replay_numpy(d: SeqDump, c: np.ndarray | None = None, scale: float = 1.0,
                  arenas: np.ndarray | None = None) -> np.ndarray:
     """Independent pure-numpy restatement (small cases only)."""

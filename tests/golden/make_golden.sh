@@ -1,0 +1,14 @@
+#!/bin/bash
+# Regenerates the committed fixtures from the UNMODIFIED reference (oracle/_ref/b2ref_*,
+# built by `make -C oracle ref` from /root/reference/src).  Each file holds the pair list the
+# reference recorded, the operand arenas, a random c, the reference's sigma = H.c, the H_eff
+# diagonal, the initial ket and the reference's Davidson eigenvalue / iteration count.
+# Pair order inside a file depends on the reference's OpenMP merge order; contents do not.
+set -e
+cd "$(dirname "$0")/../../oracle/_ref"
+export OPENBLAS_NUM_THREADS=1
+G=../../tests/golden
+./b2ref_su2 dump --fcidump data/N2.STO3G.FCIDUMP --bond 60 --sweeps 1 --site 4 --threads 4 --noise 1e-6 --out $G/n2_su2_m60_s4.b2seq
+./b2ref_sz  dump --fcidump data/H10.STO6G.R1.8.FCIDUMP --sym sz --bond 40 --sweeps 1 --site 4 --threads 4 --noise 1e-6 --out $G/h10_sz_m40_s4.b2seq
+./b2ref_su2 dump --fcidump data/N2.STO3G.FCIDUMP --bond 30 --sweeps 0 --site 1 --threads 4 --out $G/n2_su2_m30_s1.b2seq
+./b2ref_su2 dump --fcidump data/N2.STO3G.FCIDUMP --bond 30 --sweeps 0 --site 8 --threads 4 --out $G/n2_su2_m30_s8.b2seq

@@ -1,0 +1,209 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against
+(1) the sigma vectors the unmodified reference produced (tests/golden),
+(2) the C oracle on seeded synthetic pair lists, and
+(3) size-independent properties (linearity, symmetry) at larger sizes."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, GOLDEN_FILES
+from oracle import seqdump as sd
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-11  # north_star: H.C result <= 1e-11 relative in FP64
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.mark.parametrize("name", GOLDEN_FILES)
+def test_matvec_matches_reference_sigma(b2g, ctx, name):
+    sf = b2g.load_seqfile(os.path.join(GOLDEN, name))
+    plan = b2g.SeqPlan.from_seqfile(ctx, sf, sf.arenas)
+    v = np.zeros(sf.vsize)
+    plan(sf.c, v)
+    assert rel(v, sf.v_ref) < TOL
+    # accumulate semantics (beta = 1) and scale
+    plan(sf.c, v, -0.5)
+    assert rel(v, 0.5 * sf.v_ref) < 10 * TOL
+    st = plan.stats
+    assert st.pairs == sf.npairs and st.nflop_mnk == sf.nflop_mnk
+    plan.close()
+
+
+def random_pair_list(rng, n_out=6, n_terms=12, maxdim=70, strided=True):
+    """Synthetic pair list in the spirit of the reference's TestRotateTasked
+    (unit_test/test_batch_gemm.cpp:88): random shapes, both transpose flags,
+    strided wavefunction windows, several terms per output window."""
+    from types import SimpleNamespace
+    rows = []
+    c_blocks, v_blocks, arenas = [], [], []
+    coff = voff = aoff = 0
+    for _ in range(n_out):
+        m1, n0 = (int(x) for x in rng.integers(1, maxdim, 2))
+        ldc1 = n0 + (int(rng.integers(0, 5)) if strided else 0)
+        vlen = (m1 - 1) * ldc1 + n0
+        for _ in range(int(rng.integers(1, n_terms))):
+            m0, k0 = (int(x) for x in rng.integers(1, maxdim, 2))
+            lda0 = k0 + (int(rng.integers(0, 5)) if strided else 0)
+            clen = (m0 - 1) * lda0 + k0
+            tb0, ta1 = int(rng.integers(2)), int(rng.integers(2))
+            ldb0 = (k0 if tb0 else n0) + int(rng.integers(0, 3))
+            b0len = ((n0 if tb0 else k0) - 1) * ldb0 + (k0 if tb0 else n0)
+            lda1 = (m1 if ta1 else m0) + int(rng.integers(0, 3))
+            a1len = ((m0 if ta1 else m1) - 1) * lda1 + (m1 if ta1 else m0)
+            rows.append(dict(ta0=0, tb0=tb0, m0=m0, n0=n0, k0=k0, lda0=lda0, ldb0=ldb0, ldc0=n0, ta1=ta1, tb1=0,
+                             m1=m1, n1=n0, k1=m0, lda1=lda1, ldb1=n0, ldc1=ldc1,
+                             alpha0=float(rng.choice([1.0, -1.0, 0.5 ** 0.5])), beta0=0.0,
+                             alpha1=float(rng.standard_normal()), beta1=1.0, a0_off=coff, b0_arena=0, b0_off=aoff,
+                             a1_arena=0, a1_off=aoff + b0len, c1_off=voff, w_off=0))
+            aoff += b0len + a1len
+            coff += clen
+        voff += vlen
+    p = {k: np.array([r[k] for r in rows]) for k in rows[0]}
+    for k in sd.I32_NAMES:
+        p[k] = p[k].astype(np.int32)
+    for k in sd.I64_NAMES:
+        p[k] = p[k].astype(np.int64)
+    mw = int((p["m0"].astype(np.int64) * p["n0"]).max())
+    nf = int((p["m0"].astype(np.int64) * p["n0"] * p["k0"] + p["m1"].astype(np.int64) * p["n1"] * p["k1"]).sum())
+    d = sd.SeqDump(npairs=len(rows), csize=coff, vsize=voff, max_work=mw, nflop_mnk=nf, site=0, bond_dim=0,
+                   n_sites=0, ndav_ref=0, has_eigs=False, e_ref=0.0, const_e=0.0, t_ref_matvec=0.0, conv_thrd=0.0,
+                   arena_sizes=np.array([aoff], dtype=np.int64), p=p)
+    d.arenas = rng.standard_normal(aoff)
+    d.c = rng.standard_normal(coff)
+    return d
+
+
+def as_seqfile(b2g, d):
+    return b2g.SeqFile(npairs=d.npairs, csize=d.csize, vsize=d.vsize, max_work=d.max_work, nflop_mnk=d.nflop_mnk,
+                       site=0, bond_dim=0, n_sites=0, ndav_ref=0, e_ref=0.0, const_e=0.0, conv_thrd=0.0,
+                       arena_sizes=d.arena_sizes, p=d.p, arenas=d.arenas, c=d.c)
+
+
+@pytest.mark.parametrize("seed,maxdim", [(0, 9), (1, 40), (2, 70), (3, 150), (4, 300)])
+def test_matvec_matches_oracle_on_random_lists(b2g, ctx, seed, maxdim):
+    rng = np.random.default_rng(seed)
+    d = random_pair_list(rng, maxdim=maxdim, n_out=5 if maxdim > 100 else 8)
+    want = sd.replay(d, nthreads=4)
+    plan = b2g.SeqPlan.from_seqfile(ctx, as_seqfile(b2g, d), d.arenas)
+    got = np.zeros(d.vsize)
+    plan(d.c, got)
+    assert rel(got, want) < TOL
+    plan.close()
+
+
+def test_empty_and_degenerate_lists(b2g, ctx):
+    rng = np.random.default_rng(5)
+    d = random_pair_list(rng, n_out=1, n_terms=2, maxdim=3)
+    for k in d.p:
+        d.p[k] = d.p[k][:0]
+    d.npairs = 0
+    plan = b2g.SeqPlan.from_seqfile(ctx, as_seqfile(b2g, d), d.arenas)
+    v = np.ones(d.vsize)
+    plan(d.c, v)
+    assert (v == 1).all()
+    plan.close()
+    # 1 x 1 x 1 pairs only
+    d = random_pair_list(rng, n_out=4, n_terms=5, maxdim=2)
+    plan = b2g.SeqPlan.from_seqfile(ctx, as_seqfile(b2g, d), d.arenas)
+    got = np.zeros(d.vsize)
+    plan(d.c, got)
+    assert rel(got, sd.replay(d)) < TOL
+    plan.close()
+
+
+def test_plan_rejects_non_chained_lists(b2g, ctx):
+    d = random_pair_list(np.random.default_rng(6), n_out=2, n_terms=3, maxdim=5)
+    d.p["beta1"] = d.p["beta1"] * 0.0
+    with pytest.raises(b2g.B2GError, match="chained"):
+        b2g.SeqPlan.from_seqfile(ctx, as_seqfile(b2g, d), d.arenas)
+
+
+def test_device_resident_matvec_linearity_and_determinism(b2g, ctx):
+    torch = pytest.importorskip("torch")
+    sf = b2g.load_seqfile(os.path.join(GOLDEN, "h10_sz_m40_s4.b2seq"))
+    dev = torch.device("cuda", 0)
+    ops = torch.from_numpy(sf.arenas).to(dev)
+    plan = b2g.SeqPlan.from_seqfile(ctx, sf, ops.data_ptr(), b2g.OPERANDS_DEVICE)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randn(sf.csize, dtype=torch.float64, generator=g).to(dev)
+    y = torch.randn(sf.csize, dtype=torch.float64, generator=g).to(dev)
+
+    def H(vec):
+        out = torch.zeros(sf.vsize, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        plan.matvec_dev(vec.data_ptr(), out.data_ptr(), 1.0)
+        ctx.synchronize()
+        return out
+
+    hx, hy, hxy = H(x), H(y), H(2.0 * x - 3.0 * y)
+    assert float((hxy - (2.0 * hx - 3.0 * hy)).norm() / hxy.norm()) < TOL
+    # H_eff is symmetric: <y|Hx> = <x|Hy>
+    assert abs(float(y @ hx - x @ hy)) < 1e-10 * float(x.norm() * y.norm())
+    want = sd.replay(sd.load(os.path.join(GOLDEN, "h10_sz_m40_s4.b2seq")), c=x.cpu().numpy())
+    assert rel(hx.cpu().numpy(), want) < TOL
+    plan.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_FILES)
+def test_davidson_matches_reference(b2g, ctx, name):
+    sf = b2g.load_seqfile(os.path.join(GOLDEN, name))
+    plan = b2g.SeqPlan.from_seqfile(ctx, sf, sf.arenas)
+    ket = sf.ket0.copy()
+    e, nd = plan.davidson(sf.diag, ket, conv_thrd=sf.conv_thrd, soft_max_iter=4000)
+    assert abs(e - sf.e_ref) < 1e-9, (e, sf.e_ref)          # energies within 1e-8 Ha (north_star)
+    assert abs(nd - sf.ndav_ref) <= 1, (nd, sf.ndav_ref)
+    v = np.zeros(sf.vsize)
+    plan(ket, v)
+    r = v - e * ket
+    assert abs(np.linalg.norm(ket) - 1) < 1e-12 and r @ r < max(sf.conv_thrd, 1e-12) * 1.01
+    plan.close()
+
+
+def test_dgemm_batch_matches_oracle(b2g, ctx):
+    import ctypes
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(11)
+    dev = torch.device("cuda", 0)
+    G = 40
+    ta, tb = rng.integers(0, 2, G), rng.integers(0, 2, G)
+    m, n, k = rng.integers(1, 40, G), rng.integers(1, 40, G), rng.integers(1, 40, G)
+    m[:8], k[:8], n[:8] = rng.integers(1, 200, 8), 1, 1   # rows-as-AXPY groups (tensor_product lowering)
+    ta[:8] = tb[:8] = 0
+    lda = np.where(ta == 1, m, k) + rng.integers(0, 3, G)
+    ldb = np.where(tb == 1, k, n) + rng.integers(0, 3, G)
+    ldc = n + rng.integers(0, 3, G)
+    gs = rng.integers(1, 4, G)
+    alpha, beta = rng.standard_normal(G), rng.choice([0.0, 1.0, -0.5], G)
+    ha, hb, hc, oa, ob, oc = [], [], [], [], [], []
+    for g in range(G):
+        for _ in range(gs[g]):
+            ha.append(rng.standard_normal(((k[g] if ta[g] else m[g]) - 1) * lda[g] + (m[g] if ta[g] else k[g])))
+            hb.append(rng.standard_normal(((n[g] if tb[g] else k[g]) - 1) * ldb[g] + (k[g] if tb[g] else n[g])))
+            hc.append(rng.standard_normal((m[g] - 1) * ldc[g] + n[g]))
+    flat = lambda lst: (np.concatenate(lst), np.cumsum([0] + [len(x) for x in lst])[:-1])
+    A, oa = flat(ha); B, ob = flat(hb); C, oc = flat(hc)
+    dA, dB, dC = (torch.from_numpy(x).to(dev) for x in (A, B, C))
+    ctx.dgemm_batch(ta, tb, m, n, k, alpha, dA.data_ptr() + 8 * oa, lda, dB.data_ptr() + 8 * ob, ldb, beta,
+                    dC.data_ptr() + 8 * oc, ldc, gs)
+    got = dC.cpu().numpy()
+    want = C.copy()
+    L = sd.lib()
+    i32p = lambda a: np.ascontiguousarray(a, dtype=np.int32).ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+    f64p = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    pp = lambda base, off: (base + 8 * off).astype(np.uint64)
+    pa, pb, pc = pp(A.ctypes.data, oa), pp(B.ctypes.data, ob), pp(want.ctypes.data, oc)
+    vp = ctypes.POINTER(ctypes.c_void_p)
+    keep = [np.ascontiguousarray(x, dtype=np.int32) for x in (ta, tb, m, n, k, lda, ldb, ldc, gs)]
+    al, be = np.ascontiguousarray(alpha), np.ascontiguousarray(beta)
+    L.b2o_dgemm_batch(ctypes.c_int64(G), *(x.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)) for x in keep[:5]),
+                      al.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), pa.ctypes.data_as(vp),
+                      keep[5].ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), pb.ctypes.data_as(vp),
+                      keep[6].ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                      be.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), pc.ctypes.data_as(vp),
+                      keep[7].ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                      keep[8].ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+    assert np.allclose(got, want, rtol=0, atol=1e-11)
