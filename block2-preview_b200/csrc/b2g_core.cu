@@ -8,6 +8,7 @@
 #include "b2g_internal.h"
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -267,8 +268,17 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
     B2G_CUDA(cudaStreamSynchronize(ctx->stream));
     p->stats.upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     p->n_generic = n;
-    p->stats.n_small = 0, p->stats.n_large = n;
+    p->stats.n_small = n, p->stats.n_large = 0;
     p->stats.launches = n > 0 ? 1 : 0;
+    // default route: two-phase DMMA tile engine; B2G_FORCE_GENERIC=1 keeps the one-CTA-per-pair
+    // kernel (the correctness anchor the tiled path is tested against)
+    const char *force = getenv("B2G_FORCE_GENERIC");
+    if (!(force && force[0] == '1') && n > 0) {
+        if (b2g_tiled_build(p)) {
+            b2g_plan_destroy(p);
+            return 1;
+        }
+    }
     *out = p;
     return 0;
 }
@@ -284,6 +294,7 @@ extern "C" int b2g_plan_destroy(b2g_plan *p) {
         cudaFree(p->d_pairs);
     if (p->d_work)
         cudaFree(p->d_work);
+    b2g_tiled_destroy(p->tiled);
     delete p;
     return 0;
 }

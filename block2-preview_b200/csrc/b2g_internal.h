@@ -49,6 +49,7 @@ struct b2g_plan {
     double *d_work = nullptr;     // spill space for W of pairs too large for shared memory
     size_t work_doubles = 0;
     std::vector<B2GPair> h_pairs; // host copy (debug / stats)
+    void *tiled = nullptr;        // b2g::TiledPlan (two-phase DMMA path); null -> generic kernel only
 };
 
 void b2g_set_error(const std::string &msg);
@@ -63,3 +64,7 @@ void b2g_set_error(const std::string &msg);
 
 // kernels (b2g_kernels.cu)
 int b2g_launch_matvec(b2g_plan *plan, const double *c_dev, double *v_dev, double scale);
+// two-phase DMMA path (b2g_tiled.cu)
+int b2g_tiled_build(b2g_plan *plan);
+int b2g_tiled_launch(b2g_plan *plan, const double *c_dev, double *v_dev, double scale);
+void b2g_tiled_destroy(void *tiled);

@@ -54,6 +54,8 @@ int b2g_launch_matvec(b2g_plan *p, const double *c_dev, double *v_dev, double sc
     b2g_context *ctx = p->ctx;
     if (p->npairs == 0)
         return 0;
+    if (p->tiled)
+        return b2g_tiled_launch(p, c_dev, v_dev, scale);
     if (p->n_generic > 0) {
         const int grid = (int)std::min<int64_t>(p->n_generic, (int64_t)ctx->sm_count * 8);
         const size_t need = (p->max_work > GEN_SMEM_W) ? (size_t)p->max_work * grid : 0;

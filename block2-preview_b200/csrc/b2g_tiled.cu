@@ -1,0 +1,449 @@
+// b2g_tiled.cu — the two-phase DMMA replay of the H.C pair list (see b2g_tiled.cuh).
+#include "b2g_tiled.cuh"
+#include <algorithm>
+#include <cstdlib>
+#include <map>
+#include <numeric>
+#include <tuple>
+
+namespace b2g {
+
+// ----------------------------------------------------------------------------
+// Shared pipelined main loop.  Src provides:
+//   int  steps() const          number of BK-deep stages of this unit
+//   void issue(double*, double*) cp.async the next stage into (As, Bs) and advance
+// ----------------------------------------------------------------------------
+template <class Cfg, bool A_KC, bool B_KC, class Src>
+__device__ __forceinline__ void mainloop(Src &src, double *smem, double (&acc)[Cfg::MI][Cfg::NI][2], int wm0, int wn0,
+                                         int mi_n, int ni_n) {
+    double *As = smem, *Bs = smem + Cfg::STAGES * Cfg::A_STAGE;
+    const int total = src.steps();
+#pragma unroll
+    for (int s = 0; s < Cfg::STAGES - 1; s++) {
+        if (s < total)
+            src.issue(As + s * Cfg::A_STAGE, Bs + s * Cfg::B_STAGE);
+        cp_async_commit();
+    }
+    for (int step = 0; step < total; step++) {
+        cp_async_wait<Cfg::STAGES - 2>();
+        __syncthreads();
+        const int nxt = step + Cfg::STAGES - 1;
+        if (nxt < total) {
+            const int st = nxt % Cfg::STAGES;
+            src.issue(As + st * Cfg::A_STAGE, Bs + st * Cfg::B_STAGE);
+        }
+        cp_async_commit();
+        const int cur = step % Cfg::STAGES;
+        compute_stage<Cfg, A_KC, B_KC>(As + cur * Cfg::A_STAGE, Bs + cur * Cfg::B_STAGE, acc, wm0, wn0, mi_n, ni_n);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+}
+
+template <class Cfg> __device__ __forceinline__ void warp_origin(int &wm0, int &wn0) {
+    const int warp = threadIdx.x >> 5;
+    wm0 = (warp / Cfg::WN) * Cfg::WTM;
+    wn0 = (warp % Cfg::WN) * Cfg::WTN;
+}
+
+__device__ __forceinline__ int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// ------------------------------ phase 1 -------------------------------------
+template <class Cfg, bool B_KC> struct P1Src {
+    const double *a, *b;
+    int lda, ldb, m_valid, n_valid, k_left, nsteps;
+    __device__ int steps() const { return nsteps; }
+    __device__ void issue(double *As, double *Bs) {
+        load_tile<Cfg::BM, Cfg::THREADS, true>(As, a, lda, m_valid, k_left);
+        load_tile<Cfg::BN, Cfg::THREADS, B_KC>(Bs, b, ldb, n_valid, k_left);
+        a += BK;
+        b += B_KC ? BK : (size_t)BK * ldb;
+        k_left -= BK;
+    }
+};
+
+template <class Cfg, bool B_KC>
+__global__ void __launch_bounds__(Cfg::THREADS)
+phase1_kernel(const P1Pair *__restrict__ pairs, const Unit *__restrict__ units, int n_units,
+              unsigned int *__restrict__ counter, const double *__restrict__ c, double *__restrict__ wbuf) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_unit;
+    int wm0, wn0;
+    warp_origin<Cfg>(wm0, wn0);
+    const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
+    while (true) {
+        if (threadIdx.x == 0)
+            s_unit = (int)atomicAdd(counter, 1u);
+        __syncthreads();
+        const int u = s_unit;
+        __syncthreads();
+        if (u >= n_units)
+            break;
+        const Unit un = units[u];
+        const P1Pair p = pairs[un.idx];
+        const int row0 = un.tm * Cfg::BM, col0 = un.tn * Cfg::BN;
+        P1Src<Cfg, B_KC> src;
+        src.a = c + p.a_off + (size_t)row0 * p.lda;
+        src.b = B_KC ? p.b0 + (size_t)col0 * p.ldb : p.b0 + col0;
+        src.lda = p.lda, src.ldb = p.ldb;
+        src.m_valid = p.m0 - row0, src.n_valid = p.n0 - col0;
+        src.k_left = p.k0, src.nsteps = (p.k0 + BK - 1) / BK;
+        const int mi_n = clampi((src.m_valid - wm0 + 7) / 8, 0, Cfg::MI);
+        const int ni_n = clampi((src.n_valid - wn0 + 7) / 8, 0, Cfg::NI);
+        double acc[Cfg::MI][Cfg::NI][2];
+#pragma unroll
+        for (int mi = 0; mi < Cfg::MI; mi++)
+#pragma unroll
+            for (int ni = 0; ni < Cfg::NI; ni++)
+                acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        mainloop<Cfg, true, B_KC>(src, smem, acc, wm0, wn0, mi_n, ni_n);
+        double *w = wbuf + p.w_off;
+#pragma unroll
+        for (int mi = 0; mi < Cfg::MI; mi++)
+#pragma unroll
+            for (int ni = 0; ni < Cfg::NI; ni++) {
+                const int r = row0 + wm0 + mi * 8 + lr, cc = col0 + wn0 + ni * 8 + lc * 2;
+                if (mi < mi_n && ni < ni_n && r < p.m0) {
+                    if (cc < p.n0)
+                        w[(size_t)r * p.n0 + cc] = p.alpha * acc[mi][ni][0];
+                    if (cc + 1 < p.n0)
+                        w[(size_t)r * p.n0 + cc + 1] = p.alpha * acc[mi][ni][1];
+                }
+            }
+    }
+}
+
+// ------------------------------ phase 2 -------------------------------------
+template <class Cfg, bool A_KC> struct P2Src {
+    const P2Seg *seg, *seg_end;
+    const double *wbuf;
+    const double *a, *b;
+    int lda, n0, row0, col0, m_valid, n_valid, k_left, nsteps;
+    __device__ int steps() const { return nsteps; }
+    __device__ void open() {
+        const P2Seg s = *seg;
+        lda = s.lda;
+        a = A_KC ? s.a1 + (size_t)row0 * lda : s.a1 + row0;
+        b = wbuf + s.w_off + col0;
+        k_left = s.klen;
+    }
+    __device__ void issue(double *As, double *Bs) {
+        load_tile<Cfg::BM, Cfg::THREADS, A_KC>(As, a, lda, m_valid, k_left);
+        load_tile<Cfg::BN, Cfg::THREADS, false>(Bs, b, n0, n_valid, k_left);
+        k_left -= BK;
+        if (k_left > 0) {
+            a += A_KC ? BK : (size_t)BK * lda;
+            b += (size_t)BK * n0;
+        } else if (++seg < seg_end)
+            open();
+    }
+};
+
+template <class Cfg, bool A_KC>
+__global__ void __launch_bounds__(Cfg::THREADS)
+phase2_kernel(const P2Window *__restrict__ wins, const P2Seg *__restrict__ segs, const Unit *__restrict__ units,
+              int n_units, unsigned int *__restrict__ counter, const double *__restrict__ wbuf,
+              double *__restrict__ v, double scale) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_unit;
+    int wm0, wn0;
+    warp_origin<Cfg>(wm0, wn0);
+    const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
+    while (true) {
+        if (threadIdx.x == 0)
+            s_unit = (int)atomicAdd(counter, 1u);
+        __syncthreads();
+        const int u = s_unit;
+        __syncthreads();
+        if (u >= n_units)
+            break;
+        const Unit un = units[u];
+        const P2Window win = wins[un.idx];
+        P2Src<Cfg, A_KC> src;
+        src.seg = segs + un.seg_begin, src.seg_end = segs + un.seg_end, src.wbuf = wbuf;
+        src.n0 = win.n0, src.row0 = un.tm * Cfg::BM, src.col0 = un.tn * Cfg::BN;
+        src.m_valid = win.m1 - src.row0, src.n_valid = win.n0 - src.col0;
+        int ns = 0;
+        for (const P2Seg *s = src.seg; s < src.seg_end; s++)
+            ns += (s->klen + BK - 1) / BK;
+        src.nsteps = ns;
+        src.open();
+        const int mi_n = clampi((src.m_valid - wm0 + 7) / 8, 0, Cfg::MI);
+        const int ni_n = clampi((src.n_valid - wn0 + 7) / 8, 0, Cfg::NI);
+        double acc[Cfg::MI][Cfg::NI][2];
+#pragma unroll
+        for (int mi = 0; mi < Cfg::MI; mi++)
+#pragma unroll
+            for (int ni = 0; ni < Cfg::NI; ni++)
+                acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        mainloop<Cfg, A_KC, false>(src, smem, acc, wm0, wn0, mi_n, ni_n);
+        double *out = v + win.c_off;
+#pragma unroll
+        for (int mi = 0; mi < Cfg::MI; mi++)
+#pragma unroll
+            for (int ni = 0; ni < Cfg::NI; ni++) {
+                const int r = src.row0 + wm0 + mi * 8 + lr, cc = src.col0 + wn0 + ni * 8 + lc * 2;
+                if (mi < mi_n && ni < ni_n && r < win.m1) {
+                    if (cc < win.n0)
+                        atomicAdd(out + (size_t)r * win.ldc + cc, scale * acc[mi][ni][0]);
+                    if (cc + 1 < win.n0)
+                        atomicAdd(out + (size_t)r * win.ldc + cc + 1, scale * acc[mi][ni][1]);
+                }
+            }
+    }
+}
+
+// ----------------------------------------------------------------------------
+// Host side: tile configurations, unit lists, launches
+// ----------------------------------------------------------------------------
+using CfgL = TileCfg<128, 64, 4, 2, 3>;  // large sectors: 8 warps, 32x32 warp tiles
+using CfgM = TileCfg<64, 64, 2, 2, 3>;   // medium: 4 warps
+using CfgS = TileCfg<128, 8, 8, 1, 4>;   // skinny sigma windows (n0 <= 8): 8 warps, 16x8 warp tiles
+constexpr int NCFG = 3;
+
+struct CfgInfo {
+    int bm, bn, threads, smem;
+};
+static const CfgInfo kCfg[NCFG] = {{CfgL::BM, CfgL::BN, CfgL::THREADS, CfgL::SMEM_BYTES},
+                                   {CfgM::BM, CfgM::BN, CfgM::THREADS, CfgM::SMEM_BYTES},
+                                   {CfgS::BM, CfgS::BN, CfgS::THREADS, CfgS::SMEM_BYTES}};
+
+static inline int pick_cfg(int m, int n) {
+    if (n <= 8)
+        return 2;
+    // padded-area cost with a mild preference for the bigger tile (better operand reuse)
+    auto cost = [&](int c) {
+        const double tiles = (double)((m + kCfg[c].bm - 1) / kCfg[c].bm) * ((n + kCfg[c].bn - 1) / kCfg[c].bn);
+        return tiles * kCfg[c].bm * kCfg[c].bn * (c == 0 ? 1.0 : 1.08);
+    };
+    return cost(0) <= cost(1) ? 0 : 1;
+}
+
+struct LaunchGroup { // one kernel launch: units of one (phase, cfg, layout)
+    int phase, cfg, layout;
+    Unit *d_units = nullptr;
+    int n_units = 0;
+};
+
+struct TiledPlan {
+    P1Pair *d_p1 = nullptr;
+    P2Window *d_win = nullptr;
+    P2Seg *d_seg = nullptr;
+    double *d_wbuf = nullptr;
+    unsigned int *d_counters = nullptr;
+    size_t wbuf_doubles = 0;
+    std::vector<LaunchGroup> groups;
+    std::vector<void *> to_free;
+};
+
+template <class Cfg, bool L> static int launch_p1(const LaunchGroup &g, const TiledPlan &tp, b2g_context *ctx,
+                                                  unsigned int *counter, const double *c) {
+    auto kern = phase1_kernel<Cfg, L>;
+    static bool attr = false;
+    if (!attr) {
+        B2G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr = true;
+    }
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::THREADS, Cfg::SMEM_BYTES);
+    const int grid = std::min(g.n_units, ctx->sm_count * std::max(per_sm, 1));
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(tp.d_p1, g.d_units, g.n_units, counter, c, tp.d_wbuf);
+    return 0;
+}
+template <class Cfg, bool L> static int launch_p2(const LaunchGroup &g, const TiledPlan &tp, b2g_context *ctx,
+                                                  unsigned int *counter, double *v, double scale) {
+    auto kern = phase2_kernel<Cfg, L>;
+    static bool attr = false;
+    if (!attr) {
+        B2G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr = true;
+    }
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::THREADS, Cfg::SMEM_BYTES);
+    const int grid = std::min(g.n_units, ctx->sm_count * std::max(per_sm, 1));
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(tp.d_win, tp.d_seg, g.d_units, g.n_units, counter,
+                                                                tp.d_wbuf, v, scale);
+    return 0;
+}
+
+} // namespace b2g
+
+using namespace b2g;
+
+void b2g_tiled_destroy(void *h) {
+    TiledPlan *tp = (TiledPlan *)h;
+    if (!tp)
+        return;
+    for (void *p : tp->to_free)
+        cudaFree(p);
+    delete tp;
+}
+
+// Build the two-phase plan from the (device-pointer) pair list of the generic plan.
+int b2g_tiled_build(b2g_plan *p) {
+    b2g_context *ctx = p->ctx;
+    const std::vector<B2GPair> &hp = p->h_pairs;
+    const size_t n = hp.size();
+    TiledPlan *tp = new TiledPlan();
+    p->tiled = tp;
+    if (n == 0)
+        return 0;
+    const char *env_kc = getenv("B2G_KCHUNK");
+    const int64_t kchunk = env_kc ? atoll(env_kc) : 4096;
+
+    // ---- phase 1 descriptors + W workspace layout
+    std::vector<P1Pair> p1(n);
+    size_t woff = 0;
+    for (size_t i = 0; i < n; i++) {
+        const B2GPair &q = hp[i];
+        P1Pair &d = p1[i];
+        d.b0 = q.b0, d.w_off = (int64_t)woff, d.alpha = q.alpha0 * q.alpha1;
+        d.a_off = q.a0_off, d.lda = q.lda0, d.ldb = q.ldb0;
+        d.m0 = q.m0, d.n0 = q.n0, d.k0 = q.k0, d.tb0 = (q.flags & B2G_F_TB0) ? 1 : 0, d.pad = 0;
+        woff += (size_t)q.m0 * q.n0;
+    }
+    tp->wbuf_doubles = woff;
+
+    // ---- windows: pairs that accumulate into the same sigma window
+    std::map<std::tuple<int, int, int, int>, int> wid;
+    std::vector<P2Window> wins;
+    std::vector<std::vector<size_t>> wpairs[2]; // [layout][window] -> pair indices
+    for (size_t i = 0; i < n; i++) {
+        const B2GPair &q = hp[i];
+        auto key = std::make_tuple(q.c1_off, q.m1, q.n0, q.ldc1);
+        auto it = wid.find(key);
+        int w;
+        if (it == wid.end()) {
+            w = (int)wins.size();
+            wid[key] = w;
+            wins.push_back(P2Window{q.c1_off, q.ldc1, q.m1, q.n0});
+            wpairs[0].emplace_back(), wpairs[1].emplace_back();
+        } else
+            w = it->second;
+        wpairs[(q.flags & B2G_F_TA1) ? 1 : 0][w].push_back(i);
+    }
+
+    // ---- units
+    struct HostUnit {
+        Unit u;
+        double cost;
+    };
+    std::map<std::tuple<int, int, int>, std::vector<HostUnit>> groups; // (phase, cfg, layout)
+    for (size_t i = 0; i < n; i++) {
+        const B2GPair &q = hp[i];
+        if (q.m0 == 0 || q.n0 == 0)
+            continue;
+        const int c = pick_cfg(q.m0, q.n0);
+        auto &g = groups[std::make_tuple(1, c, p1[i].tb0)];
+        for (int tm = 0; tm < (q.m0 + kCfg[c].bm - 1) / kCfg[c].bm; tm++)
+            for (int tn = 0; tn < (q.n0 + kCfg[c].bn - 1) / kCfg[c].bn; tn++)
+                g.push_back(HostUnit{Unit{(int)i, tm, tn, 0, 0}, (double)kCfg[c].bm * kCfg[c].bn * (q.k0 + 2 * BK)});
+    }
+    std::vector<P2Seg> segs;
+    for (int lay = 0; lay < 2; lay++)
+        for (size_t w = 0; w < wins.size(); w++) {
+            auto &lst = wpairs[lay][w];
+            if (lst.empty() || wins[w].m1 == 0 || wins[w].n0 == 0)
+                continue;
+            // neighbours share the operator block when possible (L2 reuse across K-chunks)
+            std::stable_sort(lst.begin(), lst.end(), [&hp](size_t x, size_t y) { return hp[x].a1 < hp[y].a1; });
+            const int c = pick_cfg(wins[w].m1, wins[w].n0);
+            auto &g = groups[std::make_tuple(2, c, lay)];
+            size_t s0 = segs.size();
+            int64_t ksum = 0;
+            auto flush = [&](size_t s1) {
+                if (s1 == s0)
+                    return;
+                for (int tm = 0; tm < (wins[w].m1 + kCfg[c].bm - 1) / kCfg[c].bm; tm++)
+                    for (int tn = 0; tn < (wins[w].n0 + kCfg[c].bn - 1) / kCfg[c].bn; tn++)
+                        g.push_back(HostUnit{Unit{(int)w, tm, tn, (int)s0, (int)s1},
+                                             (double)kCfg[c].bm * kCfg[c].bn * (double)(ksum + 2 * BK)});
+                s0 = s1, ksum = 0;
+            };
+            for (size_t idx : lst) {
+                const B2GPair &q = hp[idx];
+                if (q.m0 == 0)
+                    continue;
+                segs.push_back(P2Seg{q.a1, p1[idx].w_off, q.lda1, q.m0});
+                ksum += q.m0;
+                if (ksum >= kchunk)
+                    flush(segs.size());
+            }
+            flush(segs.size());
+        }
+
+    // ---- upload
+    auto upload = [&](const void *src, size_t bytes, void **dst) -> int {
+        B2G_CUDA(cudaMalloc(dst, std::max<size_t>(bytes, 16)));
+        tp->to_free.push_back(*dst);
+        if (bytes)
+            B2G_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return 0;
+    };
+    if (upload(p1.data(), p1.size() * sizeof(P1Pair), (void **)&tp->d_p1))
+        return 1;
+    if (upload(wins.data(), wins.size() * sizeof(P2Window), (void **)&tp->d_win))
+        return 1;
+    if (upload(segs.data(), segs.size() * sizeof(P2Seg), (void **)&tp->d_seg))
+        return 1;
+    B2G_CUDA(cudaMalloc((void **)&tp->d_wbuf, std::max<size_t>(tp->wbuf_doubles, 2) * sizeof(double)));
+    tp->to_free.push_back(tp->d_wbuf);
+    std::vector<std::vector<Unit>> keep; // host copies must outlive the async copies
+    for (auto &kv : groups) {
+        auto &hu = kv.second;
+        if (hu.empty())
+            continue;
+        std::stable_sort(hu.begin(), hu.end(), [](const HostUnit &x, const HostUnit &y) { return x.cost > y.cost; });
+        keep.emplace_back(hu.size());
+        for (size_t i = 0; i < hu.size(); i++)
+            keep.back()[i] = hu[i].u;
+        LaunchGroup g;
+        g.phase = std::get<0>(kv.first), g.cfg = std::get<1>(kv.first), g.layout = std::get<2>(kv.first);
+        g.n_units = (int)hu.size();
+        if (upload(keep.back().data(), hu.size() * sizeof(Unit), (void **)&g.d_units))
+            return 1;
+        tp->groups.push_back(g);
+    }
+    std::stable_sort(tp->groups.begin(), tp->groups.end(),
+                     [](const LaunchGroup &a, const LaunchGroup &b) { return a.phase < b.phase; });
+    B2G_CUDA(cudaMalloc((void **)&tp->d_counters, sizeof(unsigned int) * 32));
+    tp->to_free.push_back(tp->d_counters);
+    B2G_CUDA(cudaStreamSynchronize(ctx->stream));
+    p->stats.launches = (int64_t)tp->groups.size() + 1;
+    p->stats.n_large = (int64_t)n, p->stats.n_small = 0;
+    return 0;
+}
+
+int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double scale) {
+    TiledPlan *tp = (TiledPlan *)p->tiled;
+    b2g_context *ctx = p->ctx;
+    if (!tp || tp->groups.empty())
+        return 0;
+    B2G_CUDA(cudaMemsetAsync(tp->d_counters, 0, sizeof(unsigned int) * 32, ctx->stream));
+    int gi = 0;
+    for (const LaunchGroup &g : tp->groups) {
+        unsigned int *counter = tp->d_counters + gi++;
+        int rc = 0;
+#define B2G_DISPATCH(PH, CFG, LAY, CALL)                                                \
+    if (g.phase == PH && g.cfg == CFG && g.layout == LAY)                               \
+        rc = CALL;
+        B2G_DISPATCH(1, 0, 0, (launch_p1<CfgL, false>(g, *tp, ctx, counter, c_dev)))
+        B2G_DISPATCH(1, 0, 1, (launch_p1<CfgL, true>(g, *tp, ctx, counter, c_dev)))
+        B2G_DISPATCH(1, 1, 0, (launch_p1<CfgM, false>(g, *tp, ctx, counter, c_dev)))
+        B2G_DISPATCH(1, 1, 1, (launch_p1<CfgM, true>(g, *tp, ctx, counter, c_dev)))
+        B2G_DISPATCH(1, 2, 0, (launch_p1<CfgS, false>(g, *tp, ctx, counter, c_dev)))
+        B2G_DISPATCH(1, 2, 1, (launch_p1<CfgS, true>(g, *tp, ctx, counter, c_dev)))
+        B2G_DISPATCH(2, 0, 0, (launch_p2<CfgL, true>(g, *tp, ctx, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 0, 1, (launch_p2<CfgL, false>(g, *tp, ctx, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 1, 0, (launch_p2<CfgM, true>(g, *tp, ctx, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 1, 1, (launch_p2<CfgM, false>(g, *tp, ctx, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 2, 0, (launch_p2<CfgS, true>(g, *tp, ctx, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 2, 1, (launch_p2<CfgS, false>(g, *tp, ctx, counter, v_dev, scale)))
+#undef B2G_DISPATCH
+        if (rc)
+            return rc;
+        ctx->launches++;
+    }
+    B2G_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -95,6 +95,18 @@ def test_matvec_matches_oracle_on_random_lists(b2g, ctx, seed, maxdim):
     plan.close()
 
 
+def test_generic_kernel_route_matches_oracle(b2g, ctx, monkeypatch):
+    """B2G_FORCE_GENERIC=1 keeps the one-CTA-per-pair kernel: the anchor of the tiled path."""
+    monkeypatch.setenv("B2G_FORCE_GENERIC", "1")
+    d = random_pair_list(np.random.default_rng(21), maxdim=90, n_out=6)
+    plan = b2g.SeqPlan.from_seqfile(ctx, as_seqfile(b2g, d), d.arenas)
+    assert plan.stats.launches == 1
+    got = np.zeros(d.vsize)
+    plan(d.c, got)
+    assert rel(got, sd.replay(d, nthreads=4)) < TOL
+    plan.close()
+
+
 def test_empty_and_degenerate_lists(b2g, ctx):
     rng = np.random.default_rng(5)
     d = random_pair_list(rng, n_out=1, n_terms=2, maxdim=3)
