@@ -63,7 +63,7 @@ template <class Cfg, bool B_KC> struct P1Src {
 };
 
 template <class Cfg, bool B_KC>
-__global__ void __launch_bounds__(Cfg::THREADS)
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
 phase1_kernel(const P1Pair *__restrict__ pairs, const Unit *__restrict__ units, int n_units,
               unsigned int *__restrict__ counter, const double *__restrict__ c, double *__restrict__ wbuf) {
     extern __shared__ __align__(16) double smem[];
@@ -81,7 +81,7 @@ phase1_kernel(const P1Pair *__restrict__ pairs, const Unit *__restrict__ units, 
             break;
         const Unit un = units[u];
         const P1Pair p = pairs[un.idx];
-        const int row0 = un.tm * Cfg::BM, col0 = un.tn * Cfg::BN;
+        const int row0 = un.row0, col0 = un.col0;
         P1Src<Cfg, B_KC> src;
         src.a = c + p.a_off + (size_t)row0 * p.lda;
         src.b = B_KC ? p.b0 + (size_t)col0 * p.ldb : p.b0 + col0;
@@ -140,7 +140,7 @@ template <class Cfg, bool A_KC> struct P2Src {
 };
 
 template <class Cfg, bool A_KC>
-__global__ void __launch_bounds__(Cfg::THREADS)
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
 phase2_kernel(const P2Window *__restrict__ wins, const P2Seg *__restrict__ segs, const Unit *__restrict__ units,
               int n_units, unsigned int *__restrict__ counter, const double *__restrict__ wbuf,
               double *__restrict__ v, double scale) {
@@ -161,7 +161,7 @@ phase2_kernel(const P2Window *__restrict__ wins, const P2Seg *__restrict__ segs,
         const P2Window win = wins[un.idx];
         P2Src<Cfg, A_KC> src;
         src.seg = segs + un.seg_begin, src.seg_end = segs + un.seg_end, src.wbuf = wbuf;
-        src.n0 = win.n0, src.row0 = un.tm * Cfg::BM, src.col0 = un.tn * Cfg::BN;
+        src.n0 = win.n0, src.row0 = un.row0, src.col0 = un.col0;
         src.m_valid = win.m1 - src.row0, src.n_valid = win.n0 - src.col0;
         int ns = 0;
         for (const P2Seg *s = src.seg; s < src.seg_end; s++)
@@ -196,27 +196,59 @@ phase2_kernel(const P2Window *__restrict__ wins, const P2Seg *__restrict__ segs,
 // ----------------------------------------------------------------------------
 // Host side: tile configurations, unit lists, launches
 // ----------------------------------------------------------------------------
-using CfgL = TileCfg<128, 64, 4, 2, 3>;  // large sectors: 8 warps, 32x32 warp tiles
-using CfgM = TileCfg<64, 64, 2, 2, 3>;   // medium: 4 warps
-using CfgS = TileCfg<128, 8, 8, 1, 4>;   // skinny sigma windows (n0 <= 8): 8 warps, 16x8 warp tiles
-constexpr int NCFG = 3;
+// Tile configurations.  An output matrix is cut into 128-row tiles plus one 64-row strip for the
+// remainder, and into 64-column tiles plus 16- or 8-column strips for the remainder, so padding
+// waste stays at the 8-element granularity of the DMMA blocks.
+using Cfg0 = TileCfg<128, 64, 4, 2, 3, 2>; // 8 warps, 32x32 warp tiles (bulk of large sectors)
+using Cfg1 = TileCfg<64, 64, 2, 2, 3>;  // 4 warps, 32x32
+using Cfg2 = TileCfg<128, 16, 8, 1, 4>; // 8 warps, 16x16 (column remainders)
+using Cfg3 = TileCfg<64, 16, 4, 1, 4>;  // 4 warps, 16x16
+using Cfg4 = TileCfg<128, 8, 8, 1, 4>;  // 8 warps, 16x8  (skinny sigma windows, n0 <= 8)
+using Cfg5 = TileCfg<64, 8, 4, 1, 4>;   // 4 warps, 16x8
+constexpr int NCFG = 6;
 
 struct CfgInfo {
     int bm, bn, threads, smem;
 };
-static const CfgInfo kCfg[NCFG] = {{CfgL::BM, CfgL::BN, CfgL::THREADS, CfgL::SMEM_BYTES},
-                                   {CfgM::BM, CfgM::BN, CfgM::THREADS, CfgM::SMEM_BYTES},
-                                   {CfgS::BM, CfgS::BN, CfgS::THREADS, CfgS::SMEM_BYTES}};
+static const CfgInfo kCfg[NCFG] = {{Cfg0::BM, Cfg0::BN, Cfg0::THREADS, Cfg0::SMEM_BYTES},
+                                   {Cfg1::BM, Cfg1::BN, Cfg1::THREADS, Cfg1::SMEM_BYTES},
+                                   {Cfg2::BM, Cfg2::BN, Cfg2::THREADS, Cfg2::SMEM_BYTES},
+                                   {Cfg3::BM, Cfg3::BN, Cfg3::THREADS, Cfg3::SMEM_BYTES},
+                                   {Cfg4::BM, Cfg4::BN, Cfg4::THREADS, Cfg4::SMEM_BYTES},
+                                   {Cfg5::BM, Cfg5::BN, Cfg5::THREADS, Cfg5::SMEM_BYTES}};
 
-static inline int pick_cfg(int m, int n) {
-    if (n <= 8)
-        return 2;
-    // padded-area cost with a mild preference for the bigger tile (better operand reuse)
-    auto cost = [&](int c) {
-        const double tiles = (double)((m + kCfg[c].bm - 1) / kCfg[c].bm) * ((n + kCfg[c].bn - 1) / kCfg[c].bn);
-        return tiles * kCfg[c].bm * kCfg[c].bn * (c == 0 ? 1.0 : 1.08);
-    };
-    return cost(0) <= cost(1) ? 0 : 1;
+static inline int cfg_of(int bm, int bn) { return (bn == 64 ? 0 : bn == 16 ? 2 : 4) + (bm == 128 ? 0 : 1); }
+
+struct Strip {
+    int origin, tile; // first element, tile extent class
+};
+// rows: 128-row tiles, then a 64-row strip when the remainder fits one
+static std::vector<Strip> split_rows(int m) {
+    std::vector<Strip> out;
+    int r = 0;
+    while (m - r > 64) {
+        out.push_back(Strip{r, 128});
+        r += 128;
+    }
+    if (m - r > 0)
+        out.push_back(Strip{r, 64});
+    return out;
+}
+// columns: 64-column tiles, then 16- / 8-column strips for the remainder
+static std::vector<Strip> split_cols(int n) {
+    std::vector<Strip> out;
+    int c = 0;
+    while (n - c > 32) {
+        out.push_back(Strip{c, 64});
+        c += 64;
+    }
+    while (n - c > 8) {
+        out.push_back(Strip{c, 16});
+        c += 16;
+    }
+    if (n - c > 0)
+        out.push_back(Strip{c, 8});
+    return out;
 }
 
 struct LaunchGroup { // one kernel launch: units of one (phase, cfg, layout)
@@ -333,11 +365,12 @@ int b2g_tiled_build(b2g_plan *p) {
         const B2GPair &q = hp[i];
         if (q.m0 == 0 || q.n0 == 0)
             continue;
-        const int c = pick_cfg(q.m0, q.n0);
-        auto &g = groups[std::make_tuple(1, c, p1[i].tb0)];
-        for (int tm = 0; tm < (q.m0 + kCfg[c].bm - 1) / kCfg[c].bm; tm++)
-            for (int tn = 0; tn < (q.n0 + kCfg[c].bn - 1) / kCfg[c].bn; tn++)
-                g.push_back(HostUnit{Unit{(int)i, tm, tn, 0, 0}, (double)kCfg[c].bm * kCfg[c].bn * (q.k0 + 2 * BK)});
+        for (const Strip &rs : split_rows(q.m0))
+            for (const Strip &cs : split_cols(q.n0)) {
+                const int c = cfg_of(rs.tile, cs.tile);
+                groups[std::make_tuple(1, c, p1[i].tb0)].push_back(
+                    HostUnit{Unit{(int)i, rs.origin, cs.origin, 0, 0}, (double)rs.tile * cs.tile * (q.k0 + 2 * BK)});
+            }
     }
     std::vector<P2Seg> segs;
     for (int lay = 0; lay < 2; lay++)
@@ -347,17 +380,17 @@ int b2g_tiled_build(b2g_plan *p) {
                 continue;
             // neighbours share the operator block when possible (L2 reuse across K-chunks)
             std::stable_sort(lst.begin(), lst.end(), [&hp](size_t x, size_t y) { return hp[x].a1 < hp[y].a1; });
-            const int c = pick_cfg(wins[w].m1, wins[w].n0);
-            auto &g = groups[std::make_tuple(2, c, lay)];
+            const std::vector<Strip> rsv = split_rows(wins[w].m1), csv = split_cols(wins[w].n0);
             size_t s0 = segs.size();
             int64_t ksum = 0;
             auto flush = [&](size_t s1) {
                 if (s1 == s0)
                     return;
-                for (int tm = 0; tm < (wins[w].m1 + kCfg[c].bm - 1) / kCfg[c].bm; tm++)
-                    for (int tn = 0; tn < (wins[w].n0 + kCfg[c].bn - 1) / kCfg[c].bn; tn++)
-                        g.push_back(HostUnit{Unit{(int)w, tm, tn, (int)s0, (int)s1},
-                                             (double)kCfg[c].bm * kCfg[c].bn * (double)(ksum + 2 * BK)});
+                for (const Strip &rs : rsv)
+                    for (const Strip &cs : csv)
+                        groups[std::make_tuple(2, cfg_of(rs.tile, cs.tile), lay)].push_back(
+                            HostUnit{Unit{(int)w, rs.origin, cs.origin, (int)s0, (int)s1},
+                                     (double)rs.tile * cs.tile * (double)(ksum + 2 * BK)});
                 s0 = s1, ksum = 0;
             };
             for (size_t idx : lst) {
@@ -406,7 +439,7 @@ int b2g_tiled_build(b2g_plan *p) {
     }
     std::stable_sort(tp->groups.begin(), tp->groups.end(),
                      [](const LaunchGroup &a, const LaunchGroup &b) { return a.phase < b.phase; });
-    B2G_CUDA(cudaMalloc((void **)&tp->d_counters, sizeof(unsigned int) * 32));
+    B2G_CUDA(cudaMalloc((void **)&tp->d_counters, sizeof(unsigned int) * 64));
     tp->to_free.push_back(tp->d_counters);
     B2G_CUDA(cudaStreamSynchronize(ctx->stream));
     p->stats.launches = (int64_t)tp->groups.size() + 1;
@@ -419,7 +452,7 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
     b2g_context *ctx = p->ctx;
     if (!tp || tp->groups.empty())
         return 0;
-    B2G_CUDA(cudaMemsetAsync(tp->d_counters, 0, sizeof(unsigned int) * 32, ctx->stream));
+    B2G_CUDA(cudaMemsetAsync(tp->d_counters, 0, sizeof(unsigned int) * 64, ctx->stream));
     int gi = 0;
     for (const LaunchGroup &g : tp->groups) {
         unsigned int *counter = tp->d_counters + gi++;
@@ -427,18 +460,30 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
 #define B2G_DISPATCH(PH, CFG, LAY, CALL)                                                \
     if (g.phase == PH && g.cfg == CFG && g.layout == LAY)                               \
         rc = CALL;
-        B2G_DISPATCH(1, 0, 0, (launch_p1<CfgL, false>(g, *tp, ctx, counter, c_dev)))
-        B2G_DISPATCH(1, 0, 1, (launch_p1<CfgL, true>(g, *tp, ctx, counter, c_dev)))
-        B2G_DISPATCH(1, 1, 0, (launch_p1<CfgM, false>(g, *tp, ctx, counter, c_dev)))
-        B2G_DISPATCH(1, 1, 1, (launch_p1<CfgM, true>(g, *tp, ctx, counter, c_dev)))
-        B2G_DISPATCH(1, 2, 0, (launch_p1<CfgS, false>(g, *tp, ctx, counter, c_dev)))
-        B2G_DISPATCH(1, 2, 1, (launch_p1<CfgS, true>(g, *tp, ctx, counter, c_dev)))
-        B2G_DISPATCH(2, 0, 0, (launch_p2<CfgL, true>(g, *tp, ctx, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 0, 1, (launch_p2<CfgL, false>(g, *tp, ctx, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 1, 0, (launch_p2<CfgM, true>(g, *tp, ctx, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 1, 1, (launch_p2<CfgM, false>(g, *tp, ctx, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 2, 0, (launch_p2<CfgS, true>(g, *tp, ctx, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 2, 1, (launch_p2<CfgS, false>(g, *tp, ctx, counter, v_dev, scale)))
+        B2G_DISPATCH(1, 0, 0, (launch_p1<Cfg0, false>(g, *tp, ctx, counter, c_dev)))
+        B2G_DISPATCH(1, 0, 1, (launch_p1<Cfg0, true>(g, *tp, ctx, counter, c_dev)))
+        B2G_DISPATCH(1, 1, 0, (launch_p1<Cfg1, false>(g, *tp, ctx, counter, c_dev)))
+        B2G_DISPATCH(1, 1, 1, (launch_p1<Cfg1, true>(g, *tp, ctx, counter, c_dev)))
+        B2G_DISPATCH(1, 2, 0, (launch_p1<Cfg2, false>(g, *tp, ctx, counter, c_dev)))
+        B2G_DISPATCH(1, 2, 1, (launch_p1<Cfg2, true>(g, *tp, ctx, counter, c_dev)))
+        B2G_DISPATCH(1, 3, 0, (launch_p1<Cfg3, false>(g, *tp, ctx, counter, c_dev)))
+        B2G_DISPATCH(1, 3, 1, (launch_p1<Cfg3, true>(g, *tp, ctx, counter, c_dev)))
+        B2G_DISPATCH(1, 4, 0, (launch_p1<Cfg4, false>(g, *tp, ctx, counter, c_dev)))
+        B2G_DISPATCH(1, 4, 1, (launch_p1<Cfg4, true>(g, *tp, ctx, counter, c_dev)))
+        B2G_DISPATCH(1, 5, 0, (launch_p1<Cfg5, false>(g, *tp, ctx, counter, c_dev)))
+        B2G_DISPATCH(1, 5, 1, (launch_p1<Cfg5, true>(g, *tp, ctx, counter, c_dev)))
+        B2G_DISPATCH(2, 0, 0, (launch_p2<Cfg0, true>(g, *tp, ctx, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 0, 1, (launch_p2<Cfg0, false>(g, *tp, ctx, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 1, 0, (launch_p2<Cfg1, true>(g, *tp, ctx, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 1, 1, (launch_p2<Cfg1, false>(g, *tp, ctx, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 2, 0, (launch_p2<Cfg2, true>(g, *tp, ctx, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 2, 1, (launch_p2<Cfg2, false>(g, *tp, ctx, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 3, 0, (launch_p2<Cfg3, true>(g, *tp, ctx, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 3, 1, (launch_p2<Cfg3, false>(g, *tp, ctx, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 4, 0, (launch_p2<Cfg4, true>(g, *tp, ctx, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 4, 1, (launch_p2<Cfg4, false>(g, *tp, ctx, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 5, 0, (launch_p2<Cfg5, true>(g, *tp, ctx, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 5, 1, (launch_p2<Cfg5, false>(g, *tp, ctx, counter, v_dev, scale)))
 #undef B2G_DISPATCH
         if (rc)
             return rc;

@@ -49,7 +49,7 @@ struct P2Seg {           // phase 2: one K-segment (= one pair)
 
 struct Unit {            // one CTA-tile x K-chunk
     int32_t idx;         // phase 1: pair index; phase 2: window index
-    int32_t tm, tn;      // tile coordinates
+    int32_t row0, col0;  // origin of the tile inside the output matrix (elements)
     int32_t seg_begin, seg_end; // phase 2: segment range (phase 1: unused)
 };
 
@@ -69,8 +69,9 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 }
 
 // Tile configuration: CTA tile BM x BN, WM x WN warps, each warp (BM/WM) x (BN/WN).
-template <int BM_, int BN_, int WM_, int WN_, int STAGES_> struct TileCfg {
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int MINB_ = 1> struct TileCfg {
     static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_;
+    static constexpr int MINB = MINB_; // resident CTAs per SM the register budget is capped for
     static constexpr int THREADS = WM * WN * 32;
     static constexpr int WTM = BM / WM, WTN = BN / WN; // warp tile
     static constexpr int MI = WTM / 8, NI = WTN / 8;   // 8x8 DMMA blocks per warp

@@ -1,0 +1,196 @@
+// b2g_adapter.hpp — the reference-side binding of libb2g.so.
+//
+// This header is compiled TOGETHER WITH block2's own headers (it is what a block2
+// maintainer would add) and talks to the CUDA library only through
+// the C ABI in include/b2g.h.  It installs the GPU executor behind the reference's own
+// operator surface, without touching the MPO builder, the quantum-number bookkeeping or
+// the sweep driver:
+//
+//   GPUTensorFunctions<S>  : TensorFunctions<S,double>   (core/tensor_functions.hpp:47)
+//       operator()(b, c, scale)  -> b2g_seq_matvec     (was: opf->seq->operator()(b, c, scale), :59-62)
+//       tensor_product_multiply  -> reference recording, then marks the device plan stale
+//                                   (this is the call EffectiveHamiltonian::precompute() makes,
+//                                    dmrg/effective_hamiltonian.hpp:226-246)
+//       copy()                   -> keeps the dynamic type (EffectiveHamiltonian stores ptf->copy(), :137)
+//   GPUDMRG<S>             : DMRG<S,double,double>        (dmrg/sweep_algorithm.hpp:71)
+//       two_dot_eigs_and_perturb (virtual, :1183) -> H_eff built by the reference,
+//                                   Davidson run device-resident by b2g_davidson
+//
+// The recording itself (OperatorFunctions::tensor_product_multiply /
+// three_tensor_product_multiply -> BatchGEMMSeq::rotate / three_rotate) is the
+// reference's, unchanged, so sector indexing and batch bookkeeping are bit-exact by
+// construction; only the executor of the recorded list changes.
+#pragma once
+#include "b2g.h"
+#include "block2_core.hpp"
+#include "block2_dmrg.hpp"
+#include <atomic>
+#include <stdexcept>
+
+namespace b2g_host {
+
+using namespace block2;
+
+struct Session {
+    b2g_context *ctx = nullptr;
+    std::atomic<bool> recording{false};
+    double t_plan = 0, t_matvec = 0;
+    size_t n_plan = 0, n_matvec = 0;
+    explicit Session(int device = 0) {
+        if (b2g_context_create(device, &ctx) != 0)
+            throw std::runtime_error(std::string("b2g_context_create: ") + b2g_last_error());
+    }
+    ~Session() { b2g_context_destroy(ctx); }
+    Session(const Session &) = delete;
+};
+
+// View of a BatchGEMM<double> as the C-ABI batch descriptor (same arrays, no copies).
+inline b2g_batch as_b2g_batch(const BatchGEMM<double> &b) {
+    static_assert(sizeof(CBLAS_TRANSPOSE) == sizeof(int32_t), "CBLAS_TRANSPOSE must be int-sized");
+    static_assert(sizeof(MKL_INT) == sizeof(int32_t), "LP64 MKL_INT expected");
+    for (size_t i = 0; i < b.gp.size(); i++)
+        if (b.gp[i] != 1)
+            throw std::runtime_error("b2g: grouped entries (gp != 1) are not part of the H.C replay list");
+    if (b.acidxs.size() != 0)
+        throw std::runtime_error("b2g: acidxs-tagged lists (partial expectation / complex) are not supported");
+    b2g_batch r;
+    r.count = (int64_t)b.gp.size();
+    r.ta = (const int32_t *)b.ta.data(), r.tb = (const int32_t *)b.tb.data();
+    r.m = b.m.data(), r.n = b.n.data(), r.k = b.k.data();
+    r.lda = b.lda.data(), r.ldb = b.ldb.data(), r.ldc = b.ldc.data();
+    r.alpha = b.alpha.data(), r.beta = b.beta.data();
+    r.a = b.a.data(), r.b = b.b.data(), r.c = b.c.data();
+    return r;
+}
+
+template <typename S> struct GPUTensorFunctions : TensorFunctions<S, double> {
+    typedef double FL;
+    using TensorFunctions<S, FL>::opf;
+    shared_ptr<Session> session;
+    mutable b2g_plan *plan = nullptr;
+    mutable bool stale = true;
+    mutable size_t csize = 0, vsize = 0;
+    GPUTensorFunctions(const shared_ptr<OperatorFunctions<S, FL>> &opf, const shared_ptr<Session> &session)
+        : TensorFunctions<S, FL>(opf), session(session) {}
+    ~GPUTensorFunctions() override { drop(); }
+    void drop() const {
+        if (plan != nullptr)
+            b2g_plan_destroy(plan);
+        plan = nullptr;
+    }
+    shared_ptr<TensorFunctions<S, FL>> copy() const override {
+        return make_shared<GPUTensorFunctions<S>>(opf->copy(), session);
+    }
+    // Top-level recording call of precompute(): run the reference's recorder, then invalidate
+    // the device plan.  Nested calls (the per-term calls parallel_reduce makes on copies)
+    // see `recording` set and only record.
+    void tensor_product_multiply(const shared_ptr<OpExpr<S>> &expr, const shared_ptr<OpExpr<S>> &xexpr,
+                                 const shared_ptr<OperatorTensor<S, FL>> &lopt,
+                                 const shared_ptr<OperatorTensor<S, FL>> &ropt,
+                                 const shared_ptr<SparseMatrix<S, FL>> &cmat,
+                                 const shared_ptr<SparseMatrix<S, FL>> &vmat, S opdq,
+                                 bool all_reduce) const override {
+        const bool top = !session->recording.exchange(true);
+        TensorFunctions<S, FL>::tensor_product_multiply(expr, xexpr, lopt, ropt, cmat, vmat, opdq, all_reduce);
+        if (top) {
+            session->recording = false;
+            if (cmat->data == nullptr && (opf->seq->mode & SeqTypes::Tasked)) {
+                drop();
+                stale = true;
+                csize = cmat->total_memory, vsize = vmat->total_memory;
+            }
+        }
+    }
+    void build_plan() const {
+        Timer t;
+        t.get_time();
+        drop();
+        auto &seq = opf->seq;
+        b2g_batch b0 = as_b2g_batch(*seq->batch[0]), b1 = as_b2g_batch(*seq->batch[1]);
+        if (b2g_plan_create(session->ctx, &b0, &b1, (int64_t)seq->max_work, (int64_t)csize, (int64_t)vsize,
+                            B2G_OPERANDS_HOST, &plan) != 0)
+            throw std::runtime_error(std::string("b2g_plan_create: ") + b2g_last_error());
+        stale = false;
+        session->t_plan += t.get_time(), session->n_plan++;
+    }
+    b2g_plan *get_plan() const {
+        if (stale || plan == nullptr)
+            build_plan();
+        return plan;
+    }
+    // sigma += scale * H.c  (host buffers, same contract as BatchGEMMSeq::operator())
+    void operator()(const GMatrix<FL> &b, const GMatrix<FL> &c, FL scale = 1.0) override {
+        if (!(opf->seq->mode & SeqTypes::Tasked))
+            throw std::runtime_error("b2g: GPUTensorFunctions needs SeqTypes::Tasked (or SimpleTasked)");
+        if (opf->seq->batch[0]->gp.size() == 0)
+            return;
+        Timer t;
+        t.get_time();
+        if (b2g_seq_matvec(get_plan(), b.data, c.data, scale) != 0)
+            throw std::runtime_error(std::string("b2g_seq_matvec: ") + b2g_last_error());
+        // keep the reference's FLOP accounting (batch_gemm.hpp:1687-1688)
+        opf->seq->cumulative_nflop += opf->seq->batch[0]->nflop + opf->seq->batch[1]->nflop;
+        session->t_matvec += t.get_time(), session->n_matvec++;
+    }
+};
+
+// DMRG with the Davidson solver device-resident. Everything that is not the plain
+// ground-state path falls through to the reference implementation.
+template <typename S> struct GPUDMRG : DMRG<S, double, double> {
+    typedef DMRG<S, double, double> Base;
+    typedef typename Base::FPLS FPLS;
+    using Base::me;
+    bool device_davidson = true;
+    GPUDMRG(const shared_ptr<MovingEnvironment<S, double, double>> &me, const vector<ubond_t> &bond_dims,
+            const vector<double> &noises)
+        : Base(me, bond_dims, noises) {}
+    tuple<FPLS, int, size_t, double>
+    two_dot_eigs_and_perturb(const bool forward, const int i, const double davidson_conv_thrd, const double noise,
+                             shared_ptr<SparseMatrixGroup<S, double>> &pket) override {
+        const bool plain = device_davidson && !this->state_specific && this->projection_weights.size() == 0 &&
+                           this->metric_me == nullptr && this->context_ket == nullptr && me->para_rule == nullptr &&
+                           this->davidson_type == DavidsonTypes::Normal && this->eff_kernel == nullptr &&
+                           !((this->noise_type & NoiseTypes::Perturbative) && noise != 0);
+        if (!plain)
+            return Base::two_dot_eigs_and_perturb(forward, i, davidson_conv_thrd, noise, pket);
+        Timer t;
+        t.get_time();
+        shared_ptr<EffectiveHamiltonian<S, double>> h_eff =
+            me->eff_ham(FuseTypes::FuseLR, forward, true, me->bra->tensors[i], me->ket->tensors[i]);
+        this->sweep_max_eff_ham_size = max(this->sweep_max_eff_ham_size, h_eff->op->get_total_memory());
+        this->sweep_max_eff_wfn_size = max(this->sweep_max_eff_wfn_size, (size_t)h_eff->ket->total_memory);
+        this->teff += t.get_time();
+        auto gtf = dynamic_pointer_cast<GPUTensorFunctions<S>>(h_eff->tf);
+        if (gtf == nullptr)
+            throw std::runtime_error("b2g: GPUDMRG needs mpo->tf to be a GPUTensorFunctions");
+        frame_<double>()->activate(0);
+        h_eff->precompute();
+        double e = 0;
+        int ndav = 0;
+        size_t nflop = 0;
+        if (h_eff->tf->opf->seq->batch[0]->gp.size() != 0) {
+            if (b2g_davidson(gtf->get_plan(), h_eff->diag->data, h_eff->ket->data, davidson_conv_thrd,
+                             this->davidson_rel_conv_thrd, this->davidson_max_iter, this->davidson_soft_max_iter,
+                             this->davidson_def_min_size, this->davidson_def_max_size, &e, &ndav) != 0)
+                throw std::runtime_error(std::string("b2g_davidson: ") + b2g_last_error());
+            nflop = (size_t)ndav * (h_eff->tf->opf->seq->batch[0]->nflop + h_eff->tf->opf->seq->batch[1]->nflop);
+        }
+        h_eff->post_precompute();
+        gtf->drop();
+        double tdav = t.get_time();
+        this->teig += tdav;
+        h_eff->deallocate();
+        return make_tuple((FPLS)e, ndav, nflop, tdav);
+    }
+};
+
+// Install the executor on an MPO (after simplification): mpo->tf is the only seam
+// MovingEnvironment and EffectiveHamiltonian use (moving_environment.hpp:329,362,2173).
+template <typename S>
+inline shared_ptr<Session> install(const shared_ptr<MPO<S, double>> &mpo, int device = 0) {
+    shared_ptr<Session> session = make_shared<Session>(device);
+    mpo->tf = make_shared<GPUTensorFunctions<S>>(mpo->tf->opf, session);
+    return session;
+}
+
+} // namespace b2g_host
