@@ -13,9 +13,9 @@ namespace b2g {
 //   int  steps() const          number of BK-deep stages of this unit
 //   void issue(double*, double*) cp.async the next stage into (As, Bs) and advance
 // ----------------------------------------------------------------------------
-template <class Cfg, bool A_KC, bool B_KC, class Src>
-__device__ __forceinline__ void mainloop(Src &src, double *smem, double (&acc)[Cfg::MI][Cfg::NI][2], int wm0, int wn0,
-                                         int mi_n, int ni_n) {
+template <class Cfg, bool A_KC, bool B_KC, bool FULL, class Src>
+__device__ __forceinline__ void mainloop_impl(Src &src, double *smem, double (&acc)[Cfg::MI][Cfg::NI][2], int wm0,
+                                              int wn0, int mi_n, int ni_n) {
     double *As = smem, *Bs = smem + Cfg::STAGES * Cfg::A_STAGE;
     const int total = src.steps();
 #pragma unroll
@@ -34,10 +34,21 @@ __device__ __forceinline__ void mainloop(Src &src, double *smem, double (&acc)[C
         }
         cp_async_commit();
         const int cur = step % Cfg::STAGES;
-        compute_stage<Cfg, A_KC, B_KC>(As + cur * Cfg::A_STAGE, Bs + cur * Cfg::B_STAGE, acc, wm0, wn0, mi_n, ni_n);
+        compute_stage<Cfg, A_KC, B_KC, FULL>(As + cur * Cfg::A_STAGE, Bs + cur * Cfg::B_STAGE, acc, wm0, wn0, mi_n,
+                                             ni_n);
     }
     cp_async_wait<0>();
     __syncthreads();
+}
+
+// The guard-free body is chosen per CTA (block-uniform: every warp of an interior tile is full).
+template <class Cfg, bool A_KC, bool B_KC, class Src>
+__device__ __forceinline__ void mainloop(Src &src, double *smem, double (&acc)[Cfg::MI][Cfg::NI][2], int wm0, int wn0,
+                                         int mi_n, int ni_n, bool cta_full) {
+    if (cta_full)
+        mainloop_impl<Cfg, A_KC, B_KC, true>(src, smem, acc, wm0, wn0, mi_n, ni_n);
+    else
+        mainloop_impl<Cfg, A_KC, B_KC, false>(src, smem, acc, wm0, wn0, mi_n, ni_n);
 }
 
 template <class Cfg> __device__ __forceinline__ void warp_origin(int &wm0, int &wn0) {
@@ -96,7 +107,7 @@ phase1_kernel(const P1Pair *__restrict__ pairs, const Unit *__restrict__ units, 
 #pragma unroll
             for (int ni = 0; ni < Cfg::NI; ni++)
                 acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-        mainloop<Cfg, true, B_KC>(src, smem, acc, wm0, wn0, mi_n, ni_n);
+        mainloop<Cfg, true, B_KC>(src, smem, acc, wm0, wn0, mi_n, ni_n, src.m_valid >= Cfg::BM && src.n_valid >= Cfg::BN);
         double *w = wbuf + p.w_off;
 #pragma unroll
         for (int mi = 0; mi < Cfg::MI; mi++)
@@ -176,7 +187,7 @@ phase2_kernel(const P2Window *__restrict__ wins, const P2Seg *__restrict__ segs,
 #pragma unroll
             for (int ni = 0; ni < Cfg::NI; ni++)
                 acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-        mainloop<Cfg, A_KC, false>(src, smem, acc, wm0, wn0, mi_n, ni_n);
+        mainloop<Cfg, A_KC, false>(src, smem, acc, wm0, wn0, mi_n, ni_n, src.m_valid >= Cfg::BM && src.n_valid >= Cfg::BN);
         double *out = v + win.c_off;
 #pragma unroll
         for (int mi = 0; mi < Cfg::MI; mi++)
@@ -200,7 +211,7 @@ phase2_kernel(const P2Window *__restrict__ wins, const P2Seg *__restrict__ segs,
 // remainder, and into 64-column tiles plus 16- or 8-column strips for the remainder, so padding
 // waste stays at the 8-element granularity of the DMMA blocks.
 using Cfg0 = TileCfg<128, 64, 4, 2, 3, 2>; // 8 warps, 32x32 warp tiles (bulk of large sectors)
-using Cfg1 = TileCfg<64, 64, 2, 2, 3>;  // 4 warps, 32x32
+using Cfg1 = TileCfg<64, 64, 2, 2, 3, 3>; // 4 warps, 32x32
 using Cfg2 = TileCfg<128, 16, 8, 1, 4>; // 8 warps, 16x16 (column remainders)
 using Cfg3 = TileCfg<64, 16, 4, 1, 4>;  // 4 warps, 16x16
 using Cfg4 = TileCfg<128, 8, 8, 1, 4>;  // 8 warps, 16x8  (skinny sigma windows, n0 <= 8)

@@ -127,29 +127,31 @@ __device__ __forceinline__ void load_tile(double *smem, const double *g, int ld,
 
 // One BK-deep stage of DMMAs for this warp. mi_n / ni_n: number of 8-row / 8-col blocks of the
 // warp tile that intersect the valid output (warp-uniform), so edge tiles skip dead blocks.
-template <class Cfg, bool A_KC, bool B_KC>
+// FULL = true: the warp tile lies entirely inside the output (no guards, no reconvergence
+// points around the DMMAs - the common case); FULL = false: edge tiles.
+template <class Cfg, bool A_KC, bool B_KC, bool FULL>
 __device__ __forceinline__ void compute_stage(const double *As, const double *Bs, double (&acc)[Cfg::MI][Cfg::NI][2],
                                               int wm0, int wn0, int mi_n, int ni_n) {
     const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
+    const double *ap = A_KC ? As + (wm0 + lr) * KC_LD + lc : As + lc * (Cfg::BM + 4) + wm0 + lr;
+    const double *bp = B_KC ? Bs + (wn0 + lr) * KC_LD + lc : Bs + lc * (Cfg::BN + 4) + wn0 + lr;
 #pragma unroll
     for (int kk = 0; kk < BK / 4; kk++) {
         double a[Cfg::MI], b[Cfg::NI];
 #pragma unroll
         for (int mi = 0; mi < Cfg::MI; mi++)
-            if (mi < mi_n)
-                a[mi] = A_KC ? As[(wm0 + mi * 8 + lr) * KC_LD + kk * 4 + lc]
-                             : As[(kk * 4 + lc) * (Cfg::BM + 4) + wm0 + mi * 8 + lr];
+            if (FULL || mi < mi_n)
+                a[mi] = A_KC ? ap[mi * 8 * KC_LD + kk * 4] : ap[kk * 4 * (Cfg::BM + 4) + mi * 8];
 #pragma unroll
         for (int ni = 0; ni < Cfg::NI; ni++)
-            if (ni < ni_n)
-                b[ni] = B_KC ? Bs[(wn0 + ni * 8 + lr) * KC_LD + kk * 4 + lc]
-                             : Bs[(kk * 4 + lc) * (Cfg::BN + 4) + wn0 + ni * 8 + lr];
+            if (FULL || ni < ni_n)
+                b[ni] = B_KC ? bp[ni * 8 * KC_LD + kk * 4] : bp[kk * 4 * (Cfg::BN + 4) + ni * 8];
 #pragma unroll
         for (int mi = 0; mi < Cfg::MI; mi++)
-            if (mi < mi_n) {
+            if (FULL || mi < mi_n) {
 #pragma unroll
                 for (int ni = 0; ni < Cfg::NI; ni++)
-                    if (ni < ni_n)
+                    if (FULL || ni < ni_n)
                         dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
             }
     }
