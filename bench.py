@@ -218,6 +218,19 @@ def run_b200(args) -> None:
         ctx.synchronize()
         kms += k0.elapsed_time(k1)
     kms /= args.steps
+    # per-launch durations (CUDA events between the launches, on the library's stream), averaged
+    prof = {}
+    for _ in range(max(args.steps, 3)):
+        with torch.cuda.stream(stream):
+            v.zero_()
+        ctx.synchronize()
+        for name, gfl, gms, units in plan.profile(c.data_ptr(), v.data_ptr(), 1.0):
+            e = prof.setdefault(name, [gfl, 0.0, units, 0])
+            e[1] += gms
+            e[3] += 1
+    kernels = [{"name": k, "gflop": e[0] * 1e-9, "ms": e[1] / e[3], "units": e[2],
+                "tflops": e[0] / (e[1] / e[3] * 1e-3) * 1e-12 if e[1] > 0 else 0.0} for k, e in prof.items()]
+    kernels.sort(key=lambda x: -x["ms"])
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     fl = torch.tensor([sf.flops], dtype=torch.float64, device=dev)
     if world > 1:
@@ -248,6 +261,8 @@ def run_b200(args) -> None:
     if rank == 0:
         st = plan.stats
         kernel_tflops = sf.flops / (kms * 1e-3) * 1e-12
+        dom = kernels[0] if kernels else {"name": "matvec", "tflops": kernel_tflops, "ms": kms, "gflop": sf.flops * 1e-9}
+        dom_share = dom["ms"] / sum(k["ms"] for k in kernels) if kernels else 1.0
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -267,13 +282,18 @@ def run_b200(args) -> None:
             "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": 8 * sf.csize,
                     "d2h_bytes_per_step": 8 * sf.vsize, "path_check_rel": chk},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "achieved": kernel_tflops, "peak": peak, "unit": "TFLOP/s",
-                         "frac": kernel_tflops / peak if peak else None, "traffic": None,
-                         "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (FP64 tensor pipe); "
-                                        "MEASURED_PEAKS.json has no FP64 entry",
-                         "kernel_ms": kms, "algorithmic_bytes": alg_bytes,
+            "roofline": {"bound": "tensor", "kernel": dom["name"], "achieved": dom["tflops"], "peak": peak,
+                         "unit": "TFLOP/s", "frac": dom["tflops"] / peak if peak else None, "traffic": None,
+                         "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (FP64 tensor pipe, of measured); "
+                                        "MEASURED_PEAKS.json has no FP64 entry; DMMA issue ceiling 37.05 TFLOP/s "
+                                        "(profiles/r01_fp64_probe.json)",
+                         "kernel_ms": dom["ms"], "kernel_gflop": dom["gflop"], "share_of_step": dom_share,
+                         "whole_matvec": {"achieved": kernel_tflops, "frac": kernel_tflops / peak if peak else None,
+                                          "ms": kms},
+                         "algorithmic_bytes": alg_bytes,
                          "hbm_gbs_if_streamed_once": alg_bytes / (kms * 1e-3) * 1e-9,
                          "hbm_peak_gbs": peaks.get("hbm_gbs")},
+            "kernels": kernels,
             "plan": {"pairs": int(st.pairs), "arenas": int(st.arenas), "launches_per_matvec": int(st.launches),
                      "n_small": int(st.n_small), "n_large": int(st.n_large)},
         }

@@ -34,7 +34,7 @@ EXPORTS = [
     "b2g_last_error", "b2g_device_count", "b2g_context_create", "b2g_context_destroy",
     "b2g_context_launches", "b2g_context_stream", "b2g_context_synchronize",
     "b2g_plan_create", "b2g_plan_destroy", "b2g_plan_get_stats", "b2g_seq_matvec",
-    "b2g_seq_matvec_dev", "b2g_dgemm_batch", "b2g_davidson", "b2g_comm_unique_id",
+    "b2g_seq_matvec_dev", "b2g_plan_profile", "b2g_dgemm_batch", "b2g_davidson", "b2g_comm_unique_id",
     "b2g_comm_init", "b2g_comm_destroy", "b2g_allreduce_sum", "b2g_malloc", "b2g_free",
     "b2g_memcpy_h2d", "b2g_memcpy_d2h", "b2g_memset_zero",
 ]
@@ -57,6 +57,10 @@ class PlanStats(ctypes.Structure):
     _fields_ = [("pairs", c_int64), ("csize", c_int64), ("vsize", c_int64), ("nflop_mnk", c_int64),
                 ("operand_doubles", c_int64), ("arenas", c_int64), ("launches", c_int64),
                 ("n_small", c_int64), ("n_large", c_int64), ("upload_seconds", c_double)]
+
+
+class KernelStat(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 64), ("flops", c_double), ("ms", c_double), ("units", c_int64)]
 
 
 _lib = None
@@ -84,6 +88,8 @@ def lib() -> ctypes.CDLL:
         L.b2g_plan_get_stats.argtypes = [c_void_p, POINTER(PlanStats)]
         L.b2g_seq_matvec.argtypes = [c_void_p, c_void_p, c_void_p, c_double]
         L.b2g_seq_matvec_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_double]
+        L.b2g_plan_profile.argtypes = [c_void_p, c_void_p, c_void_p, c_double, POINTER(KernelStat), c_int,
+                                       POINTER(c_int)]
         L.b2g_dgemm_batch.argtypes = [c_void_p, c_int64] + [c_void_p] * 13
         L.b2g_davidson.argtypes = [c_void_p, c_void_p, c_void_p, c_double, c_double, c_int, c_int, c_int, c_int,
                                    POINTER(c_double), POINTER(c_int)]
@@ -239,6 +245,14 @@ class SeqPlan:
     def matvec_dev(self, c_ptr: int, v_ptr: int, scale: float = 1.0) -> None:
         """Device-resident c and sigma; asynchronous on the context stream."""
         _check(lib().b2g_seq_matvec_dev(self._h, c_void_p(c_ptr), c_void_p(v_ptr), scale), "b2g_seq_matvec_dev")
+
+    def profile(self, c_ptr: int, v_ptr: int, scale: float = 1.0):
+        """One matvec with CUDA events between the launches: [(name, flops, ms, units), ...]."""
+        buf = (KernelStat * 64)()
+        n = c_int()
+        _check(lib().b2g_plan_profile(self._h, c_void_p(c_ptr), c_void_p(v_ptr), scale, buf, 64, byref(n)),
+               "b2g_plan_profile")
+        return [(buf[i].name.decode(), buf[i].flops, buf[i].ms, buf[i].units) for i in range(n.value)]
 
     def davidson(self, diag: np.ndarray, ket: np.ndarray, conv_thrd: float = 5e-6, rel_conv_thrd: float = 0.0,
                  max_iter: int = 5000, soft_max_iter: int = -1, deflation_min_size: int = 2,

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 
 static thread_local std::string g_err;
 void b2g_set_error(const std::string &msg) { g_err = msg; }
@@ -49,7 +50,58 @@ extern "C" int b2g_context_create(int device, b2g_context **out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     B2G_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    // keep freed blocks in the stream-ordered pool: one plan per site and one Davidson call per
+    // site would otherwise pay cudaMalloc/cudaFree every time
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    ctx->up_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     *out = ctx;
+    return 0;
+}
+
+int b2g_dmalloc(b2g_context *ctx, void **ptr, size_t bytes) {
+    B2G_CUDA(cudaMallocAsync(ptr, std::max<size_t>(bytes, 16), ctx->stream));
+    return 0;
+}
+void b2g_dfree(b2g_context *ctx, void *ptr) {
+    if (ptr)
+        cudaFreeAsync(ptr, ctx->stream);
+}
+
+int b2g_upload(b2g_context *ctx, void *dst, const void *src, size_t bytes) {
+    constexpr size_t CH = (size_t)32 << 20;
+    if (bytes < ((size_t)1 << 20)) { // small ranges: the driver's own staging is fine
+        B2G_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return 0;
+    }
+    if (!ctx->h_up[0]) {
+        for (int i = 0; i < 2; i++) {
+            B2G_CUDA(cudaMallocHost(&ctx->h_up[i], CH));
+            B2G_CUDA(cudaEventCreateWithFlags(&ctx->up_done[i], cudaEventDisableTiming));
+        }
+        ctx->up_bytes = CH;
+    }
+    int buf = 0;
+    for (size_t off = 0; off < bytes; off += CH, buf ^= 1) {
+        const size_t len = std::min(CH, bytes - off);
+        B2G_CUDA(cudaEventSynchronize(ctx->up_done[buf])); // previous DMA out of this buffer finished
+        const int nt = ctx->up_threads;
+        const size_t slice = (len / nt + 4095) & ~(size_t)4095;
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) {
+            const size_t lo = std::min(len, slice * t), hi = std::min(len, slice * (t + 1));
+            if (hi > lo)
+                th.emplace_back([=]() { memcpy((char *)ctx->h_up[buf] + lo, (const char *)src + off + lo, hi - lo); });
+        }
+        memcpy(ctx->h_up[buf], (const char *)src + off, std::min(len, slice));
+        for (auto &x : th)
+            x.join();
+        B2G_CUDA(cudaMemcpyAsync((char *)dst + off, ctx->h_up[buf], len, cudaMemcpyHostToDevice, ctx->stream));
+        B2G_CUDA(cudaEventRecord(ctx->up_done[buf], ctx->stream));
+    }
     return 0;
 }
 
@@ -61,6 +113,12 @@ extern "C" int b2g_context_destroy(b2g_context *ctx) {
         b2g_comm_destroy(ctx);
     if (ctx->h_stage)
         cudaFreeHost(ctx->h_stage);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->h_up[i])
+            cudaFreeHost(ctx->h_up[i]);
+        if (ctx->up_done[i])
+            cudaEventDestroy(ctx->up_done[i]);
+    }
     if (ctx->d_c)
         cudaFree(ctx->d_c);
     if (ctx->d_v)
@@ -220,18 +278,15 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
 
     auto t0 = std::chrono::steady_clock::now();
     if (operand_space == B2G_OPERANDS_HOST && total > 0) {
-        if (cudaMalloc(&p->d_operands, total * sizeof(double)) != cudaSuccess) {
+        if (b2g_dmalloc(ctx, (void **)&p->d_operands, total * sizeof(double)) != 0) {
             b2g_set_error("b2g_plan_create: cudaMalloc of " + std::to_string(total * 8) + " operand bytes failed");
             delete p;
             return 1;
         }
         for (const Range &r : ar) {
             // preserve the 16-byte phase of the host address so vector loads keep their alignment
-            cudaError_t e = cudaMemcpyAsync(p->d_operands + r.dev_off, (const void *)r.lo, r.hi - r.lo,
-                                            cudaMemcpyHostToDevice, ctx->stream);
-            if (e != cudaSuccess) {
-                b2g_set_error(std::string("b2g_plan_create: operand upload failed: ") + cudaGetErrorString(e));
-                cudaFree(p->d_operands);
+            if (b2g_upload(ctx, p->d_operands + r.dev_off, (const void *)r.lo, r.hi - r.lo) != 0) {
+                b2g_dfree(ctx, p->d_operands);
                 delete p;
                 return 1;
             }
@@ -261,7 +316,8 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
         return x.a0_off < y.a0_off;
     });
     if (n > 0) {
-        B2G_CUDA(cudaMalloc(&p->d_pairs, (size_t)n * sizeof(B2GPair)));
+        if (b2g_dmalloc(ctx, (void **)&p->d_pairs, (size_t)n * sizeof(B2GPair)))
+            return 1;
         B2G_CUDA(cudaMemcpyAsync(p->d_pairs, hp.data(), (size_t)n * sizeof(B2GPair), cudaMemcpyHostToDevice,
                                  ctx->stream));
     }
@@ -288,12 +344,9 @@ extern "C" int b2g_plan_destroy(b2g_plan *p) {
         return 0;
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
-    if (p->d_operands)
-        cudaFree(p->d_operands);
-    if (p->d_pairs)
-        cudaFree(p->d_pairs);
-    if (p->d_work)
-        cudaFree(p->d_work);
+    b2g_dfree(p->ctx, p->d_operands);
+    b2g_dfree(p->ctx, p->d_pairs);
+    b2g_dfree(p->ctx, p->d_work);
     b2g_tiled_destroy(p->tiled);
     delete p;
     return 0;
@@ -315,6 +368,20 @@ extern "C" int b2g_seq_matvec_dev(b2g_plan *p, const double *c_dev, double *v_de
     }
     B2G_CUDA(cudaSetDevice(p->ctx->device));
     return b2g_launch_matvec(p, c_dev, v_dev, scale);
+}
+
+extern "C" int b2g_plan_profile(b2g_plan *p, const double *c_dev, double *v_dev, double scale,
+                                b2g_kernel_stat *out, int capacity, int *count) {
+    if (!p || !out || !count) {
+        b2g_set_error("b2g_plan_profile: null argument");
+        return 1;
+    }
+    B2G_CUDA(cudaSetDevice(p->ctx->device));
+    if (!p->tiled) {
+        b2g_set_error("b2g_plan_profile: plan runs the generic kernel only");
+        return 1;
+    }
+    return b2g_tiled_launch(p, c_dev, v_dev, scale, out, capacity, count);
 }
 
 static int ensure_staging(b2g_context *ctx, size_t csize, size_t vsize) {

@@ -237,10 +237,8 @@ void jacobi_eigh(int m, std::vector<double> &a, std::vector<double> &w, std::vec
 
 struct DevBuf {
     void *p = nullptr;
-    ~DevBuf() {
-        if (p)
-            cudaFree(p);
-    }
+    b2g_context *ctx = nullptr;
+    ~DevBuf() { b2g_dfree(ctx, p); }
 };
 
 } // namespace
@@ -272,18 +270,18 @@ extern "C" int b2g_davidson(b2g_plan *plan, const double *diag_host, double *ket
     const int M = deflation_max_size;
     const int64_t ld = (n + 1) & ~(int64_t)1;
     DevBuf d_bs, d_ss, d_q, d_t, d_aa, d_scal, d_part, d_cnt, d_gpart, d_gram, d_rot;
-    B2G_CUDA(cudaMalloc(&d_bs.p, sizeof(double) * ld * M));
-    B2G_CUDA(cudaMalloc(&d_ss.p, sizeof(double) * ld * M));
-    B2G_CUDA(cudaMalloc(&d_q.p, sizeof(double) * ld));
-    B2G_CUDA(cudaMalloc(&d_t.p, sizeof(double) * ld));
-    B2G_CUDA(cudaMalloc(&d_aa.p, sizeof(double) * ld));
-    B2G_CUDA(cudaMalloc(&d_scal.p, sizeof(double) * 8));
-    B2G_CUDA(cudaMalloc(&d_part.p, sizeof(double) * RED_BLOCKS));
-    B2G_CUDA(cudaMalloc(&d_cnt.p, sizeof(unsigned int)));
+    d_bs.ctx = ctx; if (b2g_dmalloc(ctx, &d_bs.p, sizeof(double) * ld * M)) return 1;
+    d_ss.ctx = ctx; if (b2g_dmalloc(ctx, &d_ss.p, sizeof(double) * ld * M)) return 1;
+    d_q.ctx = ctx; if (b2g_dmalloc(ctx, &d_q.p, sizeof(double) * ld)) return 1;
+    d_t.ctx = ctx; if (b2g_dmalloc(ctx, &d_t.p, sizeof(double) * ld)) return 1;
+    d_aa.ctx = ctx; if (b2g_dmalloc(ctx, &d_aa.p, sizeof(double) * ld)) return 1;
+    d_scal.ctx = ctx; if (b2g_dmalloc(ctx, &d_scal.p, sizeof(double) * 8)) return 1;
+    d_part.ctx = ctx; if (b2g_dmalloc(ctx, &d_part.p, sizeof(double) * RED_BLOCKS)) return 1;
+    d_cnt.ctx = ctx; if (b2g_dmalloc(ctx, &d_cnt.p, sizeof(unsigned int))) return 1;
     const int gram_blocks = ctx->sm_count * 2;
-    B2G_CUDA(cudaMalloc(&d_gpart.p, sizeof(double) * gram_blocks * (M * (M + 1) / 2)));
-    B2G_CUDA(cudaMalloc(&d_gram.p, sizeof(double) * M * M));
-    B2G_CUDA(cudaMalloc(&d_rot.p, sizeof(double) * M * M));
+    d_gpart.ctx = ctx; if (b2g_dmalloc(ctx, &d_gpart.p, sizeof(double) * gram_blocks * (M * (M + 1) / 2))) return 1;
+    d_gram.ctx = ctx; if (b2g_dmalloc(ctx, &d_gram.p, sizeof(double) * M * M)) return 1;
+    d_rot.ctx = ctx; if (b2g_dmalloc(ctx, &d_rot.p, sizeof(double) * M * M)) return 1;
     double *bs = (double *)d_bs.p, *ss = (double *)d_ss.p, *q = (double *)d_q.p, *t = (double *)d_t.p,
            *aa = (double *)d_aa.p, *scal = (double *)d_scal.p, *part = (double *)d_part.p;
     unsigned int *cnt = (unsigned int *)d_cnt.p;

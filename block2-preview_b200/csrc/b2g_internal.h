@@ -37,6 +37,11 @@ struct b2g_context {
     size_t d_cv_doubles = 0;
     void *nccl_comm = nullptr;
     int nranks = 1, rank = 0;
+    // double-buffered pinned staging of the operand mirror (host pageable -> HBM)
+    void *h_up[2] = {nullptr, nullptr};
+    cudaEvent_t up_done[2] = {nullptr, nullptr};
+    size_t up_bytes = 0;
+    int up_threads = 8;
 };
 
 struct b2g_plan {
@@ -53,6 +58,11 @@ struct b2g_plan {
 };
 
 void b2g_set_error(const std::string &msg);
+// stream-ordered pool allocations (cached by the driver mempool across plans / Davidson calls)
+int b2g_dmalloc(b2g_context *ctx, void **ptr, size_t bytes);
+void b2g_dfree(b2g_context *ctx, void *ptr);
+// pageable host -> device copy through pinned staging filled by several host threads
+int b2g_upload(b2g_context *ctx, void *dst, const void *src, size_t bytes);
 #define B2G_CUDA(expr)                                                                   \
     do {                                                                                 \
         cudaError_t e__ = (expr);                                                        \
@@ -66,5 +76,6 @@ void b2g_set_error(const std::string &msg);
 int b2g_launch_matvec(b2g_plan *plan, const double *c_dev, double *v_dev, double scale);
 // two-phase DMMA path (b2g_tiled.cu)
 int b2g_tiled_build(b2g_plan *plan);
-int b2g_tiled_launch(b2g_plan *plan, const double *c_dev, double *v_dev, double scale);
+int b2g_tiled_launch(b2g_plan *plan, const double *c_dev, double *v_dev, double scale,
+                     b2g_kernel_stat *stats = nullptr, int cap = 0, int *count = nullptr);
 void b2g_tiled_destroy(void *tiled);

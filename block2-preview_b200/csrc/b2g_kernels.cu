@@ -60,10 +60,10 @@ int b2g_launch_matvec(b2g_plan *p, const double *c_dev, double *v_dev, double sc
         const int grid = (int)std::min<int64_t>(p->n_generic, (int64_t)ctx->sm_count * 8);
         const size_t need = (p->max_work > GEN_SMEM_W) ? (size_t)p->max_work * grid : 0;
         if (need > p->work_doubles) {
-            if (p->d_work)
-                cudaFree(p->d_work);
+            b2g_dfree(ctx, p->d_work);
             p->d_work = nullptr, p->work_doubles = 0;
-            B2G_CUDA(cudaMalloc(&p->d_work, need * sizeof(double)));
+            if (b2g_dmalloc(ctx, (void **)&p->d_work, need * sizeof(double)))
+                return 1;
             p->work_doubles = need;
         }
         b2g_pair_generic_kernel<<<grid, GEN_THREADS, 0, ctx->stream>>>(p->d_pairs, p->n_generic, c_dev, v_dev, scale,

@@ -266,9 +266,11 @@ struct LaunchGroup { // one kernel launch: units of one (phase, cfg, layout)
     int phase, cfg, layout;
     Unit *d_units = nullptr;
     int n_units = 0;
+    double flops = 0; // useful 2*m*n*k FLOPs of the launch (valid rows x cols only)
 };
 
 struct TiledPlan {
+    b2g_context *ctx = nullptr;
     P1Pair *d_p1 = nullptr;
     P2Window *d_win = nullptr;
     P2Seg *d_seg = nullptr;
@@ -318,7 +320,7 @@ void b2g_tiled_destroy(void *h) {
     if (!tp)
         return;
     for (void *p : tp->to_free)
-        cudaFree(p);
+        b2g_dfree(tp->ctx, p);
     delete tp;
 }
 
@@ -328,11 +330,12 @@ int b2g_tiled_build(b2g_plan *p) {
     const std::vector<B2GPair> &hp = p->h_pairs;
     const size_t n = hp.size();
     TiledPlan *tp = new TiledPlan();
+    tp->ctx = ctx;
     p->tiled = tp;
     if (n == 0)
         return 0;
     const char *env_kc = getenv("B2G_KCHUNK");
-    const int64_t kchunk = env_kc ? atoll(env_kc) : 4096;
+    const int64_t kchunk = env_kc ? atoll(env_kc) : 2048;
 
     // ---- phase 1 descriptors + W workspace layout
     std::vector<P1Pair> p1(n);
@@ -369,7 +372,7 @@ int b2g_tiled_build(b2g_plan *p) {
     // ---- units
     struct HostUnit {
         Unit u;
-        double cost;
+        double cost, flops;
     };
     std::map<std::tuple<int, int, int>, std::vector<HostUnit>> groups; // (phase, cfg, layout)
     for (size_t i = 0; i < n; i++) {
@@ -380,7 +383,8 @@ int b2g_tiled_build(b2g_plan *p) {
             for (const Strip &cs : split_cols(q.n0)) {
                 const int c = cfg_of(rs.tile, cs.tile);
                 groups[std::make_tuple(1, c, p1[i].tb0)].push_back(
-                    HostUnit{Unit{(int)i, rs.origin, cs.origin, 0, 0}, (double)rs.tile * cs.tile * (q.k0 + 2 * BK)});
+                    HostUnit{Unit{(int)i, rs.origin, cs.origin, 0, 0}, (double)rs.tile * cs.tile * (q.k0 + 2 * BK),
+                             2.0 * std::min(rs.tile, q.m0 - rs.origin) * std::min(cs.tile, q.n0 - cs.origin) * q.k0});
             }
     }
     std::vector<P2Seg> segs;
@@ -401,7 +405,9 @@ int b2g_tiled_build(b2g_plan *p) {
                     for (const Strip &cs : csv)
                         groups[std::make_tuple(2, cfg_of(rs.tile, cs.tile), lay)].push_back(
                             HostUnit{Unit{(int)w, rs.origin, cs.origin, (int)s0, (int)s1},
-                                     (double)rs.tile * cs.tile * (double)(ksum + 2 * BK)});
+                                     (double)rs.tile * cs.tile * (double)(ksum + 2 * BK),
+                                     2.0 * std::min(rs.tile, wins[w].m1 - rs.origin) *
+                                         std::min(cs.tile, wins[w].n0 - cs.origin) * (double)ksum});
                 s0 = s1, ksum = 0;
             };
             for (size_t idx : lst) {
@@ -418,7 +424,8 @@ int b2g_tiled_build(b2g_plan *p) {
 
     // ---- upload
     auto upload = [&](const void *src, size_t bytes, void **dst) -> int {
-        B2G_CUDA(cudaMalloc(dst, std::max<size_t>(bytes, 16)));
+        if (b2g_dmalloc(ctx, dst, bytes))
+            return 1;
         tp->to_free.push_back(*dst);
         if (bytes)
             B2G_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -430,7 +437,8 @@ int b2g_tiled_build(b2g_plan *p) {
         return 1;
     if (upload(segs.data(), segs.size() * sizeof(P2Seg), (void **)&tp->d_seg))
         return 1;
-    B2G_CUDA(cudaMalloc((void **)&tp->d_wbuf, std::max<size_t>(tp->wbuf_doubles, 2) * sizeof(double)));
+    if (b2g_dmalloc(ctx, (void **)&tp->d_wbuf, std::max<size_t>(tp->wbuf_doubles, 2) * sizeof(double)))
+        return 1;
     tp->to_free.push_back(tp->d_wbuf);
     std::vector<std::vector<Unit>> keep; // host copies must outlive the async copies
     for (auto &kv : groups) {
@@ -444,13 +452,16 @@ int b2g_tiled_build(b2g_plan *p) {
         LaunchGroup g;
         g.phase = std::get<0>(kv.first), g.cfg = std::get<1>(kv.first), g.layout = std::get<2>(kv.first);
         g.n_units = (int)hu.size();
+        for (const HostUnit &x : hu)
+            g.flops += x.flops;
         if (upload(keep.back().data(), hu.size() * sizeof(Unit), (void **)&g.d_units))
             return 1;
         tp->groups.push_back(g);
     }
     std::stable_sort(tp->groups.begin(), tp->groups.end(),
                      [](const LaunchGroup &a, const LaunchGroup &b) { return a.phase < b.phase; });
-    B2G_CUDA(cudaMalloc((void **)&tp->d_counters, sizeof(unsigned int) * 64));
+    if (b2g_dmalloc(ctx, (void **)&tp->d_counters, sizeof(unsigned int) * 64))
+        return 1;
     tp->to_free.push_back(tp->d_counters);
     B2G_CUDA(cudaStreamSynchronize(ctx->stream));
     p->stats.launches = (int64_t)tp->groups.size() + 1;
@@ -458,12 +469,22 @@ int b2g_tiled_build(b2g_plan *p) {
     return 0;
 }
 
-int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double scale) {
+int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double scale, b2g_kernel_stat *stats,
+                     int cap, int *count) {
     TiledPlan *tp = (TiledPlan *)p->tiled;
     b2g_context *ctx = p->ctx;
+    if (count)
+        *count = 0;
     if (!tp || tp->groups.empty())
         return 0;
     B2G_CUDA(cudaMemsetAsync(tp->d_counters, 0, sizeof(unsigned int) * 64, ctx->stream));
+    std::vector<cudaEvent_t> ev;
+    if (stats) {
+        ev.resize(tp->groups.size() + 1);
+        for (auto &e : ev)
+            B2G_CUDA(cudaEventCreate(&e));
+        B2G_CUDA(cudaEventRecord(ev[0], ctx->stream));
+    }
     int gi = 0;
     for (const LaunchGroup &g : tp->groups) {
         unsigned int *counter = tp->d_counters + gi++;
@@ -499,7 +520,25 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
         if (rc)
             return rc;
         ctx->launches++;
+        if (stats)
+            B2G_CUDA(cudaEventRecord(ev[gi], ctx->stream));
     }
     B2G_CUDA(cudaGetLastError());
+    if (stats) {
+        B2G_CUDA(cudaStreamSynchronize(ctx->stream));
+        int n = 0;
+        for (size_t i = 0; i < tp->groups.size() && n < cap; i++, n++) {
+            const LaunchGroup &g = tp->groups[i];
+            float ms = 0;
+            B2G_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+            snprintf(stats[n].name, sizeof(stats[n].name), "phase%d_%dx%d_%s", g.phase, kCfg[g.cfg].bm, kCfg[g.cfg].bn,
+                     g.phase == 1 ? (g.layout ? "Bt" : "Bn") : (g.layout ? "At" : "An"));
+            stats[n].flops = g.flops, stats[n].ms = ms, stats[n].units = g.n_units;
+        }
+        if (count)
+            *count = n;
+        for (auto &e : ev)
+            cudaEventDestroy(e);
+    }
     return 0;
 }

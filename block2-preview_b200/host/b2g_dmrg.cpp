@@ -75,7 +75,7 @@ static RunResult run_dmrg(const Args &args, const shared_ptr<MPO<S, double>> &mp
         dmrg = g;
     } else
         dmrg = make_shared<DMRG<S, double, double>>(me, bdims, noises);
-    dmrg->iprint = 1;
+    dmrg->iprint = 2;
     dmrg->noise_type = NoiseTypes::DensityMatrix;
     dmrg->decomp_type = DecompositionTypes::DensityMatrix;
     dmrg->davidson_soft_max_iter = 4000;

@@ -63,6 +63,14 @@ typedef struct b2g_plan_stats {
     double upload_seconds;  /* host->device mirror time of the operands */
 } b2g_plan_stats;
 
+/* per-launch record of one profiled matvec (b2g_plan_profile) */
+typedef struct b2g_kernel_stat {
+    char name[64];   /* e.g. phase2_128x64_An */
+    double flops;    /* useful 2*m*n*k FLOPs of the launch */
+    double ms;       /* CUDA-event duration on the context stream */
+    int64_t units;   /* CTA tile x K-chunk work units */
+} b2g_kernel_stat;
+
 const char *b2g_last_error(void);
 int b2g_device_count(void);
 int b2g_context_create(int device, b2g_context **ctx);
@@ -87,6 +95,10 @@ int b2g_plan_get_stats(const b2g_plan *plan, b2g_plan_stats *out);
 int b2g_seq_matvec(b2g_plan *plan, const double *c_host, double *v_host, double scale);
 /* same with device-resident c and sigma; asynchronous on the context stream */
 int b2g_seq_matvec_dev(b2g_plan *plan, const double *c_dev, double *v_dev, double scale);
+
+/* One matvec with CUDA events between the kernel launches (measurement only; synchronous). */
+int b2g_plan_profile(b2g_plan *plan, const double *c_dev, double *v_dev, double scale,
+                     b2g_kernel_stat *out, int capacity, int *count);
 
 /* Grouped GEMM list with the cblas_dgemm_batch signature (device pointers), asynchronous. */
 int b2g_dgemm_batch(b2g_context *ctx, int64_t group_count, const int32_t *ta, const int32_t *tb,
