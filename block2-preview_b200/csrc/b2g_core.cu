@@ -254,6 +254,17 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
         if (ea1)
             rg.push_back(Range{pa, pa + ea1 * sizeof(double), 0});
     }
+    const bool verbose = getenv("B2G_VERBOSE") != nullptr;
+    auto tstart = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (verbose) {
+            auto now = std::chrono::steady_clock::now();
+            fprintf(stderr, "[b2g] plan_create %-14s %8.3f ms\n", what,
+                    std::chrono::duration<double, std::milli>(now - tstart).count());
+            tstart = now;
+        }
+    };
+    lap("scan pairs");
     // merge the referenced operator ranges into arenas
     std::sort(rg.begin(), rg.end(), [](const Range &x, const Range &y) { return x.lo < y.lo; });
     std::vector<Range> ar;
@@ -309,6 +320,7 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
             q.a1 = p->d_operands + ra.dev_off + ((uintptr_t)q.a1 - ra.lo) / sizeof(double);
         }
     }
+    lap("mirror issue");
     // order: pairs writing the same sigma window become neighbours (locality of the accumulation)
     std::stable_sort(hp.begin(), hp.end(), [](const B2GPair &x, const B2GPair &y) {
         if (x.c1_off != y.c1_off)
@@ -321,7 +333,9 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
         B2G_CUDA(cudaMemcpyAsync(p->d_pairs, hp.data(), (size_t)n * sizeof(B2GPair), cudaMemcpyHostToDevice,
                                  ctx->stream));
     }
+    lap("sort pairs");
     B2G_CUDA(cudaStreamSynchronize(ctx->stream));
+    lap("mirror sync");
     p->stats.upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     p->n_generic = n;
     p->stats.n_small = n, p->stats.n_large = 0;
@@ -334,6 +348,7 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
             b2g_plan_destroy(p);
             return 1;
         }
+        lap("tiled build");
     }
     *out = p;
     return 0;

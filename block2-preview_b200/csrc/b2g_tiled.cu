@@ -82,14 +82,11 @@ phase1_kernel(const P1Pair *__restrict__ pairs, const Unit *__restrict__ units, 
     int wm0, wn0;
     warp_origin<Cfg>(wm0, wn0);
     const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
-    while (true) {
+    // units are claimed one ahead: the atomic for the next unit is in flight while this one runs
+    int u = blockIdx.x;
+    while (u < n_units) {
         if (threadIdx.x == 0)
-            s_unit = (int)atomicAdd(counter, 1u);
-        __syncthreads();
-        const int u = s_unit;
-        __syncthreads();
-        if (u >= n_units)
-            break;
+            s_unit = (int)(atomicAdd(counter, 1u) + gridDim.x);
         const Unit un = units[u];
         const P1Pair p = pairs[un.idx];
         const int row0 = un.row0, col0 = un.col0;
@@ -121,6 +118,8 @@ phase1_kernel(const P1Pair *__restrict__ pairs, const Unit *__restrict__ units, 
                         w[(size_t)r * p.n0 + cc + 1] = p.alpha * acc[mi][ni][1];
                 }
             }
+        u = s_unit; // written before the barriers of the main loop
+        __syncthreads();
     }
 }
 
@@ -160,14 +159,11 @@ phase2_kernel(const P2Window *__restrict__ wins, const P2Seg *__restrict__ segs,
     int wm0, wn0;
     warp_origin<Cfg>(wm0, wn0);
     const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
-    while (true) {
+    // units are claimed one ahead: the atomic for the next unit is in flight while this one runs
+    int u = blockIdx.x;
+    while (u < n_units) {
         if (threadIdx.x == 0)
-            s_unit = (int)atomicAdd(counter, 1u);
-        __syncthreads();
-        const int u = s_unit;
-        __syncthreads();
-        if (u >= n_units)
-            break;
+            s_unit = (int)(atomicAdd(counter, 1u) + gridDim.x);
         const Unit un = units[u];
         const P2Window win = wins[un.idx];
         P2Src<Cfg, A_KC> src;
@@ -201,6 +197,26 @@ phase2_kernel(const P2Window *__restrict__ wins, const P2Seg *__restrict__ segs,
                         atomicAdd(out + (size_t)r * win.ldc + cc + 1, scale * acc[mi][ni][1]);
                 }
             }
+        u = s_unit; // written before the barriers of the main loop
+        __syncthreads();
+    }
+}
+
+// ------------------------------ W pre-sum -----------------------------------
+// sum_p A1 * W_p = A1 * (sum_p W_p) for pairs that share the sigma window and the operator
+// block A1: their W are added (memory-bound, in place into the first one) so phase 2 multiplies
+// by A1 once.
+__global__ void __launch_bounds__(256) wsum_kernel(const SumTask *__restrict__ tasks, int n_tasks,
+                                                   double *__restrict__ wbuf) {
+    for (int t = blockIdx.x; t < n_tasks; t += gridDim.x) {
+        const SumTask k = tasks[t];
+        double *d = wbuf + k.dst + k.start;
+        for (int64_t e = threadIdx.x; e < k.count; e += 256) {
+            double s = d[e];
+            for (int j = 0; j < k.nsrc; j++)
+                s += wbuf[k.src[j] + k.start + e];
+            d[e] = s;
+        }
     }
 }
 
@@ -271,6 +287,9 @@ struct LaunchGroup { // one kernel launch: units of one (phase, cfg, layout)
 
 struct TiledPlan {
     b2g_context *ctx = nullptr;
+    SumTask *d_sum = nullptr;
+    int n_sum = 0;
+    double sum_bytes = 0;
     P1Pair *d_p1 = nullptr;
     P2Window *d_win = nullptr;
     P2Seg *d_seg = nullptr;
@@ -388,13 +407,23 @@ int b2g_tiled_build(b2g_plan *p) {
             }
     }
     std::vector<P2Seg> segs;
+    std::vector<SumTask> sums;
+    const char *env_merge = getenv("B2G_NO_WSUM");
+    const bool merge_w = !(env_merge && env_merge[0] == '1');
+    const int64_t sum_chunk = 32768;
     for (int lay = 0; lay < 2; lay++)
         for (size_t w = 0; w < wins.size(); w++) {
             auto &lst = wpairs[lay][w];
             if (lst.empty() || wins[w].m1 == 0 || wins[w].n0 == 0)
                 continue;
-            // neighbours share the operator block when possible (L2 reuse across K-chunks)
-            std::stable_sort(lst.begin(), lst.end(), [&hp](size_t x, size_t y) { return hp[x].a1 < hp[y].a1; });
+            // neighbours share the operator block (pre-summed below; L2 reuse across K-chunks)
+            std::stable_sort(lst.begin(), lst.end(), [&hp](size_t x, size_t y) {
+                if (hp[x].a1 != hp[y].a1)
+                    return hp[x].a1 < hp[y].a1;
+                if (hp[x].lda1 != hp[y].lda1)
+                    return hp[x].lda1 < hp[y].lda1;
+                return hp[x].m0 < hp[y].m0;
+            });
             const std::vector<Strip> rsv = split_rows(wins[w].m1), csv = split_cols(wins[w].n0);
             size_t s0 = segs.size();
             int64_t ksum = 0;
@@ -410,14 +439,33 @@ int b2g_tiled_build(b2g_plan *p) {
                                          std::min(cs.tile, wins[w].n0 - cs.origin) * (double)ksum});
                 s0 = s1, ksum = 0;
             };
-            for (size_t idx : lst) {
-                const B2GPair &q = hp[idx];
-                if (q.m0 == 0)
-                    continue;
-                segs.push_back(P2Seg{q.a1, p1[idx].w_off, q.lda1, q.m0});
-                ksum += q.m0;
-                if (ksum >= kchunk)
-                    flush(segs.size());
+            for (size_t z = 0; z < lst.size();) {
+                const B2GPair &q = hp[lst[z]];
+                // run of pairs with the same operator block: one segment, W summed beforehand
+                size_t z1 = z + 1;
+                while (merge_w && z1 < lst.size() && z1 - z < 4 && hp[lst[z1]].a1 == q.a1 && hp[lst[z1]].lda1 == q.lda1 &&
+                       hp[lst[z1]].m0 == q.m0)
+                    z1++;
+                if (q.m0 != 0) {
+                    const int64_t total = (int64_t)q.m0 * q.n0;
+                    for (size_t y = z + 1; y < z1; y += 3) { // up to 3 sources per task
+                        SumTask st{};
+                        st.dst = p1[lst[z]].w_off;
+                        st.nsrc = (int)std::min<size_t>(3, z1 - y);
+                        for (int j = 0; j < st.nsrc; j++)
+                            st.src[j] = p1[lst[y + j]].w_off;
+                        for (int64_t s = 0; s < total; s += sum_chunk) {
+                            st.start = s, st.count = std::min<int64_t>(sum_chunk, total - s);
+                            sums.push_back(st);
+                            tp->sum_bytes += 8.0 * st.count * (st.nsrc + 2);
+                        }
+                    }
+                    segs.push_back(P2Seg{q.a1, p1[lst[z]].w_off, q.lda1, q.m0});
+                    ksum += q.m0;
+                    if (ksum >= kchunk)
+                        flush(segs.size());
+                }
+                z = z1;
             }
             flush(segs.size());
         }
@@ -436,6 +484,10 @@ int b2g_tiled_build(b2g_plan *p) {
     if (upload(wins.data(), wins.size() * sizeof(P2Window), (void **)&tp->d_win))
         return 1;
     if (upload(segs.data(), segs.size() * sizeof(P2Seg), (void **)&tp->d_seg))
+        return 1;
+    // at most 4 pairs are merged per run, so every destination range belongs to exactly one task
+    tp->n_sum = (int)sums.size();
+    if (upload(sums.data(), sums.size() * sizeof(SumTask), (void **)&tp->d_sum))
         return 1;
     if (b2g_dmalloc(ctx, (void **)&tp->d_wbuf, std::max<size_t>(tp->wbuf_doubles, 2) * sizeof(double)))
         return 1;
@@ -478,17 +530,50 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
     if (!tp || tp->groups.empty())
         return 0;
     B2G_CUDA(cudaMemsetAsync(tp->d_counters, 0, sizeof(unsigned int) * 64, ctx->stream));
-    std::vector<cudaEvent_t> ev;
-    if (stats) {
-        ev.resize(tp->groups.size() + 1);
-        for (auto &e : ev)
-            B2G_CUDA(cudaEventCreate(&e));
-        B2G_CUDA(cudaEventRecord(ev[0], ctx->stream));
-    }
+    struct Rec {
+        std::string name;
+        double flops;
+        int64_t units;
+        cudaEvent_t e0, e1;
+    };
+    std::vector<Rec> recs;
+    auto begin = [&](const std::string &name, double flops, int64_t units) -> int {
+        if (!stats)
+            return 0;
+        Rec r{name, flops, units, nullptr, nullptr};
+        B2G_CUDA(cudaEventCreate(&r.e0));
+        B2G_CUDA(cudaEventCreate(&r.e1));
+        B2G_CUDA(cudaEventRecord(r.e0, ctx->stream));
+        recs.push_back(r);
+        return 0;
+    };
+    auto end = [&]() -> int {
+        if (stats)
+            B2G_CUDA(cudaEventRecord(recs.back().e1, ctx->stream));
+        return 0;
+    };
     int gi = 0;
+    bool summed = false;
     for (const LaunchGroup &g : tp->groups) {
+        if (g.phase == 2 && !summed) {
+            summed = true;
+            if (tp->n_sum > 0) {
+                if (begin("wsum", 0.0, tp->n_sum))
+                    return 1;
+                wsum_kernel<<<std::min(tp->n_sum, ctx->sm_count * 8), 256, 0, ctx->stream>>>(tp->d_sum, tp->n_sum,
+                                                                                             tp->d_wbuf);
+                ctx->launches++;
+                if (end())
+                    return 1;
+            }
+        }
         unsigned int *counter = tp->d_counters + gi++;
         int rc = 0;
+        char nm[64];
+        snprintf(nm, sizeof(nm), "phase%d_%dx%d_%s", g.phase, kCfg[g.cfg].bm, kCfg[g.cfg].bn,
+                 g.phase == 1 ? (g.layout ? "Bt" : "Bn") : (g.layout ? "At" : "An"));
+        if (begin(nm, g.flops, g.n_units))
+            return 1;
 #define B2G_DISPATCH(PH, CFG, LAY, CALL)                                                \
     if (g.phase == PH && g.cfg == CFG && g.layout == LAY)                               \
         rc = CALL;
@@ -520,25 +605,25 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
         if (rc)
             return rc;
         ctx->launches++;
-        if (stats)
-            B2G_CUDA(cudaEventRecord(ev[gi], ctx->stream));
+        if (end())
+            return 1;
     }
     B2G_CUDA(cudaGetLastError());
     if (stats) {
         B2G_CUDA(cudaStreamSynchronize(ctx->stream));
         int n = 0;
-        for (size_t i = 0; i < tp->groups.size() && n < cap; i++, n++) {
-            const LaunchGroup &g = tp->groups[i];
+        for (size_t i = 0; i < recs.size(); i++) {
             float ms = 0;
-            B2G_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
-            snprintf(stats[n].name, sizeof(stats[n].name), "phase%d_%dx%d_%s", g.phase, kCfg[g.cfg].bm, kCfg[g.cfg].bn,
-                     g.phase == 1 ? (g.layout ? "Bt" : "Bn") : (g.layout ? "At" : "An"));
-            stats[n].flops = g.flops, stats[n].ms = ms, stats[n].units = g.n_units;
+            B2G_CUDA(cudaEventElapsedTime(&ms, recs[i].e0, recs[i].e1));
+            if (n < cap) {
+                snprintf(stats[n].name, sizeof(stats[n].name), "%s", recs[i].name.c_str());
+                stats[n].flops = recs[i].flops, stats[n].ms = ms, stats[n].units = recs[i].units;
+                n++;
+            }
+            cudaEventDestroy(recs[i].e0), cudaEventDestroy(recs[i].e1);
         }
         if (count)
             *count = n;
-        for (auto &e : ev)
-            cudaEventDestroy(e);
     }
     return 0;
 }

@@ -47,6 +47,12 @@ struct P2Seg {           // phase 2: one K-segment (= one pair)
     int32_t lda, klen;   // leading dimension of a1, K length (= m0 of the pair)
 };
 
+struct SumTask {         // W[dst] += sum_j W[src_j]  over `count` doubles (pairs sharing sigma window and A1)
+    int64_t dst, src[3];
+    int64_t start, count; // element range of this work unit inside the blocks
+    int32_t nsrc, pad;
+};
+
 struct Unit {            // one CTA-tile x K-chunk
     int32_t idx;         // phase 1: pair index; phase 2: window index
     int32_t row0, col0;  // origin of the tile inside the output matrix (elements)
