@@ -269,6 +269,14 @@ def run_b200(args) -> None:
         except Exception:
             pass
         alg_bytes = 8.0 * (sf.operand_doubles + sf.csize + sf.vsize)
+        traffic = None  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_phase2_128x64_full.json")))
+            to_b = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            traffic = sum(float(cap[k].split()[0]) * to_b[cap[k].split()[1]]
+                          for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -283,7 +291,8 @@ def run_b200(args) -> None:
                     "d2h_bytes_per_step": 8 * sf.vsize, "path_check_rel": chk},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": dom["name"], "achieved": dom["tflops"], "peak": peak,
-                         "unit": "TFLOP/s", "frac": dom["tflops"] / peak if peak else None, "traffic": None,
+                         "unit": "TFLOP/s", "frac": dom["tflops"] / peak if peak else None, "traffic": traffic,
+                         "traffic_source": "profiles/r01_ncu_phase2_128x64_full.json (ncu --set full, 1-GPU list)",
                          "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (FP64 tensor pipe, of measured); "
                                         "MEASURED_PEAKS.json has no FP64 entry; DMMA issue ceiling 37.05 TFLOP/s "
                                         "(profiles/r01_fp64_probe.json)",
