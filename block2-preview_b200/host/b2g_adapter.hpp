@@ -36,6 +36,11 @@ struct Session {
     std::atomic<bool> recording{false};
     double t_plan = 0, t_matvec = 0;
     size_t n_plan = 0, n_matvec = 0;
+    // --verify: worst relative deviation ||sigma_gpu - sigma_cpu|| / ||sigma_cpu|| over all sites,
+    // sigma_cpu from the reference's own BatchGEMMSeq::operator() on the same recorded list
+    bool verify = false;
+    double max_matvec_err = 0;
+    size_t n_verified = 0;
     explicit Session(int device = 0) {
         if (b2g_context_create(device, &ctx) != 0)
             throw std::runtime_error(std::string("b2g_context_create: ") + b2g_last_error());
@@ -165,6 +170,20 @@ template <typename S> struct GPUDMRG : DMRG<S, double, double> {
             throw std::runtime_error("b2g: GPUDMRG needs mpo->tf to be a GPUTensorFunctions");
         frame_<double>()->activate(0);
         h_eff->precompute();
+        if (gtf->session->verify && h_eff->tf->opf->seq->batch[0]->gp.size() != 0) {
+            const size_t n = h_eff->ket->total_memory;
+            vector<double> x(n), y_gpu(n, 0.0), y_cpu(n, 0.0);
+            Random::fill<double>(x.data(), n);
+            GMatrix<double> xm(x.data(), (MKL_INT)n, 1);
+            (*gtf)(xm, GMatrix<double>(y_gpu.data(), (MKL_INT)n, 1), 1.0);
+            h_eff->tf->opf->seq->operator()(xm, GMatrix<double>(y_cpu.data(), (MKL_INT)n, 1), 1.0);
+            double num = 0, den = 0;
+            for (size_t j = 0; j < n; j++)
+                num += (y_gpu[j] - y_cpu[j]) * (y_gpu[j] - y_cpu[j]), den += y_cpu[j] * y_cpu[j];
+            const double err = den > 0 ? sqrt(num / den) : sqrt(num);
+            gtf->session->max_matvec_err = max(gtf->session->max_matvec_err, err);
+            gtf->session->n_verified++;
+        }
         double e = 0;
         int ndav = 0;
         size_t nflop = 0;
