@@ -71,19 +71,62 @@ void b2g_dfree(b2g_context *ctx, void *ptr) {
         cudaFreeAsync(ptr, ctx->stream);
 }
 
-int b2g_upload(b2g_context *ctx, void *dst, const void *src, size_t bytes) {
-    constexpr size_t CH = (size_t)32 << 20;
-    if (bytes < ((size_t)1 << 20)) { // small ranges: the driver's own staging is fine
-        B2G_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
-        return 0;
-    }
+static constexpr size_t B2G_UP_CHUNK = (size_t)32 << 20;
+
+static int ensure_upload_buffers(b2g_context *ctx) {
     if (!ctx->h_up[0]) {
         for (int i = 0; i < 2; i++) {
-            B2G_CUDA(cudaMallocHost(&ctx->h_up[i], CH));
+            B2G_CUDA(cudaMallocHost(&ctx->h_up[i], B2G_UP_CHUNK));
             B2G_CUDA(cudaEventCreateWithFlags(&ctx->up_done[i], cudaEventDisableTiming));
         }
-        ctx->up_bytes = CH;
+        ctx->up_bytes = B2G_UP_CHUNK;
     }
+    return 0;
+}
+
+// Packs many small host ranges that are neighbours in the device arena into one pinned
+// staging slice and ships the slice with a single DMA (a site has thousands of operator
+// blocks; one cudaMemcpyAsync per block from pageable memory costs ~20 us each).
+struct MirrorWriter {
+    b2g_context *ctx;
+    char *dst_base;
+    size_t slice_begin = 0, fill = 0;
+    int buf = 0;
+    int flush() {
+        if (fill) {
+            B2G_CUDA(cudaMemcpyAsync(dst_base + slice_begin, ctx->h_up[buf], fill, cudaMemcpyHostToDevice,
+                                     ctx->stream));
+            B2G_CUDA(cudaEventRecord(ctx->up_done[buf], ctx->stream));
+            buf ^= 1;
+            fill = 0;
+        }
+        return 0;
+    }
+    int add(size_t dev_off, const void *src, size_t bytes) {
+        if (bytes >= B2G_UP_CHUNK / 4) {
+            if (flush())
+                return 1;
+            return b2g_upload(ctx, dst_base + dev_off, src, bytes);
+        }
+        if (fill && (dev_off < slice_begin || dev_off - slice_begin + bytes > B2G_UP_CHUNK))
+            if (flush())
+                return 1;
+        if (!fill) {
+            B2G_CUDA(cudaEventSynchronize(ctx->up_done[buf])); // last DMA out of this buffer has finished
+            slice_begin = dev_off;
+        }
+        memcpy((char *)ctx->h_up[buf] + (dev_off - slice_begin), src, bytes);
+        fill = dev_off - slice_begin + bytes;
+        return 0;
+    }
+};
+
+int b2g_upload(b2g_context *ctx, void *dst, const void *src, size_t bytes) {
+    constexpr size_t CH = B2G_UP_CHUNK;
+    if (ensure_upload_buffers(ctx))
+        return 1;
+    B2G_CUDA(cudaEventSynchronize(ctx->up_done[0]));
+    B2G_CUDA(cudaEventSynchronize(ctx->up_done[1]));
     int buf = 0;
     for (size_t off = 0; off < bytes; off += CH, buf ^= 1) {
         const size_t len = std::min(CH, bytes - off);
@@ -294,13 +337,22 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
             delete p;
             return 1;
         }
-        for (const Range &r : ar) {
-            // preserve the 16-byte phase of the host address so vector loads keep their alignment
-            if (b2g_upload(ctx, p->d_operands + r.dev_off, (const void *)r.lo, r.hi - r.lo) != 0) {
+        if (ensure_upload_buffers(ctx)) {
+            delete p;
+            return 1;
+        }
+        MirrorWriter mw{ctx, (char *)p->d_operands};
+        B2G_CUDA(cudaEventSynchronize(ctx->up_done[0]));
+        B2G_CUDA(cudaEventSynchronize(ctx->up_done[1]));
+        for (const Range &r : ar)
+            if (mw.add(r.dev_off * sizeof(double), (const void *)r.lo, r.hi - r.lo) != 0) {
                 b2g_dfree(ctx, p->d_operands);
                 delete p;
                 return 1;
             }
+        if (mw.flush()) {
+            delete p;
+            return 1;
         }
         auto locate = [&ar](uintptr_t ptr) -> const Range & {
             size_t lo = 0, hi = ar.size();
