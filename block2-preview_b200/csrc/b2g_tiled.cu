@@ -153,7 +153,7 @@ template <class Cfg, bool A_KC>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
 phase2_kernel(const P2Window *__restrict__ wins, const P2Seg *__restrict__ segs, const Unit *__restrict__ units,
               int n_units, unsigned int *__restrict__ counter, const double *__restrict__ wbuf,
-              double *__restrict__ v, double scale) {
+              double *__restrict__ v, double scale, double *__restrict__ pbuf) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_unit;
     int wm0, wn0;
@@ -184,19 +184,35 @@ phase2_kernel(const P2Window *__restrict__ wins, const P2Seg *__restrict__ segs,
             for (int ni = 0; ni < Cfg::NI; ni++)
                 acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
         mainloop<Cfg, A_KC, false>(src, smem, acc, wm0, wn0, mi_n, ni_n, src.m_valid >= Cfg::BM && src.n_valid >= Cfg::BN);
-        double *out = v + win.c_off;
+        if (un.poff >= 0) {
+            // deterministic mode: the K-chunk partial goes to its own tile slot; reduce_kernel sums
+            // the slots of a sigma tile in chunk order
+            double *part = pbuf + un.poff;
 #pragma unroll
-        for (int mi = 0; mi < Cfg::MI; mi++)
+            for (int mi = 0; mi < Cfg::MI; mi++)
 #pragma unroll
-            for (int ni = 0; ni < Cfg::NI; ni++) {
-                const int r = src.row0 + wm0 + mi * 8 + lr, cc = src.col0 + wn0 + ni * 8 + lc * 2;
-                if (mi < mi_n && ni < ni_n && r < win.m1) {
-                    if (cc < win.n0)
-                        atomicAdd(out + (size_t)r * win.ldc + cc, scale * acc[mi][ni][0]);
-                    if (cc + 1 < win.n0)
-                        atomicAdd(out + (size_t)r * win.ldc + cc + 1, scale * acc[mi][ni][1]);
+                for (int ni = 0; ni < Cfg::NI; ni++) {
+                    const int r = wm0 + mi * 8 + lr, cc = wn0 + ni * 8 + lc * 2;
+                    if (mi < mi_n && ni < ni_n) {
+                        part[r * Cfg::BN + cc] = acc[mi][ni][0];
+                        part[r * Cfg::BN + cc + 1] = acc[mi][ni][1];
+                    }
                 }
-            }
+        } else {
+            double *out = v + win.c_off;
+#pragma unroll
+            for (int mi = 0; mi < Cfg::MI; mi++)
+#pragma unroll
+                for (int ni = 0; ni < Cfg::NI; ni++) {
+                    const int r = src.row0 + wm0 + mi * 8 + lr, cc = src.col0 + wn0 + ni * 8 + lc * 2;
+                    if (mi < mi_n && ni < ni_n && r < win.m1) {
+                        if (cc < win.n0)
+                            atomicAdd(out + (size_t)r * win.ldc + cc, scale * acc[mi][ni][0]);
+                        if (cc + 1 < win.n0)
+                            atomicAdd(out + (size_t)r * win.ldc + cc + 1, scale * acc[mi][ni][1]);
+                    }
+                }
+        }
         u = s_unit; // written before the barriers of the main loop
         __syncthreads();
     }
@@ -216,6 +232,40 @@ __global__ void __launch_bounds__(256) wsum_kernel(const SumTask *__restrict__ t
             for (int j = 0; j < k.nsrc; j++)
                 s += wbuf[k.src[j] + k.start + e];
             d[e] = s;
+        }
+    }
+}
+
+// ------------------------------ sigma reduce --------------------------------
+// Deterministic mode: sigma tile += scale * sum over its K-chunk partials, in chunk order; every
+// sigma element is written by exactly one thread, so the matvec is bit-reproducible run to run.
+constexpr int RED_SPLIT = 8; // CTAs per sigma tile
+__global__ void __launch_bounds__(256)
+reduce_kernel(const OutTile *__restrict__ tiles, int n_tiles, const int64_t *__restrict__ part_off,
+              const P2Window *__restrict__ wins, const double *__restrict__ pbuf, double *__restrict__ v,
+              double scale) {
+    for (int job = blockIdx.x; job < n_tiles * RED_SPLIT; job += gridDim.x) {
+        const OutTile ot = tiles[job / RED_SPLIT];
+        const int part = job % RED_SPLIT;
+        const P2Window win = wins[ot.win];
+        const int rows = min(ot.bm, win.m1 - ot.row0), cols = min(ot.bn, win.n0 - ot.col0);
+        const int total = rows * ot.bn, chunk = (total + RED_SPLIT - 1) / RED_SPLIT;
+        const int e_end = min(total, (part + 1) * chunk);
+        double *out = v + win.c_off + (size_t)ot.row0 * win.ldc + ot.col0;
+        for (int e = part * chunk + threadIdx.x; e < e_end; e += 256) {
+            const int r = e / ot.bn, c = e - r * ot.bn;
+            if (c < cols) {
+                double s = 0.0;
+                int p = ot.part_begin;
+                for (; p + 4 <= ot.part_end; p += 4) { // fixed summation order, four loads in flight
+                    const double x0 = pbuf[part_off[p] + e], x1 = pbuf[part_off[p + 1] + e],
+                                 x2 = pbuf[part_off[p + 2] + e], x3 = pbuf[part_off[p + 3] + e];
+                    s = (((s + x0) + x1) + x2) + x3;
+                }
+                for (; p < ot.part_end; p++)
+                    s += pbuf[part_off[p] + e];
+                out[(size_t)r * win.ldc + c] += scale * s;
+            }
         }
     }
 }
@@ -290,6 +340,15 @@ struct TiledPlan {
     SumTask *d_sum = nullptr;
     int n_sum = 0;
     double sum_bytes = 0;
+    // deterministic sigma accumulation
+    OutTile *d_tiles = nullptr;
+    int64_t *d_part_off = nullptr;
+    double *d_pbuf = nullptr;
+    int n_tiles = 0;
+    // sigma windows may overlap (a block and its sub-windows): tiles are ordered by the colour of
+    // their window in the interval-overlap graph and each colour is reduced by its own launch
+    std::vector<std::pair<int, int>> tile_ranges;
+    size_t pbuf_doubles = 0;
     P1Pair *d_p1 = nullptr;
     P2Window *d_win = nullptr;
     P2Seg *d_seg = nullptr;
@@ -326,7 +385,7 @@ template <class Cfg, bool L> static int launch_p2(const LaunchGroup &g, const Ti
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::THREADS, Cfg::SMEM_BYTES);
     const int grid = std::min(g.n_units, ctx->sm_count * std::max(per_sm, 1));
     kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(tp.d_win, tp.d_seg, g.d_units, g.n_units, counter,
-                                                                tp.d_wbuf, v, scale);
+                                                                tp.d_wbuf, v, scale, tp.d_pbuf);
     return 0;
 }
 
@@ -402,7 +461,7 @@ int b2g_tiled_build(b2g_plan *p) {
             for (const Strip &cs : split_cols(q.n0)) {
                 const int c = cfg_of(rs.tile, cs.tile);
                 groups[std::make_tuple(1, c, p1[i].tb0)].push_back(
-                    HostUnit{Unit{(int)i, rs.origin, cs.origin, 0, 0}, (double)rs.tile * cs.tile * (q.k0 + 2 * BK),
+                    HostUnit{Unit{(int)i, rs.origin, cs.origin, 0, 0, 0, -1}, (double)rs.tile * cs.tile * (q.k0 + 2 * BK),
                              2.0 * std::min(rs.tile, q.m0 - rs.origin) * std::min(cs.tile, q.n0 - cs.origin) * q.k0});
             }
     }
@@ -433,7 +492,7 @@ int b2g_tiled_build(b2g_plan *p) {
                 for (const Strip &rs : rsv)
                     for (const Strip &cs : csv)
                         groups[std::make_tuple(2, cfg_of(rs.tile, cs.tile), lay)].push_back(
-                            HostUnit{Unit{(int)w, rs.origin, cs.origin, (int)s0, (int)s1},
+                            HostUnit{Unit{(int)w, rs.origin, cs.origin, (int)s0, (int)s1, 0, -1},
                                      (double)rs.tile * cs.tile * (double)(ksum + 2 * BK),
                                      2.0 * std::min(rs.tile, wins[w].m1 - rs.origin) *
                                          std::min(cs.tile, wins[w].n0 - cs.origin) * (double)ksum});
@@ -492,6 +551,87 @@ int b2g_tiled_build(b2g_plan *p) {
     if (b2g_dmalloc(ctx, (void **)&tp->d_wbuf, std::max<size_t>(tp->wbuf_doubles, 2) * sizeof(double)))
         return 1;
     tp->to_free.push_back(tp->d_wbuf);
+    // deterministic sigma accumulation: one partial slot per phase-2 unit, grouped by sigma tile
+    // (a tile collects partials from both operand layouts), slots in K-chunk order
+    const char *env_atomic = getenv("B2G_ATOMIC_SIGMA");
+    std::vector<OutTile> tiles;
+    std::vector<int64_t> part_off;
+    if (!(env_atomic && env_atomic[0] == '1')) {
+        std::map<std::tuple<int, int, int>, std::vector<std::pair<int, HostUnit *>>> by_tile; // (win,row0,col0)
+        for (auto &kv : groups)
+            if (std::get<0>(kv.first) == 2)
+                for (HostUnit &hu : kv.second)
+                    by_tile[std::make_tuple(hu.u.idx, hu.u.row0, hu.u.col0)].push_back(
+                        std::make_pair(std::get<1>(kv.first), &hu));
+        // colour the windows so that windows sharing sigma elements never share a launch
+        std::vector<int> colour(wins.size(), 0);
+        {
+            std::vector<int> order(wins.size());
+            std::iota(order.begin(), order.end(), 0);
+            auto lo = [&wins](int w) { return (int64_t)wins[w].c_off; };
+            auto hi = [&wins](int w) {
+                return (int64_t)wins[w].c_off + (int64_t)(wins[w].m1 - 1) * wins[w].ldc + wins[w].n0;
+            };
+            std::sort(order.begin(), order.end(), [&](int x, int y) { return lo(x) < lo(y); });
+            std::vector<std::pair<int64_t, int>> active; // (hi, colour)
+            for (int w : order) {
+                std::vector<char> used(active.size() + 1, 0);
+                std::vector<std::pair<int64_t, int>> keep_a;
+                for (auto &a : active)
+                    if (a.first > lo(w)) {
+                        keep_a.push_back(a);
+                        if (a.second < (int)used.size())
+                            used[a.second] = 1;
+                    }
+                int c = 0;
+                while (c < (int)used.size() && used[c])
+                    c++;
+                colour[w] = c;
+                keep_a.push_back(std::make_pair(hi(w), c));
+                active.swap(keep_a);
+            }
+        }
+        std::vector<std::pair<int, std::tuple<int, int, int>>> tile_order;
+        for (auto &kv : by_tile)
+            tile_order.push_back(std::make_pair(colour[std::get<0>(kv.first)], kv.first));
+        std::stable_sort(tile_order.begin(), tile_order.end(),
+                         [](const std::pair<int, std::tuple<int, int, int>> &x,
+                            const std::pair<int, std::tuple<int, int, int>> &y) { return x.first < y.first; });
+        size_t poff = 0;
+        for (auto &to : tile_order) {
+            auto kvit = by_tile.find(to.second);
+            auto &kv = *kvit;
+            if (tp->tile_ranges.empty() || to.first != (int)tp->tile_ranges.size() - 1) {
+                while ((int)tp->tile_ranges.size() <= to.first)
+                    tp->tile_ranges.push_back(std::make_pair((int)tiles.size(), (int)tiles.size()));
+            }
+            auto &lst = kv.second;
+            std::stable_sort(lst.begin(), lst.end(),
+                             [](const std::pair<int, HostUnit *> &x, const std::pair<int, HostUnit *> &y) {
+                                 return x.second->u.seg_begin < y.second->u.seg_begin;
+                             });
+            const int c = lst[0].first;
+            OutTile ot{std::get<0>(kv.first), std::get<1>(kv.first), std::get<2>(kv.first), kCfg[c].bm, kCfg[c].bn,
+                       (int)part_off.size(), 0, 0};
+            for (auto &pr : lst) {
+                pr.second->u.poff = (int64_t)poff;
+                part_off.push_back((int64_t)poff);
+                poff += (size_t)kCfg[c].bm * kCfg[c].bn;
+            }
+            ot.part_end = (int)part_off.size();
+            tiles.push_back(ot);
+            tp->tile_ranges[to.first].second = (int)tiles.size();
+        }
+        tp->pbuf_doubles = poff;
+        tp->n_tiles = (int)tiles.size();
+        if (upload(tiles.data(), tiles.size() * sizeof(OutTile), (void **)&tp->d_tiles))
+            return 1;
+        if (upload(part_off.data(), part_off.size() * sizeof(int64_t), (void **)&tp->d_part_off))
+            return 1;
+        if (b2g_dmalloc(ctx, (void **)&tp->d_pbuf, std::max<size_t>(poff, 2) * sizeof(double)))
+            return 1;
+        tp->to_free.push_back(tp->d_pbuf);
+    }
     std::vector<std::vector<Unit>> keep; // host copies must outlive the async copies
     for (auto &kv : groups) {
         auto &hu = kv.second;
@@ -605,6 +745,20 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
         if (rc)
             return rc;
         ctx->launches++;
+        if (end())
+            return 1;
+    }
+    if (tp->n_tiles > 0) {
+        if (begin("sigma_reduce", 0.0, tp->n_tiles))
+            return 1;
+        for (const auto &rg : tp->tile_ranges) {
+            const int nt = rg.second - rg.first;
+            if (nt <= 0)
+                continue;
+            reduce_kernel<<<std::min(nt * RED_SPLIT, ctx->sm_count * 16), 256, 0, ctx->stream>>>(
+                tp->d_tiles + rg.first, nt, tp->d_part_off, tp->d_win, tp->d_pbuf, v_dev, scale);
+            ctx->launches++;
+        }
         if (end())
             return 1;
     }

@@ -57,6 +57,14 @@ struct Unit {            // one CTA-tile x K-chunk
     int32_t idx;         // phase 1: pair index; phase 2: window index
     int32_t row0, col0;  // origin of the tile inside the output matrix (elements)
     int32_t seg_begin, seg_end; // phase 2: segment range (phase 1: unused)
+    int32_t pad;
+    int64_t poff;        // phase 2, deterministic mode: element offset of this unit's partial tile; else -1
+};
+
+struct OutTile {         // phase 2, deterministic mode: one sigma tile and its K-chunk partials
+    int32_t win, row0, col0, bm, bn;
+    int32_t part_begin, part_end; // range in the partial-offset array, in K-chunk order
+    int32_t pad;
 };
 
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem, bool valid) {

@@ -95,6 +95,92 @@ def test_matvec_matches_oracle_on_random_lists(b2g, ctx, seed, maxdim):
     plan.close()
 
 
+def shared_operator_list(rng, reps=(1, 2, 4, 5, 9), dims=((70, 33), (9, 140), (130, 66), (5, 3), (64, 64))):
+    """Pair lists in which several pairs write the same sigma window THROUGH THE SAME operator block
+    A1 (and some share c window and B0 too): the structure the W pre-sum merges
+    (sum_p A1 W_p = A1 sum_p W_p).  Run lengths 1..9 cover the 4-pair merge limit."""
+    rows, coff, voff, aoff = [], 0, 0, 0
+    for (m1, n0), nrep in zip(dims, reps):
+        ldc1 = n0 + 2
+        for ta1 in (0, 1):
+            m0 = int(rng.integers(1, 90))
+            lda1 = (m1 if ta1 else m0) + 1
+            a1_off, a1len = aoff, ((m0 if ta1 else m1) - 1) * lda1 + (m1 if ta1 else m0)
+            aoff += a1len
+            for r in range(nrep):
+                k0 = int(rng.integers(1, 50))
+                tb0 = int(rng.integers(2))
+                ldb0 = (k0 if tb0 else n0)
+                b0len = ((n0 if tb0 else k0) - 1) * ldb0 + (k0 if tb0 else n0)
+                lda0 = k0 + int(rng.integers(0, 3))
+                rows.append(dict(ta0=0, tb0=tb0, m0=m0, n0=n0, k0=k0, lda0=lda0, ldb0=ldb0, ldc0=n0, ta1=ta1, tb1=0,
+                                 m1=m1, n1=n0, k1=m0, lda1=lda1, ldb1=n0, ldc1=ldc1, alpha0=1.0, beta0=0.0,
+                                 alpha1=float(rng.standard_normal()), beta1=1.0, a0_off=coff, b0_arena=0,
+                                 b0_off=aoff, a1_arena=0, a1_off=a1_off, c1_off=voff, w_off=0))
+                aoff += b0len
+                coff += (m0 - 1) * lda0 + k0
+                if r % 3 == 2:   # duplicate the previous pair exactly except for alpha1 (shared c window and B0)
+                    dup = dict(rows[-1]); dup["alpha1"] = float(rng.standard_normal()); rows.append(dup)
+        voff += (m1 - 1) * ldc1 + n0
+    p = {k: np.array([r[k] for r in rows]) for k in rows[0]}
+    for k in sd.I32_NAMES:
+        p[k] = p[k].astype(np.int32)
+    for k in sd.I64_NAMES:
+        p[k] = p[k].astype(np.int64)
+    mw = int((p["m0"].astype(np.int64) * p["n0"]).max())
+    nf = int((p["m0"].astype(np.int64) * p["n0"] * p["k0"] + p["m1"].astype(np.int64) * p["n1"] * p["k1"]).sum())
+    d = sd.SeqDump(npairs=len(rows), csize=coff, vsize=voff, max_work=mw, nflop_mnk=nf, site=0, bond_dim=0,
+                   n_sites=0, ndav_ref=0, has_eigs=False, e_ref=0.0, const_e=0.0, t_ref_matvec=0.0, conv_thrd=0.0,
+                   arena_sizes=np.array([aoff], dtype=np.int64), p=p)
+    d.arenas = rng.standard_normal(aoff)
+    d.c = rng.standard_normal(coff)
+    return d
+
+
+@pytest.mark.parametrize("no_wsum", ["0", "1"])
+def test_shared_operator_blocks_are_merged_correctly(b2g, ctx, monkeypatch, no_wsum):
+    monkeypatch.setenv("B2G_NO_WSUM", no_wsum)
+    d = shared_operator_list(np.random.default_rng(33))
+    want = sd.replay(d, nthreads=4)
+    plan = b2g.SeqPlan.from_seqfile(ctx, as_seqfile(b2g, d), d.arenas)
+    for scale in (1.0, -2.5):
+        got = np.zeros(d.vsize)
+        plan(d.c, got, scale)
+        assert rel(got, scale * want) < TOL
+    plan.close()
+
+
+def test_matvec_is_repeatable_on_one_plan(b2g, ctx):
+    """W is pre-summed in place: a second replay on the same plan must rebuild it, not re-add it."""
+    d = shared_operator_list(np.random.default_rng(34))
+    plan = b2g.SeqPlan.from_seqfile(ctx, as_seqfile(b2g, d), d.arenas)
+    a, b_ = np.zeros(d.vsize), np.zeros(d.vsize)
+    plan(d.c, a)
+    plan(d.c, b_)
+    assert rel(a, b_) < 1e-14 and rel(a, sd.replay(d)) < TOL
+    plan.close()
+
+
+def test_sigma_is_bit_reproducible_and_atomic_route_agrees(b2g, ctx, monkeypatch):
+    """Default route: per-chunk partial tiles summed in fixed order -> identical bits run to run.
+    B2G_ATOMIC_SIGMA=1 keeps the RED.ADD route (same value within rounding)."""
+    d = random_pair_list(np.random.default_rng(41), maxdim=260, n_out=5, n_terms=14)
+    plan = b2g.SeqPlan.from_seqfile(ctx, as_seqfile(b2g, d), d.arenas)
+    runs = []
+    for _ in range(3):
+        out = np.zeros(d.vsize)
+        plan(d.c, out)
+        runs.append(out)
+    assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2])
+    plan.close()
+    monkeypatch.setenv("B2G_ATOMIC_SIGMA", "1")
+    plan = b2g.SeqPlan.from_seqfile(ctx, as_seqfile(b2g, d), d.arenas)
+    out = np.zeros(d.vsize)
+    plan(d.c, out)
+    assert rel(out, runs[0]) < 1e-13 and rel(out, sd.replay(d, nthreads=4)) < TOL
+    plan.close()
+
+
 def test_generic_kernel_route_matches_oracle(b2g, ctx, monkeypatch):
     """B2G_FORCE_GENERIC=1 keeps the one-CTA-per-pair kernel: the anchor of the tiled path."""
     monkeypatch.setenv("B2G_FORCE_GENERIC", "1")
