@@ -34,7 +34,7 @@ EXPORTS = [
     "b2g_last_error", "b2g_device_count", "b2g_context_create", "b2g_context_destroy",
     "b2g_context_launches", "b2g_context_stream", "b2g_context_synchronize",
     "b2g_plan_create", "b2g_plan_destroy", "b2g_plan_get_stats", "b2g_seq_matvec",
-    "b2g_seq_matvec_dev", "b2g_plan_profile", "b2g_dgemm_batch", "b2g_davidson", "b2g_comm_unique_id",
+    "b2g_seq_matvec_dev", "b2g_plan_profile", "b2g_pairs_execute", "b2g_dgemm_batch", "b2g_davidson", "b2g_comm_unique_id",
     "b2g_comm_init", "b2g_comm_destroy", "b2g_allreduce_sum", "b2g_malloc", "b2g_free",
     "b2g_memcpy_h2d", "b2g_memcpy_d2h", "b2g_memset_zero",
 ]
@@ -90,6 +90,7 @@ def lib() -> ctypes.CDLL:
         L.b2g_seq_matvec_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_double]
         L.b2g_plan_profile.argtypes = [c_void_p, c_void_p, c_void_p, c_double, POINTER(KernelStat), c_int,
                                        POINTER(c_int)]
+        L.b2g_pairs_execute.argtypes = [c_void_p, POINTER(_Batch), POINTER(_Batch), c_int64, POINTER(PlanStats)]
         L.b2g_dgemm_batch.argtypes = [c_void_p, c_int64] + [c_void_p] * 13
         L.b2g_davidson.argtypes = [c_void_p, c_void_p, c_void_p, c_double, c_double, c_int, c_int, c_int, c_int,
                                    POINTER(c_double), POINTER(c_int)]
@@ -125,6 +126,24 @@ def _ptrs(a) -> np.ndarray:
 
 def _p(arr: np.ndarray, ct):
     return arr.ctypes.data_as(POINTER(ct))
+
+
+def _make_batches(batch0: dict, batch1: dict):
+    structs, keep = [], []
+    for bt in (batch0, batch1):
+        arrs = {k: _i32(bt[k]) for k in ("ta", "tb", "m", "n", "k", "lda", "ldb", "ldc")}
+        arrs.update({k: _f64(bt[k]) for k in ("alpha", "beta")})
+        arrs.update({k: _ptrs(bt[k]) for k in ("a", "b", "c")})
+        keep.append(arrs)
+        s = _Batch()
+        s.count = len(arrs["m"])
+        for k in ("ta", "tb", "m", "n", "k", "lda", "ldb", "ldc"):
+            setattr(s, k, _p(arrs[k], c_int32))
+        s.alpha, s.beta = _p(arrs["alpha"], c_double), _p(arrs["beta"], c_double)
+        for k in ("a", "b", "c"):
+            setattr(s, k, ctypes.cast(arrs[k].ctypes.data, POINTER(c_void_p)))
+        structs.append(s)
+    return structs, keep
 
 
 class Context:
@@ -171,6 +190,15 @@ class Context:
     def allreduce_sum(self, dev_ptr: int, count: int) -> None:
         _check(lib().b2g_allreduce_sum(self._h, c_void_p(dev_ptr), count), "b2g_allreduce_sum")
 
+    def pairs_execute(self, batch0: dict, batch1: dict, max_work: int) -> PlanStats:
+        """Run a chained-pair list with ALL operands in host memory once (tensor_rotate lists):
+        W_i = alpha0*op(A0_i)*op(B0_i); C1_i += alpha1*op(A1_i)*W_i, results added into the host C1."""
+        structs, keep = _make_batches(batch0, batch1)
+        st = PlanStats()
+        _check(lib().b2g_pairs_execute(self._h, byref(structs[0]), byref(structs[1]), max_work, byref(st)),
+               "b2g_pairs_execute")
+        return st
+
     def dgemm_batch(self, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, group_size) -> None:
         """Grouped GEMM list on device pointers (cblas_dgemm_batch signature)."""
         ta, tb, m, n, k, lda, ldb, ldc, gs = map(_i32, (ta, tb, m, n, k, lda, ldb, ldc, group_size))
@@ -192,20 +220,7 @@ class SeqPlan:
         self.ctx = ctx
         self._keep = keepalive
         self._h = c_void_p()
-        structs, keep = [], []
-        for bt in (batch0, batch1):
-            arrs = {k: _i32(bt[k]) for k in ("ta", "tb", "m", "n", "k", "lda", "ldb", "ldc")}
-            arrs.update({k: _f64(bt[k]) for k in ("alpha", "beta")})
-            arrs.update({k: _ptrs(bt[k]) for k in ("a", "b", "c")})
-            keep.append(arrs)
-            s = _Batch()
-            s.count = len(arrs["m"])
-            for k in ("ta", "tb", "m", "n", "k", "lda", "ldb", "ldc"):
-                setattr(s, k, _p(arrs[k], c_int32))
-            s.alpha, s.beta = _p(arrs["alpha"], c_double), _p(arrs["beta"], c_double)
-            for k in ("a", "b", "c"):
-                setattr(s, k, ctypes.cast(arrs[k].ctypes.data, POINTER(c_void_p)))
-            structs.append(s)
+        structs, keep = _make_batches(batch0, batch1)
         _check(lib().b2g_plan_create(ctx._h, byref(structs[0]), byref(structs[1]), max_work, csize, vsize,
                                      operand_space, byref(self._h)), "b2g_plan_create")
         self.csize, self.vsize = csize, vsize

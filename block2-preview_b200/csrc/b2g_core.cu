@@ -283,7 +283,7 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
         B2GPair &q = hp[(size_t)i];
         q.b0 = b0->b[i], q.a1 = b1->a[i];
         q.alpha0 = b0->alpha[i], q.alpha1 = b1->alpha[i];
-        q.a0_off = (int32_t)a0_off, q.c1_off = (int32_t)c1_off;
+        q.a0_off = (int64_t)a0_off, q.c1_off = (int64_t)c1_off;
         q.m0 = m0, q.n0 = n0, q.k0 = k0, q.m1 = m1;
         q.lda0 = b0->lda[i], q.ldb0 = b0->ldb[i], q.lda1 = b1->lda[i], q.ldc1 = b1->ldc[i];
         q.flags = (ta0 ? B2G_F_TA0 : 0) | (tb0 ? B2G_F_TB0 : 0) | (ta1 ? B2G_F_TA1 : 0);
@@ -497,5 +497,189 @@ extern "C" int b2g_seq_matvec(b2g_plan *p, const double *c_host, double *v_host,
     B2G_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int64_t i = 0; i < p->vsize; i++)
         v_host[i] += ctx->h_stage[i];
+    return 0;
+}
+
+// ------------------------------------------------------------------ rotation lists
+
+extern "C" int b2g_pairs_execute(b2g_context *ctx, const b2g_batch *b0, const b2g_batch *b1, int64_t max_work,
+                                 b2g_plan_stats *stats) {
+    if (!ctx || !b0 || !b1) {
+        b2g_set_error("b2g_pairs_execute: null argument");
+        return 1;
+    }
+    if (b0->count != b1->count) {
+        b2g_set_error("b2g_pairs_execute: batch[0] and batch[1] differ in length");
+        return 1;
+    }
+    B2G_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = b0->count;
+    if (n == 0)
+        return 0;
+    auto t0 = std::chrono::steady_clock::now();
+    b2g_plan *p = new b2g_plan();
+    p->ctx = ctx, p->npairs = n, p->max_work = max_work;
+    std::vector<B2GPair> &hp = p->h_pairs;
+    hp.resize((size_t)n);
+    std::vector<Range> in_rg, out_rg;
+    in_rg.reserve((size_t)3 * n), out_rg.reserve((size_t)n);
+    int64_t nflop = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (!valid_trans(b0->ta[i]) || !valid_trans(b0->tb[i]) || !valid_trans(b1->ta[i]) ||
+            !valid_trans(b1->tb[i])) {
+            b2g_set_error("b2g_pairs_execute: transpose flag is not N/T");
+            delete p;
+            return 1;
+        }
+        const bool ta0 = is_trans(b0->ta[i]), tb0 = is_trans(b0->tb[i]), ta1 = is_trans(b1->ta[i]),
+                   tb1 = is_trans(b1->tb[i]);
+        const int m0 = b0->m[i], n0 = b0->n[i], k0 = b0->k[i], m1 = b1->m[i], n1 = b1->n[i], k1 = b1->k[i];
+        if ((const void *)b0->c[i] != (const void *)b1->b[i] || ta0 || tb1 || k1 != m0 || n1 != n0 ||
+            b0->ldc[i] != n0 || b1->ldb[i] != n0 || b0->beta[i] != 0.0 || b1->beta[i] != 1.0) {
+            b2g_set_error("b2g_pairs_execute: pair " + std::to_string(i) +
+                          " is not a chained W = A0*B0, C1 += A1*W pair");
+            delete p;
+            return 1;
+        }
+        B2GPair &q = hp[(size_t)i];
+        q.b0 = b0->b[i], q.a1 = b1->a[i];
+        q.alpha0 = b0->alpha[i], q.alpha1 = b1->alpha[i];
+        q.a0_off = (int64_t)(uintptr_t)b0->a[i], q.c1_off = (int64_t)(uintptr_t)b1->c[i]; // host addresses for now
+        q.m0 = m0, q.n0 = n0, q.k0 = k0, q.m1 = m1;
+        q.lda0 = b0->lda[i], q.ldb0 = b0->ldb[i], q.lda1 = b1->lda[i], q.ldc1 = b1->ldc[i];
+        q.flags = (tb0 ? B2G_F_TB0 : 0) | (ta1 ? B2G_F_TA1 : 0);
+        q.pad = 0;
+        nflop += (int64_t)m0 * n0 * k0 + (int64_t)m1 * n1 * k1;
+        auto add = [](std::vector<Range> &v, const void *ptr, size_t ext) {
+            if (ext)
+                v.push_back(Range{(uintptr_t)ptr, (uintptr_t)ptr + ext * sizeof(double), 0});
+        };
+        add(in_rg, b0->a[i], extent(m0, k0, q.lda0));
+        add(in_rg, q.b0, extent(tb0 ? n0 : k0, tb0 ? k0 : n0, q.ldb0));
+        add(in_rg, q.a1, extent(ta1 ? k1 : m1, ta1 ? m1 : k1, q.lda1));
+        add(out_rg, b1->c[i], extent(m1, n1, q.ldc1));
+    }
+    auto merge = [](std::vector<Range> &rg, size_t &total) {
+        std::sort(rg.begin(), rg.end(), [](const Range &x, const Range &y) { return x.lo < y.lo; });
+        std::vector<Range> ar;
+        for (const Range &r : rg) {
+            if (!ar.empty() && r.lo <= ar.back().hi)
+                ar.back().hi = std::max(ar.back().hi, r.hi);
+            else
+                ar.push_back(r);
+        }
+        total = 0;
+        for (Range &r : ar) {
+            r.dev_off = total;
+            total += (r.hi - r.lo) / sizeof(double);
+            total = (total + 1) & ~(size_t)1;
+        }
+        rg.swap(ar);
+    };
+    size_t in_total = 0, out_total = 0;
+    merge(in_rg, in_total), merge(out_rg, out_total);
+    auto locate = [](const std::vector<Range> &ar, uintptr_t ptr) -> const Range & {
+        size_t lo = 0, hi = ar.size();
+        while (hi - lo > 1) {
+            size_t mid = (lo + hi) / 2;
+            if (ar[mid].lo <= ptr)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        return ar[lo];
+    };
+    // an output block must not also be an input of the same list
+    for (const Range &o : out_rg) {
+        const Range &r = locate(in_rg, o.lo);
+        const Range *nx = (&r + 1 < in_rg.data() + in_rg.size()) ? &r + 1 : nullptr;
+        if ((r.lo <= o.lo && o.lo < r.hi) || (o.lo <= r.lo && r.lo < o.hi) || (nx && nx->lo < o.hi && nx->lo >= o.lo)) {
+            b2g_set_error("b2g_pairs_execute: an output block aliases an input block");
+            delete p;
+            return 1;
+        }
+    }
+    double *d_in = nullptr, *d_out = nullptr;
+    int rc = 0;
+    auto fail = [&](const std::string &msg) {
+        if (!msg.empty())
+            b2g_set_error(msg);
+        b2g_dfree(ctx, d_in), b2g_dfree(ctx, d_out);
+        b2g_plan_destroy(p);
+        return 1;
+    };
+    if (b2g_dmalloc(ctx, (void **)&d_in, in_total * sizeof(double)) ||
+        b2g_dmalloc(ctx, (void **)&d_out, out_total * sizeof(double)))
+        return fail("");
+    if (ensure_upload_buffers(ctx))
+        return fail("");
+    if (cudaMemsetAsync(d_out, 0, out_total * sizeof(double), ctx->stream) != cudaSuccess)
+        return fail("b2g_pairs_execute: memset failed");
+    {
+        MirrorWriter mw{ctx, (char *)d_in};
+        cudaEventSynchronize(ctx->up_done[0]), cudaEventSynchronize(ctx->up_done[1]);
+        for (const Range &r : in_rg)
+            if (mw.add(r.dev_off * sizeof(double), (const void *)r.lo, r.hi - r.lo))
+                return fail("");
+        if (mw.flush())
+            return fail("");
+    }
+    for (B2GPair &q : hp) {
+        const Range &ra0 = locate(in_rg, (uintptr_t)q.a0_off);
+        q.a0_off = (int64_t)(ra0.dev_off + ((uintptr_t)q.a0_off - ra0.lo) / sizeof(double));
+        const Range &rb = locate(in_rg, (uintptr_t)q.b0);
+        q.b0 = d_in + rb.dev_off + ((uintptr_t)q.b0 - rb.lo) / sizeof(double);
+        const Range &ra = locate(in_rg, (uintptr_t)q.a1);
+        q.a1 = d_in + ra.dev_off + ((uintptr_t)q.a1 - ra.lo) / sizeof(double);
+        const Range &rc1 = locate(out_rg, (uintptr_t)q.c1_off);
+        q.c1_off = (int64_t)(rc1.dev_off + ((uintptr_t)q.c1_off - rc1.lo) / sizeof(double));
+    }
+    p->csize = (int64_t)in_total, p->vsize = (int64_t)out_total;
+    const double t_up = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (b2g_tiled_build(p))
+        return fail("");
+    rc = b2g_tiled_launch(p, d_in, d_out, 1.0);
+    if (rc)
+        return fail("");
+    // results: device -> pinned staging -> += into the host blocks (beta = 1 of the recorded GEMMs)
+    {
+        const size_t CH = B2G_UP_CHUNK / sizeof(double);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+            return fail("b2g_pairs_execute: kernel execution failed");
+        for (const Range &r : out_rg) {
+            const size_t len = (r.hi - r.lo) / sizeof(double);
+            double *host = (double *)r.lo;
+            for (size_t off = 0; off < len; off += CH) {
+                const size_t m = std::min(CH, len - off);
+                if (cudaMemcpyAsync(ctx->h_up[0], d_out + r.dev_off + off, m * sizeof(double), cudaMemcpyDeviceToHost,
+                                    ctx->stream) != cudaSuccess ||
+                    cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+                    return fail("b2g_pairs_execute: result download failed");
+                const double *src = (const double *)ctx->h_up[0];
+                const int nt = m > ((size_t)1 << 16) ? ctx->up_threads : 1;
+                const size_t slice = (m + nt - 1) / nt;
+                std::vector<std::thread> th;
+                for (int t = 1; t < nt; t++) {
+                    const size_t lo = std::min(m, slice * t), hi = std::min(m, slice * (t + 1));
+                    if (hi > lo)
+                        th.emplace_back([=]() {
+                            for (size_t j = lo; j < hi; j++)
+                                host[off + j] += src[j];
+                        });
+                }
+                for (size_t j = 0; j < std::min(m, slice); j++)
+                    host[off + j] += src[j];
+                for (auto &x : th)
+                    x.join();
+            }
+        }
+    }
+    if (stats) {
+        *stats = p->stats;
+        stats->pairs = n, stats->nflop_mnk = nflop, stats->operand_doubles = (int64_t)in_total;
+        stats->csize = (int64_t)in_total, stats->vsize = (int64_t)out_total, stats->upload_seconds = t_up;
+    }
+    b2g_dfree(ctx, d_in), b2g_dfree(ctx, d_out);
+    b2g_plan_destroy(p);
     return 0;
 }

@@ -6,20 +6,21 @@
 #include <string>
 #include <vector>
 
-// One GEMM pair of the H.C replay list, device layout (80 bytes).
+// One GEMM pair of the H.C replay list, device layout (88 bytes).
 //   W[m0 x n0]        = alpha0 * op(c + a0_off)[m0 x k0] * op(b0)[k0 x n0]
 //   v + c1_off [m1 x n0] += alpha1 * op(a1)[m1 x m0] * W          (k1 == m0, n1 == n0)
 struct B2GPair {
     const double *b0; // operator block of GEMM 0 (device)
     const double *a1; // operator block of GEMM 1 (device)
     double alpha0, alpha1;
-    int32_t a0_off, c1_off; // |psi| < 2^31 is asserted by the reference (effective_hamiltonian.hpp:413)
+    int64_t a0_off, c1_off; // offsets into c / sigma (|psi| < 2^31 for H.C, effective_hamiltonian.hpp:413;
+                            // 64-bit because the rotation lists address whole operator arenas)
     int32_t m0, n0, k0, m1;
     int32_t lda0, ldb0, lda1, ldc1;
     uint32_t flags; // bit0 ta0, bit1 tb0, bit2 ta1
     uint32_t pad;
 };
-static_assert(sizeof(B2GPair) == 80, "B2GPair layout");
+static_assert(sizeof(B2GPair) == 88, "B2GPair layout");
 
 #define B2G_F_TA0 1u
 #define B2G_F_TB0 2u

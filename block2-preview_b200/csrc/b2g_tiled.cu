@@ -423,13 +423,13 @@ int b2g_tiled_build(b2g_plan *p) {
         P1Pair &d = p1[i];
         d.b0 = q.b0, d.w_off = (int64_t)woff, d.alpha = q.alpha0 * q.alpha1;
         d.a_off = q.a0_off, d.lda = q.lda0, d.ldb = q.ldb0;
-        d.m0 = q.m0, d.n0 = q.n0, d.k0 = q.k0, d.tb0 = (q.flags & B2G_F_TB0) ? 1 : 0, d.pad = 0;
+        d.m0 = q.m0, d.n0 = q.n0, d.k0 = q.k0, d.tb0 = (q.flags & B2G_F_TB0) ? 1 : 0;
         woff += (size_t)q.m0 * q.n0;
     }
     tp->wbuf_doubles = woff;
 
     // ---- windows: pairs that accumulate into the same sigma window
-    std::map<std::tuple<int, int, int, int>, int> wid;
+    std::map<std::tuple<int64_t, int, int, int>, int> wid;
     std::vector<P2Window> wins;
     std::vector<std::vector<size_t>> wpairs[2]; // [layout][window] -> pair indices
     for (size_t i = 0; i < n; i++) {
@@ -440,7 +440,7 @@ int b2g_tiled_build(b2g_plan *p) {
         if (it == wid.end()) {
             w = (int)wins.size();
             wid[key] = w;
-            wins.push_back(P2Window{q.c1_off, q.ldc1, q.m1, q.n0});
+            wins.push_back(P2Window{q.c1_off, q.ldc1, q.m1, q.n0, 0});
             wpairs[0].emplace_back(), wpairs[1].emplace_back();
         } else
             w = it->second;

@@ -31,14 +31,15 @@ struct P1Pair {          // phase 1: one pair
     const double *b0;    // operator block (device)
     int64_t w_off;       // element offset of W_p in the workspace (row-major m0 x n0, ld = n0)
     double alpha;        // alpha0 * alpha1
-    int32_t a_off;       // window offset inside c
+    int64_t a_off;       // window offset inside c
     int32_t lda, ldb;
     int32_t m0, n0, k0;
-    int32_t tb0, pad;
+    int32_t tb0;
 };
 
 struct P2Window {        // phase 2: one sigma window
-    int32_t c_off, ldc, m1, n0;
+    int64_t c_off;
+    int32_t ldc, m1, n0, pad;
 };
 
 struct P2Seg {           // phase 2: one K-segment (= one pair)

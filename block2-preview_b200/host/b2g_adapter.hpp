@@ -41,6 +41,11 @@ struct Session {
     bool verify = false;
     double max_matvec_err = 0;
     size_t n_verified = 0;
+    // renormalisation (left_rotate / right_rotate) on the device
+    bool gpu_rotate = false;
+    double t_rotate = 0, max_rotate_err = 0;
+    size_t n_rotate = 0, rotate_pairs = 0;
+    double rotate_flops = 0;
     explicit Session(int device = 0) {
         if (b2g_context_create(device, &ctx) != 0)
             throw std::runtime_error(std::string("b2g_context_create: ") + b2g_last_error());
@@ -105,6 +110,80 @@ template <typename S> struct GPUTensorFunctions : TensorFunctions<S, double> {
                 csize = cmat->total_memory, vsize = vmat->total_memory;
             }
         }
+    }
+    // Renormalisation c = bra^T . a . ket of every operator of a block (core/tensor_functions.hpp:
+    // 2365-2403).  The reference's own OperatorFunctions::tensor_rotate enumerates the sector blocks
+    // and records one rotate() pair per block (operator_functions.hpp:175-210); in Auto mode nothing
+    // is executed at record time, so the list is handed to b2g_pairs_execute instead of
+    // seq->auto_perform().  c is zero-initialised by allocate() exactly as in the stock method.
+    void rotate_on_device(const shared_ptr<OperatorTensor<S, FL>> &a, const shared_ptr<SparseMatrix<S, FL>> &mpst_bra,
+                          const shared_ptr<SparseMatrix<S, FL>> &mpst_ket, shared_ptr<OperatorTensor<S, FL>> &c,
+                          const shared_ptr<Symbolic<S>> &names, bool trans) const {
+        Timer t;
+        t.get_time();
+        for (auto &p : c->ops)
+            p.second->allocate(p.second->info);
+        auto &seq = opf->seq;
+        if (seq->batch[0]->gp.size() != 0 || seq->batch[1]->gp.size() != 0)
+            throw std::runtime_error("b2g: recorder not empty at rotate");
+        const SeqTypes saved = seq->mode;
+        seq->mode = SeqTypes::Auto; // record only
+        for (size_t i = 0; i < names->data.size(); i++)
+            if (names->data[i]->get_type() != OpTypes::Zero) {
+                auto pa = abs_value(names->data[i]);
+                opf->tensor_rotate(a->ops.at(pa), c->ops.at(pa), mpst_bra, mpst_ket, trans);
+            }
+        seq->mode = saved;
+        if (seq->batch[1]->gp.size() != 0) {
+            b2g_batch b0 = as_b2g_batch(*seq->batch[0]), b1 = as_b2g_batch(*seq->batch[1]);
+            if (session->verify) { // keep a CPU copy of the result to compare with
+                vector<vector<double>> ref;
+                for (auto &p : c->ops)
+                    ref.emplace_back(p.second->data, p.second->data + p.second->total_memory);
+                if (b2g_pairs_execute(session->ctx, &b0, &b1, 0, nullptr) != 0)
+                    throw std::runtime_error(std::string("b2g_pairs_execute: ") + b2g_last_error());
+                vector<vector<double>> gpu;
+                size_t z = 0;
+                for (auto &p : c->ops) {
+                    gpu.emplace_back(p.second->data, p.second->data + p.second->total_memory);
+                    memcpy(p.second->data, ref[z++].data(), sizeof(double) * p.second->total_memory);
+                }
+                seq->mode = SeqTypes::Auto;
+                seq->auto_perform(); // the reference executor on the same list
+                seq->mode = saved;
+                double num = 0, den = 0;
+                z = 0;
+                for (auto &p : c->ops) {
+                    for (size_t j = 0; j < p.second->total_memory; j++)
+                        num += (gpu[z][j] - p.second->data[j]) * (gpu[z][j] - p.second->data[j]),
+                            den += p.second->data[j] * p.second->data[j];
+                    memcpy(p.second->data, gpu[z++].data(), sizeof(double) * p.second->total_memory);
+                }
+                session->max_rotate_err = max(session->max_rotate_err, den > 0 ? sqrt(num / den) : sqrt(num));
+            } else {
+                b2g_plan_stats st;
+                if (b2g_pairs_execute(session->ctx, &b0, &b1, 0, &st) != 0)
+                    throw std::runtime_error(std::string("b2g_pairs_execute: ") + b2g_last_error());
+                session->rotate_pairs += (size_t)st.pairs, session->rotate_flops += 2.0 * (double)st.nflop_mnk;
+                seq->cumulative_nflop += (size_t)st.nflop_mnk;
+            }
+        }
+        seq->clear();
+        session->t_rotate += t.get_time(), session->n_rotate++;
+    }
+    void left_rotate(const shared_ptr<OperatorTensor<S, FL>> &a, const shared_ptr<SparseMatrix<S, FL>> &mpst_bra,
+                     const shared_ptr<SparseMatrix<S, FL>> &mpst_ket,
+                     shared_ptr<OperatorTensor<S, FL>> &c) const override {
+        if (!session->gpu_rotate || session->recording)
+            return TensorFunctions<S, FL>::left_rotate(a, mpst_bra, mpst_ket, c);
+        rotate_on_device(a, mpst_bra, mpst_ket, c, a->lmat, false);
+    }
+    void right_rotate(const shared_ptr<OperatorTensor<S, FL>> &a, const shared_ptr<SparseMatrix<S, FL>> &mpst_bra,
+                      const shared_ptr<SparseMatrix<S, FL>> &mpst_ket,
+                      shared_ptr<OperatorTensor<S, FL>> &c) const override {
+        if (!session->gpu_rotate || session->recording)
+            return TensorFunctions<S, FL>::right_rotate(a, mpst_bra, mpst_ket, c);
+        rotate_on_device(a, mpst_bra, mpst_ket, c, a->rmat, true);
     }
     void build_plan() const {
         Timer t;

@@ -20,7 +20,7 @@ using namespace std;
 struct Args {
     string fcidump, pg = "d2h", occ = "", scratch = "/tmp/b2g_scratch", davidson = "device";
     int bond = 250, n_sweeps = 6, threads = 8, seed = 0, device = 0;
-    bool compare = false, verify = false;
+    bool compare = false, verify = false, gpu_rotate = false;
     double conv = 1e-7, noise = 1e-5;
     size_t dsize_gb = 8;
 };
@@ -111,9 +111,10 @@ int main(int argc, char **argv) {
         else if (k == "--dsize") a.dsize_gb = (size_t)atol(nxt().c_str());
         else if (k == "--compare") a.compare = true;
         else if (k == "--verify") a.verify = true;
+        else if (k == "--gpu-rotate") a.gpu_rotate = true;
         else {
             fprintf(stderr, "usage: b2g_dmrg --fcidump F [--pg d2h] [--bond M] [--nsweeps n] [--threads t] "
-                            "[--davidson host|device] [--compare] [--verify] [--occ F] [--noise x] [--conv x]\n");
+                            "[--davidson host|device] [--compare] [--verify] [--gpu-rotate] [--occ F] [--noise x] [--conv x]\n");
             return 2;
         }
     }
@@ -150,6 +151,7 @@ int main(int argc, char **argv) {
     shared_ptr<TensorFunctions<S, double>> stock_tf = mpo->tf;
     shared_ptr<b2g_host::Session> session = b2g_host::install<S>(mpo, a.device);
     session->verify = a.verify;
+    session->gpu_rotate = a.gpu_rotate;
     RunResult gpu = run_dmrg<S>(a, mpo, hamil, target, true);
     for (size_t i = 0; i < gpu.energies.size(); i++) {
         if (a.compare && i < ref.energies.size())
@@ -165,11 +167,14 @@ int main(int argc, char **argv) {
     printf("{\"mode\": \"b2g_dmrg\", \"davidson\": \"%s\", \"bond\": %d, \"sweeps\": %zu, \"t_gpu\": %.3f, "
            "\"t_ref\": %.3f, \"threads\": %d, \"e_gpu\": %.12f, \"e_ref\": %.12f, \"max_sweep_diff\": %.3e, "
            "\"plans\": %zu, \"host_matvecs\": %zu, \"t_plan\": %.3f, \"t_host_matvec\": %.3f, \"launches\": %lld, "
-           "\"matvec_sites_verified\": %zu, \"max_matvec_rel_err\": %.3e}\n",
+           "\"matvec_sites_verified\": %zu, \"max_matvec_rel_err\": %.3e, \"gpu_rotate\": %d, \"rotations\": %zu, "
+           "\"t_rotate\": %.3f, \"rotate_gflop\": %.3f, \"max_rotate_rel_err\": %.3e}\n",
            a.davidson.c_str(), a.bond, gpu.energies.size(), gpu.total, ref.total, a.threads,
            gpu.energies.empty() ? 0.0 : gpu.energies.back(), ref.energies.empty() ? 0.0 : ref.energies.back(),
            maxdiff, session->n_plan, session->n_matvec, session->t_plan, session->t_matvec,
-           (long long)b2g_context_launches(session->ctx), session->n_verified, session->max_matvec_err);
+           (long long)b2g_context_launches(session->ctx), session->n_verified, session->max_matvec_err,
+           (int)a.gpu_rotate, session->n_rotate, session->t_rotate, session->rotate_flops * 1e-9,
+           session->max_rotate_err);
     fflush(stdout);
     _exit(0);
 }

@@ -12,6 +12,8 @@
  *                           core/batch_gemm.hpp:1570-1691 (= TensorFunctions::operator(),
  *                           core/tensor_functions.hpp:59-62)
  *   b2g_plan_destroy     <- EffectiveHamiltonian::post_precompute  :247-253
+ *   b2g_pairs_execute    <- OperatorFunctions::tensor_rotate lists executed by BatchGEMMSeq::auto_perform /
+ *                           simple_perform (left_rotate / right_rotate, core/tensor_functions.hpp:2365-2403)
  *   b2g_dgemm_batch      <- cblas_xgemm_batch / BatchGEMM::perform  core/batch_gemm.hpp:81-111, 339-357
  *   b2g_davidson         <- IterativeMatrixFunctions<double>::davidson (k = 1, Normal type,
  *                           Olsen preconditioner)  core/iterative_matrix_functions.hpp:864-1173, 93-108
@@ -99,6 +101,16 @@ int b2g_seq_matvec_dev(b2g_plan *plan, const double *c_dev, double *v_dev, doubl
 /* One matvec with CUDA events between the kernel launches (measurement only; synchronous). */
 int b2g_plan_profile(b2g_plan *plan, const double *c_dev, double *v_dev, double scale,
                      b2g_kernel_stat *out, int capacity, int *count);
+
+/* Execute once a recorded chained-pair list whose operands are ALL host pointers - the list
+ * OperatorFunctions::tensor_rotate records through BatchGEMMSeq::rotate when an environment block
+ * is renormalised (core/operator_functions.hpp:175-210, core/tensor_functions.hpp:2365-2403):
+ *     W_i = alpha0 * op(A0_i) * op(B0_i);      C1_i += alpha1 * op(A1_i) * W_i
+ * A0/B0/A1 ranges are mirrored to HBM, the products run through the same tile engine as the H.C
+ * replay, and the results are added into the host C1 blocks (beta = 1).  Synchronous.
+ * stats (optional): pairs, nflop_mnk, operand_doubles (inputs), upload_seconds. */
+int b2g_pairs_execute(b2g_context *ctx, const b2g_batch *batch0, const b2g_batch *batch1,
+                      int64_t max_work, b2g_plan_stats *stats);
 
 /* Grouped GEMM list with the cblas_dgemm_batch signature (device pointers), asynchronous. */
 int b2g_dgemm_batch(b2g_context *ctx, int64_t group_count, const int32_t *ta, const int32_t *tb,

@@ -305,3 +305,26 @@ def test_dgemm_batch_matches_oracle(b2g, ctx):
                       keep[7].ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
                       keep[8].ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
     assert np.allclose(got, want, rtol=0, atol=1e-11)
+
+
+@pytest.mark.parametrize("seed,maxdim", [(51, 30), (52, 120), (53, 260)])
+def test_rotation_list_with_host_operands_matches_oracle(b2g, ctx, seed, maxdim):
+    """b2g_pairs_execute: the chained-pair lists tensor_rotate records (all operands real host
+    pointers, every pair its own output block), results added into the host C blocks."""
+    rng = np.random.default_rng(seed)
+    d = random_pair_list(rng, maxdim=maxdim, n_out=10, n_terms=2)
+    P = d.p
+    b0o, a1o = d.operand_offsets()
+    out = rng.standard_normal(d.vsize)          # pre-existing content of C (beta = 1)
+    out0 = out.copy()
+    w = np.zeros(len(P["m0"]), dtype=np.uint64)
+    batch0 = dict(ta=P["ta0"] + 111, tb=P["tb0"] + 111, m=P["m0"], n=P["n0"], k=P["k0"], lda=P["lda0"], ldb=P["ldb0"],
+                  ldc=P["ldc0"], alpha=P["alpha0"], beta=P["beta0"], a=d.c.ctypes.data + 8 * P["a0_off"],
+                  b=d.arenas.ctypes.data + 8 * b0o, c=w)
+    batch1 = dict(ta=P["ta1"] + 111, tb=P["tb1"] + 111, m=P["m1"], n=P["n1"], k=P["k1"], lda=P["lda1"], ldb=P["ldb1"],
+                  ldc=P["ldc1"], alpha=P["alpha1"], beta=P["beta1"], a=d.arenas.ctypes.data + 8 * a1o, b=w,
+                  c=out.ctypes.data + 8 * P["c1_off"])
+    st = ctx.pairs_execute(batch0, batch1, d.max_work)
+    want = out0 + sd.replay(d, nthreads=4)
+    assert rel(out, want) < TOL
+    assert st.pairs == d.npairs and st.nflop_mnk == d.nflop_mnk

@@ -48,3 +48,16 @@ def test_h10_sto6g_sz_energy_matches_reference_run():
     assert abs(r["e_gpu"] - r["e_ref"]) < 1e-8, r          # same run, CPU path first
     assert abs(r["e_gpu"] - E_H10) < 1e-7, r               # the reference's own tolerance for this value
     assert r["max_matvec_rel_err"] < 1e-11, r
+
+
+def test_renormalisation_on_device_matches_reference_executor():
+    """--gpu-rotate: left_rotate / right_rotate lists (OperatorFunctions::tensor_rotate ->
+    BatchGEMMSeq::rotate) run through b2g_pairs_execute; --verify replays every list with the
+    reference's own auto_perform() and compares all rotated operator blocks."""
+    r = run_driver("b2g_dmrg_su2", "--fcidump", os.path.join(BUILD, "data", "N2.STO3G.FCIDUMP"), "--bond", "250",
+                   "--nsweeps", "8", "--threads", "4", "--noise", "1e-6", "--gpu-rotate", "--verify")
+    assert r["rotations"] > 0 and r["max_rotate_rel_err"] < 1e-11, r
+    assert abs(r["e_gpu"] - E_N2_1AG) < 1e-8, r
+    r = run_driver("b2g_dmrg_sz", "--fcidump", os.path.join(BUILD, "data", "H10.STO6G.R1.8.FCIDUMP"), "--bond",
+                   "300", "--nsweeps", "6", "--threads", "8", "--noise", "1e-6", "--gpu-rotate")
+    assert r["rotations"] > 0 and abs(r["e_gpu"] - E_H10) < 1e-6, r
