@@ -58,6 +58,11 @@ extern "C" int b2g_context_create(int device, b2g_context **out) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     ctx->up_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    for (int i = 0; i < b2g_context::N_SIDE; i++) {
+        B2G_CUDA(cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking));
+        B2G_CUDA(cudaEventCreateWithFlags(&ctx->side_done[i], cudaEventDisableTiming));
+    }
+    B2G_CUDA(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
     *out = ctx;
     return 0;
 }
@@ -166,6 +171,14 @@ extern "C" int b2g_context_destroy(b2g_context *ctx) {
         cudaFree(ctx->d_c);
     if (ctx->d_v)
         cudaFree(ctx->d_v);
+    for (int i = 0; i < b2g_context::N_SIDE; i++) {
+        if (ctx->side[i])
+            cudaStreamDestroy(ctx->side[i]);
+        if (ctx->side_done[i])
+            cudaEventDestroy(ctx->side_done[i]);
+    }
+    if (ctx->fork_ev)
+        cudaEventDestroy(ctx->fork_ev);
     if (ctx->stream)
         cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -39,6 +39,12 @@ struct b2g_context {
     void *nccl_comm = nullptr;
     int nranks = 1, rank = 0;
     // double-buffered pinned staging of the operand mirror (host pageable -> HBM)
+    // side streams: the per-configuration launches of one phase run concurrently (small lists
+    // do not fill the chip with any single launch)
+    static constexpr int N_SIDE = 8;
+    cudaStream_t side[N_SIDE] = {};
+    cudaEvent_t side_done[N_SIDE] = {};
+    cudaEvent_t fork_ev = nullptr;
     void *h_up[2] = {nullptr, nullptr};
     cudaEvent_t up_done[2] = {nullptr, nullptr};
     size_t up_bytes = 0;

@@ -128,15 +128,18 @@ template <class Cfg, bool A_KC> struct P2Src {
     const P2Seg *seg, *seg_end;
     const double *wbuf;
     const double *a, *b;
+    P2Seg nxt; // descriptor of the following segment, fetched one segment ahead
     int lda, n0, row0, col0, m_valid, n_valid, k_left, nsteps;
     __device__ int steps() const { return nsteps; }
-    __device__ void open() {
-        const P2Seg s = *seg;
+    __device__ void use(const P2Seg &s) {
         lda = s.lda;
         a = A_KC ? s.a1 + (size_t)row0 * lda : s.a1 + row0;
         b = wbuf + s.w_off + col0;
         k_left = s.klen;
+        if (seg + 1 < seg_end)
+            nxt = seg[1];
     }
+    __device__ void open() { use(*seg); }
     __device__ void issue(double *As, double *Bs) {
         load_tile<Cfg::BM, Cfg::THREADS, A_KC>(As, a, lda, m_valid, k_left);
         load_tile<Cfg::BN, Cfg::THREADS, false>(Bs, b, n0, n_valid, k_left);
@@ -145,7 +148,7 @@ template <class Cfg, bool A_KC> struct P2Src {
             a += A_KC ? BK : (size_t)BK * lda;
             b += (size_t)BK * n0;
         } else if (++seg < seg_end)
-            open();
+            use(nxt);
     }
 };
 
@@ -360,7 +363,7 @@ struct TiledPlan {
 };
 
 template <class Cfg, bool L> static int launch_p1(const LaunchGroup &g, const TiledPlan &tp, b2g_context *ctx,
-                                                  unsigned int *counter, const double *c) {
+                                                  cudaStream_t stream, unsigned int *counter, const double *c) {
     auto kern = phase1_kernel<Cfg, L>;
     static bool attr = false;
     if (!attr) {
@@ -370,11 +373,12 @@ template <class Cfg, bool L> static int launch_p1(const LaunchGroup &g, const Ti
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::THREADS, Cfg::SMEM_BYTES);
     const int grid = std::min(g.n_units, ctx->sm_count * std::max(per_sm, 1));
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(tp.d_p1, g.d_units, g.n_units, counter, c, tp.d_wbuf);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tp.d_p1, g.d_units, g.n_units, counter, c, tp.d_wbuf);
     return 0;
 }
 template <class Cfg, bool L> static int launch_p2(const LaunchGroup &g, const TiledPlan &tp, b2g_context *ctx,
-                                                  unsigned int *counter, double *v, double scale) {
+                                                  cudaStream_t stream, unsigned int *counter, double *v,
+                                                  double scale) {
     auto kern = phase2_kernel<Cfg, L>;
     static bool attr = false;
     if (!attr) {
@@ -384,7 +388,7 @@ template <class Cfg, bool L> static int launch_p2(const LaunchGroup &g, const Ti
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::THREADS, Cfg::SMEM_BYTES);
     const int grid = std::min(g.n_units, ctx->sm_count * std::max(per_sm, 1));
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(tp.d_win, tp.d_seg, g.d_units, g.n_units, counter,
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tp.d_win, tp.d_seg, g.d_units, g.n_units, counter,
                                                                 tp.d_wbuf, v, scale, tp.d_pbuf);
     return 0;
 }
@@ -465,6 +469,22 @@ int b2g_tiled_build(b2g_plan *p) {
                              2.0 * std::min(rs.tile, q.m0 - rs.origin) * std::min(cs.tile, q.n0 - cs.origin) * q.k0});
             }
     }
+    // K-chunk: 2048 for the big lists; shorter when the list is small so that phase 2 still
+    // spreads over the whole chip (few sigma windows, each with a long chain of short segments)
+    int64_t kchunk_eff = kchunk;
+    if (!env_kc) {
+        double tile_k = 0;
+        for (int lay = 0; lay < 2; lay++)
+            for (size_t w = 0; w < wins.size(); w++) {
+                double ks = 0;
+                for (size_t idx : wpairs[lay][w])
+                    ks += hp[idx].m0;
+                tile_k += ks * (double)split_rows(wins[w].m1).size() * (double)split_cols(wins[w].n0).size();
+            }
+        const double want_units = 24.0 * ctx->sm_count;
+        kchunk_eff = (int64_t)std::min<double>(2048.0, std::max(128.0, tile_k / want_units));
+        kchunk_eff = (kchunk_eff + 15) / 16 * 16;
+    }
     std::vector<P2Seg> segs;
     std::vector<SumTask> sums;
     const char *env_merge = getenv("B2G_NO_WSUM");
@@ -521,7 +541,7 @@ int b2g_tiled_build(b2g_plan *p) {
                     }
                     segs.push_back(P2Seg{q.a1, p1[lst[z]].w_off, q.lda1, q.m0});
                     ksum += q.m0;
-                    if (ksum >= kchunk)
+                    if (ksum >= kchunk_eff)
                         flush(segs.size());
                 }
                 z = z1;
@@ -692,11 +712,29 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
             B2G_CUDA(cudaEventRecord(recs.back().e1, ctx->stream));
         return 0;
     };
+    // Without profiling, the launches of one phase are forked onto side streams and joined before
+    // the next phase; with profiling everything stays on the context stream (timed one by one).
+    // Forking pays when no single launch fills the chip (measured: up to ~2x on the C2 / H10 lists,
+    // -5 % on the 2 TFLOP Cr2 list where the big persistent kernels then compete), hence the bound.
+    const bool fork = stats == nullptr && 2.0 * (double)p->stats.nflop_mnk < 3e11;
+    int n_forked = 0;
+    auto join = [&]() -> int {
+        for (int i = 0; i < std::min(n_forked, (int)b2g_context::N_SIDE); i++)
+            B2G_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->side_done[i], 0));
+        n_forked = 0;
+        return 0;
+    };
+    if (fork)
+        B2G_CUDA(cudaEventRecord(ctx->fork_ev, ctx->stream));
     int gi = 0;
     bool summed = false;
     for (const LaunchGroup &g : tp->groups) {
         if (g.phase == 2 && !summed) {
             summed = true;
+            if (fork) {
+                if (join())
+                    return 1;
+            }
             if (tp->n_sum > 0) {
                 if (begin("wsum", 0.0, tp->n_sum))
                     return 1;
@@ -706,6 +744,14 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
                 if (end())
                     return 1;
             }
+            if (fork)
+                B2G_CUDA(cudaEventRecord(ctx->fork_ev, ctx->stream));
+        }
+        cudaStream_t gs = ctx->stream;
+        if (fork) {
+            gs = ctx->side[n_forked % b2g_context::N_SIDE];
+            if (n_forked < b2g_context::N_SIDE)
+                B2G_CUDA(cudaStreamWaitEvent(gs, ctx->fork_ev, 0));
         }
         unsigned int *counter = tp->d_counters + gi++;
         int rc = 0;
@@ -717,37 +763,43 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
 #define B2G_DISPATCH(PH, CFG, LAY, CALL)                                                \
     if (g.phase == PH && g.cfg == CFG && g.layout == LAY)                               \
         rc = CALL;
-        B2G_DISPATCH(1, 0, 0, (launch_p1<Cfg0, false>(g, *tp, ctx, counter, c_dev)))
-        B2G_DISPATCH(1, 0, 1, (launch_p1<Cfg0, true>(g, *tp, ctx, counter, c_dev)))
-        B2G_DISPATCH(1, 1, 0, (launch_p1<Cfg1, false>(g, *tp, ctx, counter, c_dev)))
-        B2G_DISPATCH(1, 1, 1, (launch_p1<Cfg1, true>(g, *tp, ctx, counter, c_dev)))
-        B2G_DISPATCH(1, 2, 0, (launch_p1<Cfg2, false>(g, *tp, ctx, counter, c_dev)))
-        B2G_DISPATCH(1, 2, 1, (launch_p1<Cfg2, true>(g, *tp, ctx, counter, c_dev)))
-        B2G_DISPATCH(1, 3, 0, (launch_p1<Cfg3, false>(g, *tp, ctx, counter, c_dev)))
-        B2G_DISPATCH(1, 3, 1, (launch_p1<Cfg3, true>(g, *tp, ctx, counter, c_dev)))
-        B2G_DISPATCH(1, 4, 0, (launch_p1<Cfg4, false>(g, *tp, ctx, counter, c_dev)))
-        B2G_DISPATCH(1, 4, 1, (launch_p1<Cfg4, true>(g, *tp, ctx, counter, c_dev)))
-        B2G_DISPATCH(1, 5, 0, (launch_p1<Cfg5, false>(g, *tp, ctx, counter, c_dev)))
-        B2G_DISPATCH(1, 5, 1, (launch_p1<Cfg5, true>(g, *tp, ctx, counter, c_dev)))
-        B2G_DISPATCH(2, 0, 0, (launch_p2<Cfg0, true>(g, *tp, ctx, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 0, 1, (launch_p2<Cfg0, false>(g, *tp, ctx, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 1, 0, (launch_p2<Cfg1, true>(g, *tp, ctx, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 1, 1, (launch_p2<Cfg1, false>(g, *tp, ctx, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 2, 0, (launch_p2<Cfg2, true>(g, *tp, ctx, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 2, 1, (launch_p2<Cfg2, false>(g, *tp, ctx, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 3, 0, (launch_p2<Cfg3, true>(g, *tp, ctx, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 3, 1, (launch_p2<Cfg3, false>(g, *tp, ctx, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 4, 0, (launch_p2<Cfg4, true>(g, *tp, ctx, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 4, 1, (launch_p2<Cfg4, false>(g, *tp, ctx, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 5, 0, (launch_p2<Cfg5, true>(g, *tp, ctx, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 5, 1, (launch_p2<Cfg5, false>(g, *tp, ctx, counter, v_dev, scale)))
+        B2G_DISPATCH(1, 0, 0, (launch_p1<Cfg0, false>(g, *tp, ctx, gs, counter, c_dev)))
+        B2G_DISPATCH(1, 0, 1, (launch_p1<Cfg0, true>(g, *tp, ctx, gs, counter, c_dev)))
+        B2G_DISPATCH(1, 1, 0, (launch_p1<Cfg1, false>(g, *tp, ctx, gs, counter, c_dev)))
+        B2G_DISPATCH(1, 1, 1, (launch_p1<Cfg1, true>(g, *tp, ctx, gs, counter, c_dev)))
+        B2G_DISPATCH(1, 2, 0, (launch_p1<Cfg2, false>(g, *tp, ctx, gs, counter, c_dev)))
+        B2G_DISPATCH(1, 2, 1, (launch_p1<Cfg2, true>(g, *tp, ctx, gs, counter, c_dev)))
+        B2G_DISPATCH(1, 3, 0, (launch_p1<Cfg3, false>(g, *tp, ctx, gs, counter, c_dev)))
+        B2G_DISPATCH(1, 3, 1, (launch_p1<Cfg3, true>(g, *tp, ctx, gs, counter, c_dev)))
+        B2G_DISPATCH(1, 4, 0, (launch_p1<Cfg4, false>(g, *tp, ctx, gs, counter, c_dev)))
+        B2G_DISPATCH(1, 4, 1, (launch_p1<Cfg4, true>(g, *tp, ctx, gs, counter, c_dev)))
+        B2G_DISPATCH(1, 5, 0, (launch_p1<Cfg5, false>(g, *tp, ctx, gs, counter, c_dev)))
+        B2G_DISPATCH(1, 5, 1, (launch_p1<Cfg5, true>(g, *tp, ctx, gs, counter, c_dev)))
+        B2G_DISPATCH(2, 0, 0, (launch_p2<Cfg0, true>(g, *tp, ctx, gs, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 0, 1, (launch_p2<Cfg0, false>(g, *tp, ctx, gs, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 1, 0, (launch_p2<Cfg1, true>(g, *tp, ctx, gs, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 1, 1, (launch_p2<Cfg1, false>(g, *tp, ctx, gs, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 2, 0, (launch_p2<Cfg2, true>(g, *tp, ctx, gs, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 2, 1, (launch_p2<Cfg2, false>(g, *tp, ctx, gs, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 3, 0, (launch_p2<Cfg3, true>(g, *tp, ctx, gs, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 3, 1, (launch_p2<Cfg3, false>(g, *tp, ctx, gs, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 4, 0, (launch_p2<Cfg4, true>(g, *tp, ctx, gs, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 4, 1, (launch_p2<Cfg4, false>(g, *tp, ctx, gs, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 5, 0, (launch_p2<Cfg5, true>(g, *tp, ctx, gs, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 5, 1, (launch_p2<Cfg5, false>(g, *tp, ctx, gs, counter, v_dev, scale)))
 #undef B2G_DISPATCH
         if (rc)
             return rc;
         ctx->launches++;
         if (end())
             return 1;
+        if (fork) {
+            B2G_CUDA(cudaEventRecord(ctx->side_done[n_forked % b2g_context::N_SIDE], gs));
+            n_forked++;
+        }
     }
+    if (fork && join())
+        return 1;
     if (tp->n_tiles > 0) {
         if (begin("sigma_reduce", 0.0, tp->n_tiles))
             return 1;

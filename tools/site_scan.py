@@ -18,9 +18,12 @@ b2g = b2gpkg.load()
 ctx = b2g.Context(0)
 dev = torch.device("cuda", 0)
 stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-files = sorted(glob.glob(os.path.join(ROOT, "workloads", "cr2_svp_m4000_sites", "*.b2seq.gz")),
-               key=lambda f: int(re.search(r"_s(\d+)\.", f).group(1)))
-files.insert(4, os.path.join(ROOT, "workloads", "cr2_svp_m4000_site20.b2seq.gz"))
+if len(sys.argv) > 1:
+    files = sys.argv[1:]
+else:
+    files = sorted(glob.glob(os.path.join(ROOT, "workloads", "cr2_svp_m4000_sites", "*.b2seq.gz")),
+                   key=lambda f: int(re.search(r"_s(\d+)\.", f).group(1)))
+    files.insert(4, os.path.join(ROOT, "workloads", "cr2_svp_m4000_site20.b2seq.gz"))
 rows = []
 for path in files:
     sf = b2g.load_seqfile(path)
@@ -42,11 +45,16 @@ for path in files:
     ctx.synchronize()
     ms = e0.elapsed_time(e1) / reps
     st = plan.stats
-    rows.append({"site": site, "pairs": sf.npairs, "psi": sf.csize, "operator_GB": 8e-9 * sf.operand_doubles,
+    rows.append({"file": os.path.basename(path), "site": site, "pairs": sf.npairs, "psi": sf.csize, "operator_GB": 8e-9 * sf.operand_doubles,
                  "gflop": sf.flops * 1e-9, "ms": ms, "tflops": sf.flops / (ms * 1e-3) * 1e-12,
                  "GBps_if_streamed_once": 8e-9 * (sf.operand_doubles + 2 * sf.csize) / (ms * 1e-3),
                  "launches": int(st.launches)})
     print(json.dumps(rows[-1]), flush=True)
+    if os.environ.get("SCAN_PROFILE"):
+        v.zero_()
+        torch.cuda.synchronize()
+        prof = sorted(plan.profile(c.data_ptr(), v.data_ptr(), 1.0), key=lambda x: -x[2])
+        print("   " + "; ".join(f"{n} {ms:.3f}ms u={u}" for n, fl, ms, u in prof[:12]), flush=True)
     plan.close()
     del ops, c, v
     torch.cuda.empty_cache()
