@@ -167,7 +167,19 @@ def run_b200(args) -> None:
         ctx.comm_init(world, rank, uid[0])
 
     full = b2g.load_seqfile(WORKLOAD)
-    sf = full.shard(rank, world) if world > 1 else full
+    # N > 1: the pair list rank r records under the reference's own ParallelRuleQC / ParallelMPO split
+    # (workloads/README.md); falls back to splitting the serial list by left-operator index
+    rank_file = os.path.join(ROOT, "workloads", "cr2_svp_m4000_site20_ranks",
+                             f"cr2_m4000_s20_P{world}_r{rank}.b2seq.gz")
+    sharding = "serial list"
+    if world > 1 and os.path.exists(rank_file):
+        sf = b2g.load_seqfile(rank_file)
+        sharding = "per-rank lists recorded by the reference under ParallelRuleQC (ParallelMPO, NewScheme)"
+    elif world > 1:
+        sf = full.shard(rank, world)
+        sharding = "serial list split by left-operator index (emulated ParallelRuleQC ownership)"
+    else:
+        sf = full
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     ops = torch.empty(max(sf.operand_doubles, 1), dtype=torch.float64, device=dev)
     ops.normal_(0.0, 1.0, generator=gen)
@@ -239,7 +251,8 @@ def run_b200(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(fl, op=dist.ReduceOp.SUM)
     ms_step = float(t.item()) / args.steps
-    total_flops = float(fl.item())
+    executed_flops = float(fl.item())   # what all ranks actually multiplied (the parallel scheme repeats work)
+    total_flops = full.flops            # the job: one H.C of the serial list, whatever N is
     value = total_flops / (ms_step * 1e-3) * 1e-12
 
     # end to end through the host-buffer C-ABI call (drop-in for BatchGEMMSeq::operator()):
@@ -286,8 +299,8 @@ def run_b200(args) -> None:
             "config": {"workload": WORKLOAD_NAME, "pairs": full.npairs, "wavefunction_doubles": full.csize,
                        "operator_bytes": 8 * full.operand_doubles, "flop_per_step": full.flops,
                        "l2": "inputs (operator blocks, %.1f GB per rank) larger than L2" % (8e-9 * sf.operand_doubles),
-                       "parallelism": "terms sharded over %d rank(s) by left-operator index, NCCL all-reduce of sigma"
-                                      % world},
+                       "parallelism": "%d rank(s), %s, NCCL all-reduce of sigma" % (world, sharding),
+                       "executed_flop_all_ranks": executed_flops},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": 8 * sf.csize,
                     "d2h_bytes_per_step": 8 * sf.vsize, "path_check_rel": chk},

@@ -24,6 +24,7 @@
 #include "b2g.h"
 #include "block2_core.hpp"
 #include "block2_dmrg.hpp"
+#include "b2g_shm_comm.hpp"
 #include <atomic>
 #include <stdexcept>
 
@@ -73,23 +74,34 @@ inline b2g_batch as_b2g_batch(const BatchGEMM<double> &b) {
     return r;
 }
 
-template <typename S> struct GPUTensorFunctions : TensorFunctions<S, double> {
+// Base = TensorFunctions<S,double> (serial) or ParallelTensorFunctions<S,double> (one process per
+// GPU under ParallelRuleQC: the base keeps the reference's distributed blocking logic, the matvec
+// and its sigma all-reduce run on the GPUs).
+template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTensorFunctions : Base {
     typedef double FL;
-    using TensorFunctions<S, FL>::opf;
+    using Base::opf;
     shared_ptr<Session> session;
+    shared_ptr<ParallelRule<S, FL>> prule;
     mutable b2g_plan *plan = nullptr;
     mutable bool stale = true;
     mutable size_t csize = 0, vsize = 0;
     GPUTensorFunctions(const shared_ptr<OperatorFunctions<S, FL>> &opf, const shared_ptr<Session> &session)
-        : TensorFunctions<S, FL>(opf), session(session) {}
+        : Base(opf), session(session) {}
+    GPUTensorFunctions(const shared_ptr<OperatorFunctions<S, FL>> &opf, const shared_ptr<ParallelRule<S, FL>> &rule,
+                       const shared_ptr<Session> &session)
+        : Base(opf, rule), session(session), prule(rule) {}
     ~GPUTensorFunctions() override { drop(); }
     void drop() const {
         if (plan != nullptr)
             b2g_plan_destroy(plan);
         plan = nullptr;
     }
-    shared_ptr<TensorFunctions<S, FL>> copy() const override {
-        return make_shared<GPUTensorFunctions<S>>(opf->copy(), session);
+    shared_ptr<TensorFunctions<S, FL>> copy() const override { return make_copy((Base *)nullptr); }
+    shared_ptr<TensorFunctions<S, FL>> make_copy(TensorFunctions<S, FL> *) const {
+        return make_shared<GPUTensorFunctions<S, Base>>(opf->copy(), session);
+    }
+    shared_ptr<TensorFunctions<S, FL>> make_copy(ParallelTensorFunctions<S, FL> *) const {
+        return make_shared<GPUTensorFunctions<S, Base>>(opf->copy(), prule, session);
     }
     // Top-level recording call of precompute(): run the reference's recorder, then invalidate
     // the device plan.  Nested calls (the per-term calls parallel_reduce makes on copies)
@@ -101,7 +113,7 @@ template <typename S> struct GPUTensorFunctions : TensorFunctions<S, double> {
                                  const shared_ptr<SparseMatrix<S, FL>> &vmat, S opdq,
                                  bool all_reduce) const override {
         const bool top = !session->recording.exchange(true);
-        TensorFunctions<S, FL>::tensor_product_multiply(expr, xexpr, lopt, ropt, cmat, vmat, opdq, all_reduce);
+        Base::tensor_product_multiply(expr, xexpr, lopt, ropt, cmat, vmat, opdq, all_reduce);
         if (top) {
             session->recording = false;
             if (cmat->data == nullptr && (opf->seq->mode & SeqTypes::Tasked)) {
@@ -175,14 +187,14 @@ template <typename S> struct GPUTensorFunctions : TensorFunctions<S, double> {
                      const shared_ptr<SparseMatrix<S, FL>> &mpst_ket,
                      shared_ptr<OperatorTensor<S, FL>> &c) const override {
         if (!session->gpu_rotate || session->recording)
-            return TensorFunctions<S, FL>::left_rotate(a, mpst_bra, mpst_ket, c);
+            return Base::left_rotate(a, mpst_bra, mpst_ket, c);
         rotate_on_device(a, mpst_bra, mpst_ket, c, a->lmat, false);
     }
     void right_rotate(const shared_ptr<OperatorTensor<S, FL>> &a, const shared_ptr<SparseMatrix<S, FL>> &mpst_bra,
                       const shared_ptr<SparseMatrix<S, FL>> &mpst_ket,
                       shared_ptr<OperatorTensor<S, FL>> &c) const override {
         if (!session->gpu_rotate || session->recording)
-            return TensorFunctions<S, FL>::right_rotate(a, mpst_bra, mpst_ket, c);
+            return Base::right_rotate(a, mpst_bra, mpst_ket, c);
         rotate_on_device(a, mpst_bra, mpst_ket, c, a->rmat, true);
     }
     void build_plan() const {
@@ -232,7 +244,7 @@ template <typename S> struct GPUDMRG : DMRG<S, double, double> {
     two_dot_eigs_and_perturb(const bool forward, const int i, const double davidson_conv_thrd, const double noise,
                              shared_ptr<SparseMatrixGroup<S, double>> &pket) override {
         const bool plain = device_davidson && !this->state_specific && this->projection_weights.size() == 0 &&
-                           this->metric_me == nullptr && this->context_ket == nullptr && me->para_rule == nullptr &&
+                           this->metric_me == nullptr && this->context_ket == nullptr &&
                            this->davidson_type == DavidsonTypes::Normal && this->eff_kernel == nullptr &&
                            !((this->noise_type & NoiseTypes::Perturbative) && noise != 0);
         if (!plain)
@@ -244,9 +256,18 @@ template <typename S> struct GPUDMRG : DMRG<S, double, double> {
         this->sweep_max_eff_ham_size = max(this->sweep_max_eff_ham_size, h_eff->op->get_total_memory());
         this->sweep_max_eff_wfn_size = max(this->sweep_max_eff_wfn_size, (size_t)h_eff->ket->total_memory);
         this->teff += t.get_time();
-        auto gtf = dynamic_pointer_cast<GPUTensorFunctions<S>>(h_eff->tf);
-        if (gtf == nullptr)
+        auto gtf_s = dynamic_pointer_cast<GPUTensorFunctions<S>>(h_eff->tf);
+        auto gtf_p = dynamic_pointer_cast<GPUTensorFunctions<S, ParallelTensorFunctions<S, double>>>(h_eff->tf);
+        if (gtf_s == nullptr && gtf_p == nullptr)
             throw std::runtime_error("b2g: GPUDMRG needs mpo->tf to be a GPUTensorFunctions");
+        if (gtf_p != nullptr)
+            return eigs_on_device(gtf_p, h_eff, davidson_conv_thrd, t);
+        return eigs_on_device(gtf_s, h_eff, davidson_conv_thrd, t);
+    }
+    template <typename GTF>
+    tuple<FPLS, int, size_t, double> eigs_on_device(const shared_ptr<GTF> &gtf,
+                                                    const shared_ptr<EffectiveHamiltonian<S, double>> &h_eff,
+                                                    const double davidson_conv_thrd, Timer &t) {
         frame_<double>()->activate(0);
         h_eff->precompute();
         if (gtf->session->verify && h_eff->tf->opf->seq->batch[0]->gp.size() != 0) {
@@ -256,6 +277,8 @@ template <typename S> struct GPUDMRG : DMRG<S, double, double> {
             GMatrix<double> xm(x.data(), (MKL_INT)n, 1);
             (*gtf)(xm, GMatrix<double>(y_gpu.data(), (MKL_INT)n, 1), 1.0);
             h_eff->tf->opf->seq->operator()(xm, GMatrix<double>(y_cpu.data(), (MKL_INT)n, 1), 1.0);
+            if (me->para_rule != nullptr) // the GPU result is already summed over ranks (NCCL)
+                me->para_rule->comm->allreduce_sum(y_cpu.data(), n);
             double num = 0, den = 0;
             for (size_t j = 0; j < n; j++)
                 num += (y_gpu[j] - y_cpu[j]) * (y_gpu[j] - y_cpu[j]), den += y_cpu[j] * y_cpu[j];
@@ -288,6 +311,26 @@ template <typename S>
 inline shared_ptr<Session> install(const shared_ptr<MPO<S, double>> &mpo, int device = 0) {
     shared_ptr<Session> session = make_shared<Session>(device);
     mpo->tf = make_shared<GPUTensorFunctions<S>>(mpo->tf->opf, session);
+    return session;
+}
+
+// Multi-GPU: mpo is a ParallelMPO over ParallelRuleQC (one process per GPU).  The NCCL communicator
+// of the session is created from an id that rank 0 broadcasts through the host communicator.
+template <typename S>
+inline shared_ptr<Session> install_parallel(const shared_ptr<MPO<S, double>> &mpo, int device = 0) {
+    shared_ptr<ParallelMPO<S, double>> pmpo = dynamic_pointer_cast<ParallelMPO<S, double>>(mpo);
+    if (pmpo == nullptr)
+        throw std::runtime_error("b2g: install_parallel needs a ParallelMPO");
+    shared_ptr<Session> session = make_shared<Session>(device);
+    auto comm = pmpo->rule->comm;
+    char id[128];
+    if (comm->rank == comm->root && b2g_comm_unique_id(id) != 0)
+        throw std::runtime_error(std::string("b2g_comm_unique_id: ") + b2g_last_error());
+    static_assert(sizeof(long long int) == 8, "");
+    comm->broadcast((long long int *)id, 16, comm->root);
+    if (b2g_comm_init(session->ctx, comm->size, comm->rank, id) != 0)
+        throw std::runtime_error(std::string("b2g_comm_init: ") + b2g_last_error());
+    mpo->tf = make_shared<GPUTensorFunctions<S, ParallelTensorFunctions<S, double>>>(mpo->tf->opf, pmpo->rule, session);
     return session;
 }
 

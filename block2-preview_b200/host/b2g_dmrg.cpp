@@ -19,7 +19,8 @@ using namespace std;
 
 struct Args {
     string fcidump, pg = "d2h", occ = "", scratch = "/tmp/b2g_scratch", davidson = "device";
-    int bond = 250, n_sweeps = 6, threads = 8, seed = 0, device = 0;
+    int bond = 250, n_sweeps = 6, threads = 8, seed = 0, device = 0, ranks = 1, rank = 0;
+    string shm = "b2g";
     bool compare = false, verify = false, gpu_rotate = false;
     double conv = 1e-7, noise = 1e-5;
     size_t dsize_gb = 8;
@@ -112,6 +113,9 @@ int main(int argc, char **argv) {
         else if (k == "--compare") a.compare = true;
         else if (k == "--verify") a.verify = true;
         else if (k == "--gpu-rotate") a.gpu_rotate = true;
+        else if (k == "--ranks") a.ranks = atoi(nxt().c_str());
+        else if (k == "--rank") a.rank = atoi(nxt().c_str());
+        else if (k == "--shm") a.shm = nxt();
         else {
             fprintf(stderr, "usage: b2g_dmrg --fcidump F [--pg d2h] [--bond M] [--nsweeps n] [--threads t] "
                             "[--davidson host|device] [--compare] [--verify] [--gpu-rotate] [--occ F] [--noise x] [--conv x]\n");
@@ -142,6 +146,18 @@ int main(int argc, char **argv) {
     mpo->basis = hamil->basis;
     mpo = make_shared<SimplifiedMPO<S, double>>(mpo, make_shared<RuleQC<S, double>>(), true, true,
                                                 OpNamesSet({OpNames::R, OpNames::RD}));
+    // one process per GPU: the reference's own ParallelMPO over ParallelRuleQC (parallel_mpo.hpp:150,
+    // qc_parallel_rule.hpp:44); host collectives through shared memory, sigma all-reduce over NCCL
+    if (a.ranks > 1) {
+        shared_ptr<ParallelCommunicator<S>> comm =
+            make_shared<b2g_host::ShmCommunicator<S>>(a.ranks, a.rank, a.shm);
+        shared_ptr<ParallelRule<S, double>> rule = make_shared<ParallelRuleQC<S, double>>(comm);
+        mpo = make_shared<ParallelMPO<S, double>>(mpo, rule);
+        // all ranks share the scratch directory: ParallelRule's constructor gives every rank its own
+        // prefix for distributed files and lets only the root write the common ones (parallel_rule.hpp:340)
+        if (a.rank != 0)
+            cout.setstate(ios::failbit); // like MPICommunicator (parallel_mpi.hpp:60-61)
+    }
     RunResult ref;
     if (a.compare) {
         printf("=== reference CPU path (stock TensorFunctions, %d threads) ===\n", a.threads);
@@ -149,7 +165,8 @@ int main(int argc, char **argv) {
     }
     printf("=== GPU path (b2g_host::install, davidson = %s) ===\n", a.davidson.c_str());
     shared_ptr<TensorFunctions<S, double>> stock_tf = mpo->tf;
-    shared_ptr<b2g_host::Session> session = b2g_host::install<S>(mpo, a.device);
+    shared_ptr<b2g_host::Session> session =
+        a.ranks > 1 ? b2g_host::install_parallel<S>(mpo, a.device) : b2g_host::install<S>(mpo, a.device);
     session->verify = a.verify;
     session->gpu_rotate = a.gpu_rotate;
     RunResult gpu = run_dmrg<S>(a, mpo, hamil, target, true);
@@ -164,12 +181,16 @@ int main(int argc, char **argv) {
     if (a.compare)
         for (size_t i = 0; i < min(gpu.energies.size(), ref.energies.size()); i++)
             maxdiff = max(maxdiff, fabs(gpu.energies[i] - ref.energies[i]));
-    printf("{\"mode\": \"b2g_dmrg\", \"davidson\": \"%s\", \"bond\": %d, \"sweeps\": %zu, \"t_gpu\": %.3f, "
+    if (a.rank != 0) {
+        fflush(stdout);
+        _exit(0);
+    }
+    printf("{\"mode\": \"b2g_dmrg\", \"ranks\": %d, \"davidson\": \"%s\", \"bond\": %d, \"sweeps\": %zu, \"t_gpu\": %.3f, "
            "\"t_ref\": %.3f, \"threads\": %d, \"e_gpu\": %.12f, \"e_ref\": %.12f, \"max_sweep_diff\": %.3e, "
            "\"plans\": %zu, \"host_matvecs\": %zu, \"t_plan\": %.3f, \"t_host_matvec\": %.3f, \"launches\": %lld, "
            "\"matvec_sites_verified\": %zu, \"max_matvec_rel_err\": %.3e, \"gpu_rotate\": %d, \"rotations\": %zu, "
            "\"t_rotate\": %.3f, \"rotate_gflop\": %.3f, \"max_rotate_rel_err\": %.3e}\n",
-           a.davidson.c_str(), a.bond, gpu.energies.size(), gpu.total, ref.total, a.threads,
+           a.ranks, a.davidson.c_str(), a.bond, gpu.energies.size(), gpu.total, ref.total, a.threads,
            gpu.energies.empty() ? 0.0 : gpu.energies.back(), ref.energies.empty() ? 0.0 : ref.energies.back(),
            maxdiff, session->n_plan, session->n_matvec, session->t_plan, session->t_matvec,
            (long long)b2g_context_launches(session->ctx), session->n_verified, session->max_matvec_err,

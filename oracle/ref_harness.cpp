@@ -30,6 +30,8 @@
  */
 #include "block2_core.hpp"
 #include "block2_dmrg.hpp"
+// MPI stand-in shared with the host driver (POSIX shared memory); infrastructure, not product logic
+#include "../block2-preview_b200/host/b2g_shm_comm.hpp"
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -45,7 +47,8 @@ struct Args {
         dav_max = 4000, seed = 0;
     bool with_data = true, structure_only = false, run_eigs = true;
     double conv = 1e-7, noise = 1e-5, max_gflop = 0;
-    int warmup = 1;
+    int warmup = 1, ranks = 1, rank = 0;
+    string shm = "";
     size_t dsize_gb = 8;
 };
 
@@ -87,6 +90,9 @@ static Args parse(int argc, char **argv) {
         else if (k == "--noise") a.noise = atof(nxt().c_str());
         else if (k == "--max-gflop") a.max_gflop = atof(nxt().c_str());
         else if (k == "--warmup") a.warmup = atoi(nxt().c_str());
+        else if (k == "--ranks") a.ranks = atoi(nxt().c_str());
+        else if (k == "--rank") a.rank = atoi(nxt().c_str());
+        else if (k == "--shm") a.shm = nxt();
         else if (k == "--nodata") a.with_data = false;
         else if (k == "--noeigs") a.run_eigs = false;
         else if (k == "--struct") a.structure_only = true, a.with_data = false, a.run_eigs = false;
@@ -138,14 +144,20 @@ static VirtualArena g_varena;
 /* Allocate-only TensorFunctions for --struct: same bookkeeping as the stock
  * methods (which operators get storage, tensor_functions.hpp:2842-2984,
  * 2365-2403) but no arithmetic, and storage that is never written. */
-template <typename S, typename FL>
-struct StructTensorFunctions : TensorFunctions<S, FL> {
+template <typename S, typename FL, typename Base = TensorFunctions<S, FL>>
+struct StructTensorFunctions : Base {
     typedef typename GMatrix<FL>::FP FP;
-    using TensorFunctions<S, FL>::opf;
-    StructTensorFunctions(const shared_ptr<OperatorFunctions<S, FL>> &opf)
-        : TensorFunctions<S, FL>(opf) {}
-    shared_ptr<TensorFunctions<S, FL>> copy() const override {
-        return make_shared<StructTensorFunctions<S, FL>>(opf->copy());
+    using Base::opf;
+    shared_ptr<ParallelRule<S, FL>> prule; // set when Base = ParallelTensorFunctions
+    StructTensorFunctions(const shared_ptr<OperatorFunctions<S, FL>> &opf) : Base(opf) {}
+    StructTensorFunctions(const shared_ptr<OperatorFunctions<S, FL>> &opf, const shared_ptr<ParallelRule<S, FL>> &rule)
+        : Base(opf, rule), prule(rule) {}
+    shared_ptr<TensorFunctions<S, FL>> copy() const override { return make_copy((Base *)nullptr); }
+    shared_ptr<TensorFunctions<S, FL>> make_copy(TensorFunctions<S, FL> *) const {
+        return make_shared<StructTensorFunctions<S, FL, Base>>(opf->copy());
+    }
+    shared_ptr<TensorFunctions<S, FL>> make_copy(ParallelTensorFunctions<S, FL> *) const {
+        return make_shared<StructTensorFunctions<S, FL, Base>>(opf->copy(), prule);
     }
     static void valloc(const shared_ptr<SparseMatrix<S, FL>> &m) {
         if (m->data != nullptr)
@@ -177,7 +189,7 @@ struct StructTensorFunctions : TensorFunctions<S, FL> {
                        const shared_ptr<Symbolic<S>> &cexprs = nullptr,
                        OpNamesSet delayed = OpNamesSet()) const override {
         if (a == nullptr) // first site: tiny site operators, stock code
-            TensorFunctions<S, FL>::left_assign(b, c);
+            Base::left_assign(b, c);
         else
             alloc_named(c->lmat, c, delayed);
     }
@@ -187,7 +199,7 @@ struct StructTensorFunctions : TensorFunctions<S, FL> {
                         const shared_ptr<Symbolic<S>> &cexprs = nullptr,
                         OpNamesSet delayed = OpNamesSet()) const override {
         if (a == nullptr)
-            TensorFunctions<S, FL>::right_assign(b, c);
+            Base::right_assign(b, c);
         else
             alloc_named(c->rmat, c, delayed);
     }
@@ -260,6 +272,34 @@ struct StructTensorFunctions : TensorFunctions<S, FL> {
                                  const shared_ptr<OperatorTensor<S, FL>> &ropt,
                                  const shared_ptr<SparseMatrix<S, FL>> &mat,
                                  S opdq) const override {}
+};
+
+/* ---------- one rank of a P-rank ParallelRuleQC run, without MPI ----------
+ * --ranks P --rank r builds the reference's own ParallelMPO (parallel_mpo.hpp:150, NewScheme)
+ * over ParallelRuleQC (qc_parallel_rule.hpp:44-80) for rank r of P.  Under NewScheme the blocking
+ * and rotation need no communication, so a rank can be run alone: its recorded H.C
+ * list is exactly the slice of MPO terms that rank would own, and sum_r sigma_r = sigma.  The
+ * collectives that remain (sigma / diagonal all-reduce, Davidson broadcasts) are no-ops here,
+ * which is fine for recording; the Davidson answer of such a run is not meaningful. */
+template <typename S> struct LoneRankCommunicator : ParallelCommunicator<S> {
+    LoneRankCommunicator(int size, int rank) : ParallelCommunicator<S>(size, rank, 0) {}
+    void barrier() override {}
+    void broadcast(double *, size_t, int) override {}
+    void broadcast(long double *, size_t, int) override {}
+    void broadcast(int *, size_t, int) override {}
+    void broadcast(long long int *, size_t, int) override {}
+    void broadcast(const shared_ptr<SparseMatrix<S, double>> &, int) override {}
+    void allreduce_sum(double *, size_t) override {}
+    void allreduce_sum(const shared_ptr<SparseMatrix<S, double>> &) override {}
+    void allreduce_sum(vector<S> &) override {}
+    void allreduce_min(double *, size_t) override {}
+    void allreduce_max(double *, size_t) override {}
+    void allreduce_logical_or(char *, size_t) override {}
+    void reduce_sum(double *, size_t, int) override {}
+    void reduce_sum(uint64_t *, size_t, int) override {}
+    void reduce_sum(const shared_ptr<SparseMatrix<S, double>> &, int) override {}
+    void reduce_sum(const shared_ptr<SparseMatrixGroup<S, double>> &, int) override {}
+    void waitall() override {}
 };
 
 /* ---------- dump writer ---------- */
@@ -670,9 +710,26 @@ template <typename S> static int run(const Args &args) {
         mpo, make_shared<RuleQC<S, FL>>(), true, true,
         OpNamesSet({OpNames::R, OpNames::RD}));
     printf("MPO simplified T=%.3f\n", t.get_time());
+    if (args.ranks > 1) {
+        // --shm NAME: real collectives between P concurrently running processes (full parallel DMRG on
+        // the CPU, validates the ParallelRuleQC path end to end); without it a lone rank (recording only)
+        shared_ptr<ParallelCommunicator<S>> comm;
+        if (args.shm != "")
+            comm = make_shared<b2g_host::ShmCommunicator<S>>(args.ranks, args.rank, args.shm);
+        else
+            comm = make_shared<LoneRankCommunicator<S>>(args.ranks, args.rank);
+        shared_ptr<ParallelRule<S, FL>> rule = make_shared<ParallelRuleQC<S, FL>>(comm);
+        mpo = make_shared<ParallelMPO<S, FL>>(mpo, rule);
+        printf("MPO parallelised: rank %d of %d (ParallelRuleQC, NewScheme) T=%.3f\n", args.rank, args.ranks,
+               t.get_time());
+    }
     if (args.structure_only) {
         g_varena.init((size_t)1 << 44);
-        mpo->tf = make_shared<StructTensorFunctions<S, FL>>(mpo->tf->opf);
+        if (args.ranks > 1)
+            mpo->tf = make_shared<StructTensorFunctions<S, FL, ParallelTensorFunctions<S, FL>>>(
+                mpo->tf->opf, dynamic_pointer_cast<ParallelMPO<S, FL>>(mpo)->rule);
+        else
+            mpo->tf = make_shared<StructTensorFunctions<S, FL>>(mpo->tf->opf);
     }
 
     ubond_t bond_dim = (ubond_t)args.bond;

@@ -12,3 +12,10 @@ G=../../tests/golden
 ./b2ref_sz  dump --fcidump data/H10.STO6G.R1.8.FCIDUMP --sym sz --bond 40 --sweeps 1 --site 4 --threads 4 --noise 1e-6 --out $G/h10_sz_m40_s4.b2seq
 ./b2ref_su2 dump --fcidump data/N2.STO3G.FCIDUMP --bond 30 --sweeps 0 --site 1 --threads 4 --out $G/n2_su2_m30_s1.b2seq
 ./b2ref_su2 dump --fcidump data/N2.STO3G.FCIDUMP --bond 30 --sweeps 0 --site 8 --threads 4 --out $G/n2_su2_m30_s8.b2seq
+# two concurrently running ranks of the reference's parallel DMRG (ParallelMPO over ParallelRuleQC; host
+# collectives through block2-preview_b200/host/b2g_shm_comm.hpp): each file holds the rank's own pair list
+# and the sigma the reference all-reduced over both ranks
+rm -rf /tmp/b2ref_par && mkdir -p /tmp/b2ref_par
+./b2ref_su2 dump --fcidump data/N2.STO3G.FCIDUMP --bond 40 --sweeps 0 --site 4 --threads 2 --noeigs --ranks 2 --rank 1 --shm gold --scratch /tmp/b2ref_par --out $G/n2_su2_m40_s4_P2_r1.b2seq &
+./b2ref_su2 dump --fcidump data/N2.STO3G.FCIDUMP --bond 40 --sweeps 0 --site 4 --threads 2 --noeigs --ranks 2 --rank 0 --shm gold --scratch /tmp/b2ref_par --out $G/n2_su2_m40_s4_P2_r0.b2seq
+wait

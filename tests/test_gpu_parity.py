@@ -328,3 +328,17 @@ def test_rotation_list_with_host_operands_matches_oracle(b2g, ctx, seed, maxdim)
     want = out0 + sd.replay(d, nthreads=4)
     assert rel(out, want) < TOL
     assert st.pairs == d.npairs and st.nflop_mnk == d.nflop_mnk
+
+
+def test_rank_lists_of_parallel_reference_on_gpu(b2g, ctx):
+    """The two per-rank lists the reference records under ParallelRuleQC, replayed on the GPU one
+    after the other into the same sigma: must equal the sigma the reference all-reduced."""
+    v = None
+    for r in (0, 1):
+        sf = b2g.load_seqfile(os.path.join(GOLDEN, f"n2_su2_m40_s4_P2_r{r}.b2seq"))
+        plan = b2g.SeqPlan.from_seqfile(ctx, sf, sf.arenas)
+        if v is None:
+            v = np.zeros(sf.vsize)
+        plan(sf.c, v)
+        plan.close()
+    assert rel(v, sf.v_ref) < TOL

@@ -102,3 +102,15 @@ def test_dgemm_batch_oracle_against_numpy():
         ref = al * opA @ opB + be * C0[:, :n]
         assert np.allclose(C[:, :n], ref, atol=1e-13)
         assert np.array_equal(C[:, n:], C0[:, n:])
+
+
+def test_rank_lists_of_parallel_reference_sum_to_its_allreduced_sigma():
+    """Two ranks of the reference's own parallel DMRG (ParallelRuleQC / ParallelMPO) each record their
+    slice of the MPO terms; the reference all-reduces sigma (parallel_tensor_functions.hpp:51-55).
+    The per-rank replays of the oracle must add up to that sigma."""
+    r0 = sd.load(os.path.join(GOLDEN, "n2_su2_m40_s4_P2_r0.b2seq"))
+    r1 = sd.load(os.path.join(GOLDEN, "n2_su2_m40_s4_P2_r1.b2seq"))
+    assert np.array_equal(r0.c, r1.c) and np.array_equal(r0.v_ref, r1.v_ref)
+    assert r0.npairs != r1.npairs or not np.array_equal(r0.p["alpha1"], r1.p["alpha1"])
+    s = sd.replay(r0) + sd.replay(r1)
+    assert np.linalg.norm(s - r0.v_ref) < 1e-13 * np.linalg.norm(r0.v_ref)
