@@ -61,3 +61,22 @@ def test_renormalisation_on_device_matches_reference_executor():
     r = run_driver("b2g_dmrg_sz", "--fcidump", os.path.join(BUILD, "data", "H10.STO6G.R1.8.FCIDUMP"), "--bond",
                    "300", "--nsweeps", "6", "--threads", "8", "--noise", "1e-6", "--gpu-rotate")
     assert r["rotations"] > 0 and abs(r["e_gpu"] - E_H10) < 1e-6, r
+
+
+def test_two_rank_dmrg_over_parallel_rule_qc_and_nccl(b2g):
+    """One process per GPU: the reference's ParallelMPO over ParallelRuleQC, host collectives through
+    shared memory, sigma all-reduce over NCCL.  Needs two GPUs (NCCL refuses two ranks on one device)."""
+    if b2g.lib().b2g_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = os.path.join(BUILD, "b2g_dmrg_su2")
+    if not os.path.exists(exe):
+        pytest.skip("driver not built")
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+    out = subprocess.run([os.path.join(ROOT, "tools", "run_ranks.sh"), "2", exe, "--fcidump",
+                          os.path.join(BUILD, "data", "N2.STO3G.FCIDUMP"), "--bond", "250", "--nsweeps", "8",
+                          "--threads", "4", "--noise", "1e-6", "--verify", "--scratch", "/tmp/b2g_test_scratch2"],
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    r = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert r["ranks"] == 2 and abs(r["e_gpu"] - E_N2_1AG) < 1e-8, r
+    assert r["matvec_sites_verified"] > 0 and r["max_matvec_rel_err"] < 1e-11, r
