@@ -151,8 +151,11 @@ def run_b200(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout and would precede the JSON line
+    # NCCL prints its version banner on stdout at communicator creation; stdout (fd 1) is pointed at
+    # stderr for the whole run and restored for the one JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
@@ -332,7 +335,10 @@ def run_b200(args) -> None:
             except Exception as exc:  # the baseline is reported, never needed by the GPU path
                 line["cpu_baseline"] = {"value": None, "unit": "TFLOP/s", "cores": host_threads(), "kind": "reference",
                                         "sample": f"unavailable: {exc}"}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     plan.close()
     if world > 1:
         dist.barrier()
