@@ -61,7 +61,7 @@ typedef struct b2g_plan_stats {
     int64_t operand_doubles;/* distinct operator doubles referenced (mirrored or resident) */
     int64_t arenas;         /* merged contiguous operand ranges */
     int64_t launches;       /* kernel launches per matvec */
-    int64_t n_small, n_large; /* pairs routed to the warp-per-pair / CTA-tiled kernels */
+    int64_t n_small, n_large; /* pairs executed by the generic one-CTA-per-pair kernel / by the DMMA tile engine */
     double upload_seconds;  /* host->device mirror time of the operands */
 } b2g_plan_stats;
 
