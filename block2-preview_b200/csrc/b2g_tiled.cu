@@ -65,11 +65,11 @@ template <class Cfg, bool B_KC> struct P1Src {
     int lda, ldb, m_valid, n_valid, k_left, nsteps;
     __device__ int steps() const { return nsteps; }
     __device__ void issue(double *As, double *Bs) {
-        load_tile<Cfg::BM, Cfg::THREADS, true>(As, a, lda, m_valid, k_left);
-        load_tile<Cfg::BN, Cfg::THREADS, B_KC>(Bs, b, ldb, n_valid, k_left);
-        a += BK;
-        b += B_KC ? BK : (size_t)BK * ldb;
-        k_left -= BK;
+        load_tile<Cfg::BM, Cfg::THREADS, true, Cfg::BK>(As, a, lda, m_valid, k_left);
+        load_tile<Cfg::BN, Cfg::THREADS, B_KC, Cfg::BK>(Bs, b, ldb, n_valid, k_left);
+        a += Cfg::BK;
+        b += B_KC ? Cfg::BK : (size_t)Cfg::BK * ldb;
+        k_left -= Cfg::BK;
     }
 };
 
@@ -95,7 +95,7 @@ phase1_kernel(const P1Pair *__restrict__ pairs, const Unit *__restrict__ units, 
         src.b = B_KC ? p.b0 + (size_t)col0 * p.ldb : p.b0 + col0;
         src.lda = p.lda, src.ldb = p.ldb;
         src.m_valid = p.m0 - row0, src.n_valid = p.n0 - col0;
-        src.k_left = p.k0, src.nsteps = (p.k0 + BK - 1) / BK;
+        src.k_left = p.k0, src.nsteps = (p.k0 + Cfg::BK - 1) / Cfg::BK;
         const int mi_n = clampi((src.m_valid - wm0 + 7) / 8, 0, Cfg::MI);
         const int ni_n = clampi((src.n_valid - wn0 + 7) / 8, 0, Cfg::NI);
         double acc[Cfg::MI][Cfg::NI][2];
@@ -141,12 +141,12 @@ template <class Cfg, bool A_KC> struct P2Src {
     }
     __device__ void open() { use(*seg); }
     __device__ void issue(double *As, double *Bs) {
-        load_tile<Cfg::BM, Cfg::THREADS, A_KC>(As, a, lda, m_valid, k_left);
-        load_tile<Cfg::BN, Cfg::THREADS, false>(Bs, b, n0, n_valid, k_left);
-        k_left -= BK;
+        load_tile<Cfg::BM, Cfg::THREADS, A_KC, Cfg::BK>(As, a, lda, m_valid, k_left);
+        load_tile<Cfg::BN, Cfg::THREADS, false, Cfg::BK>(Bs, b, n0, n_valid, k_left);
+        k_left -= Cfg::BK;
         if (k_left > 0) {
-            a += A_KC ? BK : (size_t)BK * lda;
-            b += (size_t)BK * n0;
+            a += A_KC ? Cfg::BK : (size_t)Cfg::BK * lda;
+            b += (size_t)Cfg::BK * n0;
         } else if (++seg < seg_end)
             use(nxt);
     }
@@ -175,7 +175,7 @@ phase2_kernel(const P2Window *__restrict__ wins, const P2Seg *__restrict__ segs,
         src.m_valid = win.m1 - src.row0, src.n_valid = win.n0 - src.col0;
         int ns = 0;
         for (const P2Seg *s = src.seg; s < src.seg_end; s++)
-            ns += (s->klen + BK - 1) / BK;
+            ns += (s->klen + Cfg::BK - 1) / Cfg::BK;
         src.nsteps = ns;
         src.open();
         const int mi_n = clampi((src.m_valid - wm0 + 7) / 8, 0, Cfg::MI);
@@ -465,7 +465,7 @@ int b2g_tiled_build(b2g_plan *p) {
             for (const Strip &cs : split_cols(q.n0)) {
                 const int c = cfg_of(rs.tile, cs.tile);
                 groups[std::make_tuple(1, c, p1[i].tb0)].push_back(
-                    HostUnit{Unit{(int)i, rs.origin, cs.origin, 0, 0, 0, -1}, (double)rs.tile * cs.tile * (q.k0 + 2 * BK),
+                    HostUnit{Unit{(int)i, rs.origin, cs.origin, 0, 0, 0, -1}, (double)rs.tile * cs.tile * (q.k0 + 32),
                              2.0 * std::min(rs.tile, q.m0 - rs.origin) * std::min(cs.tile, q.n0 - cs.origin) * q.k0});
             }
     }
@@ -513,7 +513,7 @@ int b2g_tiled_build(b2g_plan *p) {
                     for (const Strip &cs : csv)
                         groups[std::make_tuple(2, cfg_of(rs.tile, cs.tile), lay)].push_back(
                             HostUnit{Unit{(int)w, rs.origin, cs.origin, (int)s0, (int)s1, 0, -1},
-                                     (double)rs.tile * cs.tile * (double)(ksum + 2 * BK),
+                                     (double)rs.tile * cs.tile * (double)(ksum + 32),
                                      2.0 * std::min(rs.tile, wins[w].m1 - rs.origin) *
                                          std::min(cs.tile, wins[w].n0 - cs.origin) * (double)ksum});
                 s0 = s1, ksum = 0;

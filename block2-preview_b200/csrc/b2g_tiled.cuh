@@ -22,10 +22,9 @@
 
 namespace b2g {
 
-constexpr int BK = 16;     // K depth of one pipeline stage
-constexpr int KC_LD = BK + 4;  // row pitch (doubles) of a K-contiguous tile  [row][k]
-// row pitch of an MN-contiguous tile [k][row] is (rows + 4): both pitches are = 4 mod 16,
-// which makes the 8x4 / 4x8 DMMA fragment reads of a half-warp hit 16 distinct bank pairs
+// Shared-memory tile pitches: a K-contiguous tile [row][k] has pitch BK + 4, an MN-contiguous tile
+// [k][row] has pitch rows + 4; both are = 4 mod 16, which makes the 8x4 / 4x8 DMMA fragment reads of
+// a half-warp hit 16 distinct bank pairs.  BK = K depth of one pipeline stage (16 or 32).
 
 struct P1Pair {          // phase 1: one pair
     const double *b0;    // operator block (device)
@@ -84,8 +83,9 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 }
 
 // Tile configuration: CTA tile BM x BN, WM x WN warps, each warp (BM/WM) x (BN/WN).
-template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int MINB_ = 1> struct TileCfg {
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int MINB_ = 1, int BK_ = 16> struct TileCfg {
     static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_;
+    static constexpr int BK = BK_, KC_LD = BK_ + 4;
     static constexpr int MINB = MINB_; // resident CTAs per SM the register budget is capped for
     static constexpr int THREADS = WM * WN * 32;
     static constexpr int WTM = BM / WM, WTN = BN / WN; // warp tile
@@ -99,7 +99,7 @@ template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int MINB_ = 1> struct
 //   KC = true : global operand is [row][k] (k contiguous, pitch ld)  -> smem [row][KC_LD]
 //   KC = false: global operand is [k][row] (row contiguous, pitch ld) -> smem [k][ROWS + 4]
 // rows_valid / k_valid clip the tile (zero fill outside).
-template <int ROWS, int THREADS, bool KC>
+template <int ROWS, int THREADS, bool KC, int BK>
 __device__ __forceinline__ void load_tile(double *smem, const double *g, int ld, int rows_valid, int k_valid) {
     const int tid = threadIdx.x;
     if (KC) {
@@ -111,7 +111,7 @@ __device__ __forceinline__ void load_tile(double *smem, const double *g, int ld,
             const int r = r0 + i * RPP;
             if (ROWS % RPP == 0 || r < ROWS) {
                 const bool ok = kv && r < rows_valid;
-                cp_async8(smem + r * KC_LD + k, ok ? g + (size_t)r * ld + k : g, ok);
+                cp_async8(smem + r * (BK + 4) + k, ok ? g + (size_t)r * ld + k : g, ok);
             }
         }
     } else {
@@ -148,19 +148,19 @@ template <class Cfg, bool A_KC, bool B_KC, bool FULL>
 __device__ __forceinline__ void compute_stage(const double *As, const double *Bs, double (&acc)[Cfg::MI][Cfg::NI][2],
                                               int wm0, int wn0, int mi_n, int ni_n) {
     const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
-    const double *ap = A_KC ? As + (wm0 + lr) * KC_LD + lc : As + lc * (Cfg::BM + 4) + wm0 + lr;
-    const double *bp = B_KC ? Bs + (wn0 + lr) * KC_LD + lc : Bs + lc * (Cfg::BN + 4) + wn0 + lr;
+    const double *ap = A_KC ? As + (wm0 + lr) * Cfg::KC_LD + lc : As + lc * (Cfg::BM + 4) + wm0 + lr;
+    const double *bp = B_KC ? Bs + (wn0 + lr) * Cfg::KC_LD + lc : Bs + lc * (Cfg::BN + 4) + wn0 + lr;
 #pragma unroll
-    for (int kk = 0; kk < BK / 4; kk++) {
+    for (int kk = 0; kk < Cfg::BK / 4; kk++) {
         double a[Cfg::MI], b[Cfg::NI];
 #pragma unroll
         for (int mi = 0; mi < Cfg::MI; mi++)
             if (FULL || mi < mi_n)
-                a[mi] = A_KC ? ap[mi * 8 * KC_LD + kk * 4] : ap[kk * 4 * (Cfg::BM + 4) + mi * 8];
+                a[mi] = A_KC ? ap[mi * 8 * Cfg::KC_LD + kk * 4] : ap[kk * 4 * (Cfg::BM + 4) + mi * 8];
 #pragma unroll
         for (int ni = 0; ni < Cfg::NI; ni++)
             if (FULL || ni < ni_n)
-                b[ni] = B_KC ? bp[ni * 8 * KC_LD + kk * 4] : bp[kk * 4 * (Cfg::BN + 4) + ni * 8];
+                b[ni] = B_KC ? bp[ni * 8 * Cfg::KC_LD + kk * 4] : bp[kk * 4 * (Cfg::BN + 4) + ni * 8];
 #pragma unroll
         for (int mi = 0; mi < Cfg::MI; mi++)
             if (FULL || mi < mi_n) {
