@@ -70,7 +70,7 @@ def run_reference(args) -> None:
     line = {
         "impl": "reference", "metric": METRIC, "value": r["tflops"], "unit": "TFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds_per_matvec"] * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD_NAME, "sample": sample},
         "cpu_baseline": {"value": r["tflops"], "unit": "TFLOP/s", "cores": threads, "kind": "reference",
                          "sample": sample},
