@@ -10,6 +10,8 @@ Names follow the reference's operator surface:
     SeqPlan.__call__   <-> BatchGEMMSeq::operator()(c, v, scale)   (core/batch_gemm.hpp:1570)
     SeqPlan.davidson   <-> EffectiveHamiltonian::eigs -> IterativeMatrixFunctions::davidson
     dgemm_batch        <-> cblas_xgemm_batch / BatchGEMM::perform  (core/batch_gemm.hpp:81-111)
+    Context.batch_execute <-> BatchGEMMSeq::auto_perform on the blocking list of
+                           TensorFunctions::left_contract / right_contract (core/tensor_functions.hpp:2842, 2941)
 
 The directory name is not an importable identifier; load it with `import b2gpkg`
 (repo root), which registers this package as `block2_preview_b200`.
@@ -22,6 +24,7 @@ from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64, 
 
 import numpy as np
 
+from .blkfile import BlkFile, load_blkfile  # noqa: F401
 from .seqfile import SeqFile, load_seqfile  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -34,7 +37,7 @@ EXPORTS = [
     "b2g_last_error", "b2g_device_count", "b2g_context_create", "b2g_context_destroy",
     "b2g_context_launches", "b2g_context_stream", "b2g_context_synchronize",
     "b2g_plan_create", "b2g_plan_destroy", "b2g_plan_get_stats", "b2g_seq_matvec",
-    "b2g_seq_matvec_dev", "b2g_plan_profile", "b2g_pairs_execute", "b2g_dgemm_batch", "b2g_davidson", "b2g_comm_unique_id",
+    "b2g_seq_matvec_dev", "b2g_plan_profile", "b2g_pairs_execute", "b2g_dgemm_batch", "b2g_batch_execute", "b2g_tensor_product_execute", "b2g_davidson", "b2g_comm_unique_id",
     "b2g_comm_init", "b2g_comm_destroy", "b2g_allreduce_sum", "b2g_malloc", "b2g_free",
     "b2g_memcpy_h2d", "b2g_memcpy_d2h", "b2g_memset_zero",
 ]
@@ -57,6 +60,28 @@ class PlanStats(ctypes.Structure):
     _fields_ = [("pairs", c_int64), ("csize", c_int64), ("vsize", c_int64), ("nflop_mnk", c_int64),
                 ("operand_doubles", c_int64), ("arenas", c_int64), ("launches", c_int64),
                 ("n_small", c_int64), ("n_large", c_int64), ("upload_seconds", c_double)]
+
+
+class BlockingStats(ctypes.Structure):
+    _fields_ = [("entries", c_int64), ("merged", c_int64), ("clusters", c_int64), ("units", c_int64),
+                ("serial_entries", c_int64), ("nflop_mnk", c_int64), ("bytes_in", c_int64), ("bytes_out", c_int64),
+                ("launches", c_int64), ("kernel_ms", c_double), ("upload_seconds", c_double),
+                ("download_seconds", c_double), ("plan_seconds", c_double)]
+
+
+DST_ZERO = 1
+
+
+class TPTerm(ctypes.Structure):
+    """b2g_tp_term: one GMatrixFunctions::tensor_product call of the blocking step."""
+    _fields_ = [("a", c_void_p), ("b", c_void_p), ("c", c_void_p), ("am", c_int32), ("an", c_int32),
+                ("bm", c_int32), ("bn", c_int32), ("cn", c_int32), ("conja", c_int32), ("conjb", c_int32),
+                ("reserved", c_int32), ("scale", c_double)]
+
+
+TP_DTYPE = np.dtype([("a", np.uint64), ("b", np.uint64), ("c", np.uint64), ("am", np.int32), ("an", np.int32),
+                     ("bm", np.int32), ("bn", np.int32), ("cn", np.int32), ("conja", np.int32), ("conjb", np.int32),
+                     ("reserved", np.int32), ("scale", np.float64)], align=True)
 
 
 class KernelStat(ctypes.Structure):
@@ -92,6 +117,8 @@ def lib() -> ctypes.CDLL:
                                        POINTER(c_int)]
         L.b2g_pairs_execute.argtypes = [c_void_p, POINTER(_Batch), POINTER(_Batch), c_int64, POINTER(PlanStats)]
         L.b2g_dgemm_batch.argtypes = [c_void_p, c_int64] + [c_void_p] * 13
+        L.b2g_batch_execute.argtypes = [c_void_p, c_int64] + [c_void_p] * 14 + [c_int, c_int, POINTER(BlockingStats)]
+        L.b2g_tensor_product_execute.argtypes = [c_void_p, c_int64, c_void_p, c_int, c_int, POINTER(BlockingStats)]
         L.b2g_davidson.argtypes = [c_void_p, c_void_p, c_void_p, c_double, c_double, c_int, c_int, c_int, c_int,
                                    POINTER(c_double), POINTER(c_int)]
         L.b2g_comm_unique_id.argtypes = [c_void_p]
@@ -208,6 +235,45 @@ class Context:
                                      n.ctypes.data, k.ctypes.data, alpha.ctypes.data, a.ctypes.data,
                                      lda.ctypes.data, b.ctypes.data, ldb.ctypes.data, beta.ctypes.data,
                                      c.ctypes.data, ldc.ctypes.data, gs.ctypes.data), "b2g_dgemm_batch")
+
+
+def _batch_execute(ctx, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, group_size, operand_space, flags):
+    ta, tb, m, n, k, lda, ldb, ldc, gs = map(_i32, (ta, tb, m, n, k, lda, ldb, ldc, group_size))
+    alpha, beta = _f64(alpha), _f64(beta)
+    a, b, c = _ptrs(a), _ptrs(b), _ptrs(c)
+    st = BlockingStats()
+    _check(lib().b2g_batch_execute(ctx._h, len(gs), ta.ctypes.data, tb.ctypes.data, m.ctypes.data, n.ctypes.data,
+                                   k.ctypes.data, alpha.ctypes.data, a.ctypes.data, lda.ctypes.data, b.ctypes.data,
+                                   ldb.ctypes.data, beta.ctypes.data, c.ctypes.data, ldc.ctypes.data,
+                                   gs.ctypes.data, operand_space, flags, byref(st)), "b2g_batch_execute")
+    return st
+
+
+def _ctx_batch_execute(self, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, group_size,
+                       operand_space: int = OPERANDS_HOST, flags: int = 0) -> BlockingStats:
+    """Run a conflict-carrying single-batch GEMM list (the blocking list of left_contract /
+    right_contract, cblas_dgemm_batch group signature) once; contributions to one output element
+    are applied in list order.  Host operands: results land in the host blocks."""
+    return _batch_execute(self, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, group_size, operand_space,
+                          flags)
+
+
+Context.batch_execute = _ctx_batch_execute
+
+
+def _ctx_tensor_product_execute(self, terms: np.ndarray, operand_space: int = OPERANDS_HOST,
+                                flags: int = 0) -> BlockingStats:
+    """terms: structured array of TP_DTYPE (b2g_tp_term): C window += scale * op(A) (x) op(B) each,
+    same-window terms applied in list order."""
+    terms = np.ascontiguousarray(terms, dtype=TP_DTYPE)
+    assert TP_DTYPE.itemsize == ctypes.sizeof(TPTerm)
+    st = BlockingStats()
+    _check(lib().b2g_tensor_product_execute(self._h, len(terms), terms.ctypes.data, operand_space, flags, byref(st)),
+           "b2g_tensor_product_execute")
+    return st
+
+
+Context.tensor_product_execute = _ctx_tensor_product_execute
 
 
 class SeqPlan:

@@ -1,0 +1,646 @@
+// b2g_blocking.cu — executor of the blocking lists (sm_100a).
+//
+// What is executed: the single-batch GEMM list TensorFunctions::left_contract / right_contract
+// record in SeqTypes::Auto through OperatorFunctions::tensor_product and
+// AdvancedGEMM<double>::tensor_product (block2 src/core/tensor_functions.hpp:2842-2885, 2941-2984,
+// src/core/operator_functions.hpp:672-711, src/core/batch_gemm.hpp:433-503): every term
+// a[x] (x) b[y] of a blocked operator becomes k = 1 "rows-as-AXPY" GEMM groups that all accumulate
+// into the same output block.  The reference resolves those write conflicts with work arrays and a
+// post-batch reduction (BatchGEMMSeq::prepare / auto_perform, batch_gemm.hpp:1222-1530); here the
+// list is regrouped by OUTPUT window instead: each window element is owned by one thread, which
+// walks the contributions of that window in list order with the running value in a register and
+// writes it once.  No atomics, no work arrays, bit-reproducible, and each source element is read
+// exactly once - the kernel is HBM-bound (algorithmic bytes = 8 * (sources + outputs)).
+//
+// Entries are held in an element-wise canonical form that covers the GEMM (any k), the AXPY rows
+// and the 2-D windows the rows of one group fold into:
+//     C(i, j) = beta * C(i, j) + alpha * sum_kk A[i*sa_i + j*sa_j + kk*sa_k] * B[i*sb_i + j*sb_j + kk*sb_k]
+// Nothing of the reference is compiled into this file.
+#include "b2g_internal.h"
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <numeric>
+
+namespace {
+
+struct BlkEntry { // 64 bytes
+    const double *a, *b;
+    double alpha, beta;
+    int32_t sa_i, sa_j, sa_k, sb_i, sb_j, sb_k;
+    int32_t k;
+    int32_t nd; // != 0: the window is addressed flat (one contiguous vector) and this entry's own
+                // logical width is nd: i = e / nd, j = e % nd
+};
+static_assert(sizeof(BlkEntry) == 64, "BlkEntry layout");
+
+struct BlkUnit { // one warp: `len` consecutive logical elements of one output window
+    double *dst;
+    int64_t e0;
+    int32_t len, n, ldc, first, count, pad;
+};
+static_assert(sizeof(BlkUnit) == 40, "BlkUnit layout");
+
+struct BlkSerial { // entry of an irregularly overlapping component, with its own window
+    BlkEntry e;
+    double *dst;
+    int32_t m, n, ldc, comp;
+};
+
+constexpr int UNIT_ELEMS = 128; // 4 per lane
+constexpr int PER_LANE = UNIT_ELEMS / 32;
+constexpr int BLK_THREADS = 256;
+
+__device__ __forceinline__ double blk_apply(const BlkEntry &E, double acc, int64_t i, int64_t j) {
+    if (E.nd) {
+        const int64_t e = i;
+        i = e / E.nd, j = e - i * E.nd;
+    }
+    const double base = E.beta == 1.0 ? acc : (E.beta == 0.0 ? 0.0 : E.beta * acc);
+    if (E.alpha == 0.0 || E.k == 0) // BLAS: A and B are not referenced
+        return base;
+    const double *ap = E.a + i * E.sa_i + j * E.sa_j;
+    const double *bp = E.b + i * E.sb_i + j * E.sb_j;
+    double s;
+    if (E.k == 1)
+        s = __ldg(ap) * __ldg(bp);
+    else {
+        s = 0.0;
+        for (int kk = 0; kk < E.k; kk++)
+            s = fma(__ldg(ap + (int64_t)kk * E.sa_k), __ldg(bp + (int64_t)kk * E.sb_k), s);
+    }
+    return fma(E.alpha, s, base);
+}
+
+// AXPY windows (every contribution is k = 1 with one scalar B): one warp per unit, persistent
+// grid-stride over units, 4 elements per lane held in registers across the contributions.
+// dst_zero: outputs start from 0 (not read).
+__global__ void __launch_bounds__(BLK_THREADS, 4)
+b2g_blocking_kernel(const BlkUnit *__restrict__ units, int64_t nunits, const BlkEntry *__restrict__ entries,
+                    int dst_zero) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * BLK_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * BLK_THREADS) >> 5;
+    for (int64_t u = warp; u < nunits; u += nwarps) {
+        const BlkUnit U = units[u];
+        double acc[PER_LANE];
+        int32_t ei[PER_LANE], ej[PER_LANE]; // m, n < 2^31
+#pragma unroll
+        for (int r = 0; r < PER_LANE; r++) {
+            const int l = r * 32 + lane;
+            const int64_t e = U.e0 + l;
+            ei[r] = (int32_t)(U.n == 1 ? e : e / U.n);
+            ej[r] = (int32_t)(U.n == 1 ? 0 : e - (int64_t)ei[r] * U.n);
+            acc[r] = (l < U.len && !dst_zero) ? U.dst[(int64_t)ei[r] * U.ldc + ej[r]] : 0.0;
+        }
+        for (int t = 0; t < U.count; t++) {
+            const BlkEntry E = entries[U.first + t];
+            const double s = E.alpha == 0.0 ? 0.0 : __ldg(E.b);
+#pragma unroll
+            for (int r = 0; r < PER_LANE; r++)
+                if (r * 32 + lane < U.len) {
+                    const double base = E.beta == 1.0 ? acc[r] : (E.beta == 0.0 ? 0.0 : E.beta * acc[r]);
+                    int32_t i = ei[r], j = ej[r];
+                    if (E.nd)
+                        i = ei[r] / E.nd, j = ei[r] - i * E.nd;
+                    acc[r] = E.alpha == 0.0 ? base
+                                            : fma(E.alpha, __ldg(E.a + (int64_t)i * E.sa_i + (int64_t)j * E.sa_j) * s, base);
+                }
+        }
+#pragma unroll
+        for (int r = 0; r < PER_LANE; r++)
+            if (r * 32 + lane < U.len)
+                U.dst[(int64_t)ei[r] * U.ldc + ej[r]] = acc[r];
+    }
+}
+
+// Windows with a general contribution (k > 1, or B varying over the window): one thread per element.
+__global__ void __launch_bounds__(BLK_THREADS)
+b2g_blocking_general_kernel(const BlkUnit *__restrict__ units, int64_t nunits, const BlkEntry *__restrict__ entries,
+                            int dst_zero) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * BLK_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * BLK_THREADS) >> 5;
+    for (int64_t u = warp; u < nunits; u += nwarps) {
+        const BlkUnit U = units[u];
+        for (int l = lane; l < U.len; l += 32) {
+            const int64_t e = U.e0 + l;
+            const int64_t i = e / U.n, j = e - i * U.n;
+            double *p = U.dst + i * U.ldc + j;
+            double acc = dst_zero ? 0.0 : *p;
+            for (int t = 0; t < U.count; t++)
+                acc = blk_apply(entries[U.first + t], acc, i, j);
+            *p = acc;
+        }
+    }
+}
+
+// Irregular components (windows that overlap without being identical): one CTA per component, the
+// entries strictly one after the other in list order.
+__global__ void __launch_bounds__(BLK_THREADS)
+b2g_blocking_serial_kernel(const BlkSerial *__restrict__ se, const int64_t *__restrict__ comp_first, int ncomp) {
+    for (int c = blockIdx.x; c < ncomp; c += gridDim.x) {
+        for (int64_t t = comp_first[c]; t < comp_first[c + 1]; t++) {
+            const BlkSerial S = se[t];
+            const int64_t total = (int64_t)S.m * S.n;
+            for (int64_t e = threadIdx.x; e < total; e += BLK_THREADS) {
+                const int64_t i = e / S.n, j = e - i * S.n;
+                double *p = S.dst + i * S.ldc + j;
+                *p = blk_apply(S.e, *p, i, j);
+            }
+            __threadfence_block();
+            __syncthreads();
+        }
+    }
+}
+
+struct HostEntry {
+    BlkEntry e;
+    double *dst;
+    int32_t m, n, ldc;
+    int64_t order; // position in the recorded list
+};
+
+inline bool is_t(int32_t t) { return t == B2G_TRANS || t == 1; }
+inline bool ok_t(int32_t t) { return t == B2G_TRANS || t == B2G_NOTRANS || t == 0 || t == 1; }
+
+inline size_t window_extent(int32_t m, int32_t n, int32_t ldc) {
+    return (size_t)(m - 1) * (size_t)ldc + (size_t)n;
+}
+
+// element-overlap test of two row-major windows: exact for equal pitches, conservative otherwise
+struct Win {
+    uintptr_t lo;
+    int64_t rows, cols, ld;
+};
+inline Win win_of(const HostEntry &h) {
+    if (h.n == 1 && h.ldc == 1) // contiguous column vector == one row
+        return Win{(uintptr_t)h.dst, 1, h.m, h.m};
+    return Win{(uintptr_t)h.dst, h.m, h.n, h.ldc};
+}
+bool windows_overlap(const HostEntry &hx, const HostEntry &hy) {
+    Win x = win_of(hx), y = win_of(hy);
+    const uintptr_t xh = x.lo + ((x.rows - 1) * x.ld + x.cols) * 8, yh = y.lo + ((y.rows - 1) * y.ld + y.cols) * 8;
+    if (xh <= y.lo || yh <= x.lo)
+        return false;
+    if (x.rows == 1) // the pitch of a single row is irrelevant
+        x.ld = y.ld;
+    if (y.rows == 1)
+        y.ld = x.ld;
+    if (x.ld != y.ld)
+        return true;
+    const int64_t ld = x.ld;
+    const Win &lo = x.lo <= y.lo ? x : y, &hi = x.lo <= y.lo ? y : x;
+    if (lo.cols > ld || hi.cols > ld)
+        return true;
+    const int64_t d = (int64_t)((hi.lo - lo.lo) / 8);
+    const int64_t r = d / ld, col = d % ld;
+    if (col + hi.cols > ld)
+        return true; // wraps around the pitch
+    if (col >= lo.cols)
+        return false; // disjoint column ranges on every shared row
+    return r < lo.rows; // shared columns: overlap iff the row ranges intersect
+}
+
+struct UF {
+    std::vector<int> p;
+    explicit UF(size_t n) : p(n) { std::iota(p.begin(), p.end(), 0); }
+    int find(int x) {
+        while (p[x] != x)
+            x = p[x] = p[p[x]];
+        return x;
+    }
+    void unite(int a, int b) { p[find(a)] = find(b); }
+};
+
+} // namespace
+
+// Back end shared by the list and the term entry points: entries -> output-window clusters -> warp
+// units -> kernels, with the operand mirroring of the host operand space around it.
+static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int operand_space, bool dst_zero,
+                           b2g_blocking_stats &st, b2g_blocking_stats *stats,
+                           std::chrono::steady_clock::time_point t_begin, const char *who) {
+    st.merged = (int64_t)he.size();
+    if (he.empty()) {
+        if (stats)
+            *stats = st;
+        return 0;
+    }
+    for (const HostEntry &h : he)
+        if (h.e.alpha != 0.0 && h.e.k > 0) { // distinct source elements of the entry
+            const int64_t na = (int64_t)(h.e.sa_i ? h.m : 1) * (h.e.sa_j ? h.n : 1) * h.e.k;
+            const int64_t nb = (int64_t)(h.e.sb_i ? h.m : 1) * (h.e.sb_j ? h.n : 1) * h.e.k;
+            st.bytes_in += 8 * (na + nb);
+        }
+    // dense windows (whole rows of their block, or a single row) are addressed as one contiguous vector
+    // whatever logical shape the contributing entry has: a term and its transposed partner, or the
+    // recorder's whole-block AXPY (a.n == c.n branch), then share one cluster
+    for (HostEntry &h : he)
+        if (h.n > 1 && (h.ldc == h.n || h.m == 1) && (int64_t)h.m * h.n < INT32_MAX) {
+            h.e.nd = h.n;
+            h.m = h.m * h.n, h.n = 1, h.ldc = 1;
+        }
+
+    // ---- 2. clusters = identical output windows, members in list order
+    std::vector<int> idx(he.size());
+    std::iota(idx.begin(), idx.end(), 0);
+    std::sort(idx.begin(), idx.end(), [&he](int x, int y) {
+        const HostEntry &p = he[x], &q = he[y];
+        if (p.dst != q.dst)
+            return p.dst < q.dst;
+        if (p.m != q.m)
+            return p.m < q.m;
+        if (p.n != q.n)
+            return p.n < q.n;
+        if (p.ldc != q.ldc)
+            return p.ldc < q.ldc;
+        return p.order < q.order;
+    });
+    struct Cluster {
+        int first, count; // into idx
+    };
+    std::vector<Cluster> cl;
+    for (size_t i = 0; i < idx.size();) {
+        size_t j = i + 1;
+        const HostEntry &p = he[idx[i]];
+        while (j < idx.size() && he[idx[j]].dst == p.dst && he[idx[j]].m == p.m && he[idx[j]].n == p.n &&
+               he[idx[j]].ldc == p.ldc)
+            j++;
+        cl.push_back(Cluster{(int)i, (int)(j - i)});
+        i = j;
+    }
+    st.clusters = (int64_t)cl.size();
+
+    // ---- 3. windows that overlap without being identical -> serial components (sweep over sorted starts)
+    UF uf(cl.size());
+    std::vector<char> irregular(cl.size(), 0);
+    {
+        std::vector<int> active;
+        for (size_t ci = 0; ci < cl.size(); ci++) {
+            const HostEntry &w = he[idx[cl[ci].first]];
+            const uintptr_t lo = (uintptr_t)w.dst;
+            size_t keep = 0;
+            for (size_t q = 0; q < active.size(); q++) {
+                const HostEntry &o = he[idx[cl[active[q]].first]];
+                if ((uintptr_t)o.dst + window_extent(o.m, o.n, o.ldc) * 8 > lo)
+                    active[keep++] = active[q];
+            }
+            active.resize(keep);
+            for (int q : active)
+                if (windows_overlap(he[idx[cl[q].first]], w)) {
+                    irregular[q] = irregular[ci] = 1;
+                    uf.unite(q, (int)ci);
+                }
+            active.push_back((int)ci);
+        }
+    }
+
+    // ---- 4. device descriptors
+    std::vector<BlkEntry> dev_entries;
+    std::vector<BlkUnit> units, gunits; // AXPY windows / windows with a general contribution
+    dev_entries.reserve(he.size());
+    std::vector<BlkSerial> serial;
+    for (size_t ci = 0; ci < cl.size(); ci++) {
+        const HostEntry &w = he[idx[cl[ci].first]];
+        if (irregular[ci]) {
+            for (int q = 0; q < cl[ci].count; q++) {
+                const HostEntry &h = he[idx[cl[ci].first + q]];
+                serial.push_back(BlkSerial{h.e, h.dst, h.m, h.n, h.ldc, uf.find((int)ci)});
+            }
+            continue;
+        }
+        const int first = (int)dev_entries.size();
+        bool axpy = true;
+        for (int q = 0; q < cl[ci].count; q++) {
+            const BlkEntry &e = he[idx[cl[ci].first + q]].e;
+            axpy = axpy && (e.alpha == 0.0 || (e.k == 1 && e.sb_i == 0 && e.sb_j == 0));
+            dev_entries.push_back(e);
+        }
+        const int64_t total = (int64_t)w.m * w.n;
+        std::vector<BlkUnit> &dstu = axpy ? units : gunits;
+        for (int64_t e0 = 0; e0 < total; e0 += UNIT_ELEMS)
+            dstu.push_back(BlkUnit{w.dst, e0, (int32_t)std::min<int64_t>(UNIT_ELEMS, total - e0), w.n, w.ldc, first,
+                                    cl[ci].count, 0});
+        st.bytes_out += total * 8;
+    }
+    // serial entries: by component, then list order (order kept in a side array: pad is 31-bit only)
+    std::vector<int64_t> comp_first;
+    if (!serial.empty()) {
+        std::vector<int64_t> sorder;
+        sorder.reserve(serial.size());
+        for (size_t ci = 0; ci < cl.size(); ci++)
+            if (irregular[ci])
+                for (int q = 0; q < cl[ci].count; q++)
+                    sorder.push_back(he[idx[cl[ci].first + q]].order);
+        std::vector<int> sidx(serial.size());
+        std::iota(sidx.begin(), sidx.end(), 0);
+        std::sort(sidx.begin(), sidx.end(), [&](int x, int y) {
+            if (serial[x].comp != serial[y].comp)
+                return serial[x].comp < serial[y].comp;
+            return sorder[x] < sorder[y];
+        });
+        std::vector<BlkSerial> tmp(serial.size());
+        for (size_t i = 0; i < sidx.size(); i++)
+            tmp[i] = serial[sidx[i]];
+        serial.swap(tmp);
+        for (size_t i = 0; i < serial.size(); i++)
+            if (i == 0 || serial[i].comp != serial[i - 1].comp)
+                comp_first.push_back((int64_t)i);
+        comp_first.push_back((int64_t)serial.size());
+        for (const BlkSerial &s : serial)
+            st.bytes_out += (int64_t)s.m * s.n * 8;
+    }
+    st.units = (int64_t)(units.size() + gunits.size());
+    st.serial_entries = (int64_t)serial.size();
+    if (dst_zero && operand_space == B2G_OPERANDS_DEVICE && !serial.empty()) {
+        b2g_set_error("" + std::string(who) + ": B2G_DST_ZERO with device operands needs regular (identical or disjoint) output windows");
+        return 1;
+    }
+    st.plan_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+
+    // ---- 5. operands
+    double *d_in = nullptr, *d_out = nullptr;
+    BlkEntry *d_entries = nullptr;
+    BlkUnit *d_units = nullptr, *d_gunits = nullptr;
+    BlkSerial *d_serial = nullptr;
+    int64_t *d_comp = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    auto cleanup = [&]() {
+        b2g_dfree(ctx, d_in), b2g_dfree(ctx, d_out), b2g_dfree(ctx, d_entries), b2g_dfree(ctx, d_units), b2g_dfree(ctx, d_gunits);
+        b2g_dfree(ctx, d_serial), b2g_dfree(ctx, d_comp);
+        if (ev0)
+            cudaEventDestroy(ev0);
+        if (ev1)
+            cudaEventDestroy(ev1);
+    };
+    auto fail = [&](const std::string &msg) {
+        if (!msg.empty())
+            b2g_set_error(msg);
+        cudaStreamSynchronize(ctx->stream);
+        cleanup();
+        return 1;
+    };
+    std::vector<B2GRange> in_rg, out_rg;
+    auto t_up = std::chrono::steady_clock::now();
+    if (operand_space == B2G_OPERANDS_HOST) {
+        auto add = [](std::vector<B2GRange> &v, const void *ptr, size_t ext) {
+            if (ext)
+                v.push_back(B2GRange{(uintptr_t)ptr, (uintptr_t)ptr + ext * sizeof(double), 0});
+        };
+        for (const HostEntry &h : he) {
+            add(out_rg, h.dst, window_extent(h.m, h.n, h.ldc));
+            if (h.e.alpha == 0.0 || h.e.k == 0)
+                continue;
+            add(in_rg, h.e.a,
+                (size_t)(h.m - 1) * h.e.sa_i + (size_t)(h.n - 1) * h.e.sa_j + (size_t)(h.e.k - 1) * h.e.sa_k + 1);
+            add(in_rg, h.e.b,
+                (size_t)(h.m - 1) * h.e.sb_i + (size_t)(h.n - 1) * h.e.sb_j + (size_t)(h.e.k - 1) * h.e.sb_k + 1);
+        }
+        size_t in_total = 0, out_total = 0;
+        b2g_merge_ranges(in_rg, in_total), b2g_merge_ranges(out_rg, out_total);
+        for (const B2GRange &o : out_rg) // an output block must not also be an input of the same list
+            if (!in_rg.empty()) {
+                const B2GRange &r = b2g_locate_range(in_rg, o.lo);
+                const B2GRange *nx = (&r + 1 < in_rg.data() + in_rg.size()) ? &r + 1 : nullptr;
+                if ((r.lo < o.hi && o.lo < r.hi) || (nx && nx->lo < o.hi && o.lo < nx->hi))
+                    return fail("" + std::string(who) + ": an output block aliases an input block of the same list");
+            }
+        if ((in_total && b2g_dmalloc(ctx, (void **)&d_in, in_total * sizeof(double))) ||
+            b2g_dmalloc(ctx, (void **)&d_out, out_total * sizeof(double)))
+            return fail("");
+        if (in_total && b2g_mirror_ranges(ctx, in_rg, d_in))
+            return fail("");
+        if (dst_zero) {
+            if (cudaMemsetAsync(d_out, 0, out_total * sizeof(double), ctx->stream) != cudaSuccess)
+                return fail("" + std::string(who) + ": memset failed");
+        } else if (b2g_mirror_ranges(ctx, out_rg, d_out))
+            return fail("");
+        for (BlkEntry &e : dev_entries)
+            if (e.alpha != 0.0 && e.k > 0)
+                e.a = b2g_translate(in_rg, d_in, e.a), e.b = b2g_translate(in_rg, d_in, e.b);
+        for (BlkUnit &u : units)
+            u.dst = b2g_translate(out_rg, d_out, u.dst);
+        for (BlkUnit &u : gunits)
+            u.dst = b2g_translate(out_rg, d_out, u.dst);
+        for (BlkSerial &s : serial) {
+            if (s.e.alpha != 0.0 && s.e.k > 0)
+                s.e.a = b2g_translate(in_rg, d_in, s.e.a), s.e.b = b2g_translate(in_rg, d_in, s.e.b);
+            s.dst = b2g_translate(out_rg, d_out, s.dst);
+        }
+    }
+    // descriptors (pageable -> device; synchronised below before the vectors die)
+    if (!dev_entries.empty()) {
+        if (b2g_dmalloc(ctx, (void **)&d_entries, dev_entries.size() * sizeof(BlkEntry)) ||
+            b2g_dmalloc(ctx, (void **)&d_units, units.size() * sizeof(BlkUnit)) ||
+            b2g_dmalloc(ctx, (void **)&d_gunits, gunits.size() * sizeof(BlkUnit)))
+            return fail("");
+        if (cudaMemcpyAsync(d_entries, dev_entries.data(), dev_entries.size() * sizeof(BlkEntry),
+                            cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(d_units, units.data(), units.size() * sizeof(BlkUnit), cudaMemcpyHostToDevice,
+                            ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(d_gunits, gunits.data(), gunits.size() * sizeof(BlkUnit), cudaMemcpyHostToDevice,
+                            ctx->stream) != cudaSuccess)
+            return fail("" + std::string(who) + ": descriptor upload failed");
+    }
+    if (!serial.empty()) {
+        if (b2g_dmalloc(ctx, (void **)&d_serial, serial.size() * sizeof(BlkSerial)) ||
+            b2g_dmalloc(ctx, (void **)&d_comp, comp_first.size() * sizeof(int64_t)))
+            return fail("");
+        if (cudaMemcpyAsync(d_serial, serial.data(), serial.size() * sizeof(BlkSerial), cudaMemcpyHostToDevice,
+                            ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(d_comp, comp_first.data(), comp_first.size() * sizeof(int64_t), cudaMemcpyHostToDevice,
+                            ctx->stream) != cudaSuccess)
+            return fail("" + std::string(who) + ": descriptor upload failed");
+    }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        return fail("" + std::string(who) + ": operand upload failed");
+    st.upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_up).count();
+
+    // ---- 6. kernels
+    if (cudaEventCreate(&ev0) != cudaSuccess || cudaEventCreate(&ev1) != cudaSuccess)
+        return fail("" + std::string(who) + ": event creation failed");
+    cudaEventRecord(ev0, ctx->stream);
+    if (!units.empty()) {
+        const int64_t want = ((int64_t)units.size() * 32 + BLK_THREADS - 1) / BLK_THREADS;
+        const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 8);
+        b2g_blocking_kernel<<<grid, BLK_THREADS, 0, ctx->stream>>>(d_units, (int64_t)units.size(), d_entries,
+                                                                   dst_zero ? 1 : 0);
+        ctx->launches++, st.launches++;
+    }
+    if (!gunits.empty()) {
+        const int64_t want = ((int64_t)gunits.size() * 32 + BLK_THREADS - 1) / BLK_THREADS;
+        const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 8);
+        b2g_blocking_general_kernel<<<grid, BLK_THREADS, 0, ctx->stream>>>(d_gunits, (int64_t)gunits.size(), d_entries,
+                                                                           dst_zero ? 1 : 0);
+        ctx->launches++, st.launches++;
+    }
+    if (!serial.empty()) {
+        const int ncomp = (int)comp_first.size() - 1;
+        b2g_blocking_serial_kernel<<<std::min(ncomp, ctx->sm_count * 4), BLK_THREADS, 0, ctx->stream>>>(d_serial, d_comp,
+                                                                                                       ncomp);
+        ctx->launches++, st.launches++;
+    }
+    cudaEventRecord(ev1, ctx->stream);
+    if (cudaGetLastError() != cudaSuccess || cudaEventSynchronize(ev1) != cudaSuccess)
+        return fail(std::string("" + std::string(who) + ": kernel failed: ") + cudaGetErrorString(cudaGetLastError()));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    st.kernel_ms = ms;
+
+    // ---- 7. results
+    if (operand_space == B2G_OPERANDS_HOST) {
+        auto t_dn = std::chrono::steady_clock::now();
+        if (b2g_download_ranges(ctx, out_rg, d_out, dst_zero))
+            return fail("");
+        st.download_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_dn).count();
+    }
+    cleanup();
+    if (stats)
+        *stats = st;
+    return 0;
+}
+
+extern "C" int b2g_batch_execute(b2g_context *ctx, int64_t group_count, const int32_t *ta, const int32_t *tb,
+                                 const int32_t *m, const int32_t *n, const int32_t *k, const double *alpha,
+                                 const double *const *a, const int32_t *lda, const double *const *b,
+                                 const int32_t *ldb, const double *beta, double *const *c, const int32_t *ldc,
+                                 const int32_t *group_size, int operand_space, int flags,
+                                 b2g_blocking_stats *stats) {
+    if (!ctx) {
+        b2g_set_error("b2g_batch_execute: null context");
+        return 1;
+    }
+    if (group_count > 0 && (!ta || !tb || !m || !n || !k || !alpha || !a || !lda || !b || !ldb || !beta || !c || !ldc ||
+                            !group_size)) {
+        b2g_set_error("b2g_batch_execute: null argument");
+        return 1;
+    }
+    if (operand_space != B2G_OPERANDS_HOST && operand_space != B2G_OPERANDS_DEVICE) {
+        b2g_set_error("b2g_batch_execute: unknown operand space");
+        return 1;
+    }
+    B2G_CUDA(cudaSetDevice(ctx->device));
+    b2g_blocking_stats st;
+    memset(&st, 0, sizeof(st));
+    auto t_begin = std::chrono::steady_clock::now();
+    const bool dst_zero = (flags & B2G_DST_ZERO) != 0;
+
+    // ---- 1. expand the groups, fold constant-stride AXPY rows of one group into 2-D windows
+    std::vector<HostEntry> he;
+    int64_t z = 0, order = 0;
+    for (int64_t g = 0; g < group_count; g++) {
+        if (!ok_t(ta[g]) || !ok_t(tb[g])) {
+            b2g_set_error("b2g_batch_execute: group " + std::to_string(g) + ": transpose flag is not N/T");
+            return 1;
+        }
+        const bool tA = is_t(ta[g]), tB = is_t(tb[g]);
+        const int32_t gm = m[g], gn = n[g], gk = k[g], gs = group_size[g];
+        if (gs < 0 || gk < 0) {
+            b2g_set_error("b2g_batch_execute: negative group size or k");
+            return 1;
+        }
+        if (gm <= 0 || gn <= 0) {
+            z += gs;
+            continue;
+        }
+        if (ldc[g] < gn || (gk > 0 && (lda[g] < (tA ? gm : gk) || ldb[g] < (tB ? gk : gn)))) {
+            b2g_set_error("b2g_batch_execute: group " + std::to_string(g) + ": leading dimension too small");
+            return 1;
+        }
+        st.entries += gs;
+        st.nflop_mnk += (int64_t)gm * gn * gk * gs;
+        const bool foldable = gk == 1 && gn == 1 && ldc[g] == 1;
+        for (int32_t q = 0; q < gs;) {
+            HostEntry h;
+            h.e.a = a[z + q], h.e.b = b[z + q], h.dst = c[z + q];
+            h.e.alpha = alpha[g], h.e.beta = beta[g];
+            h.e.sa_i = tA ? 1 : lda[g], h.e.sa_k = tA ? lda[g] : 1, h.e.sa_j = 0;
+            h.e.sb_j = tB ? ldb[g] : 1, h.e.sb_k = tB ? 1 : ldb[g], h.e.sb_i = 0;
+            h.e.k = gk, h.e.nd = 0;
+            h.m = gm, h.n = gn, h.ldc = ldc[g];
+            h.order = order;
+            int32_t run = 1;
+            if (foldable && q + 1 < gs) {
+                const int64_t da = a[z + q + 1] - a[z + q], db = b[z + q + 1] - b[z + q],
+                              dc = c[z + q + 1] - c[z + q];
+                if (dc >= gm && dc < INT32_MAX && da >= 0 && da < INT32_MAX && db >= 0 && db < INT32_MAX) {
+                    while (q + run < gs && a[z + q + run] - a[z + q + run - 1] == da &&
+                           b[z + q + run] - b[z + q + run - 1] == db && c[z + q + run] - c[z + q + run - 1] == dc)
+                        run++;
+                    if (run > 1) { // rows r = 0..run-1, columns = the gm elements of one row
+                        h.e.sa_j = h.e.sa_i, h.e.sa_i = (int32_t)da;
+                        h.e.sb_i = (int32_t)db, h.e.sb_j = 0;
+                        h.m = run, h.n = gm, h.ldc = (int32_t)dc;
+                    }
+                }
+            }
+            he.push_back(h);
+            order += run, q += run;
+        }
+        z += gs;
+    }
+    return execute_entries(ctx, he, operand_space, dst_zero, st, stats, t_begin, "b2g_batch_execute");
+}
+
+// One GMatrixFunctions::tensor_product call (block2 src/core/matrix_functions.hpp:1269-1397, recorded
+// form AdvancedGEMM<double>::tensor_product, src/core/batch_gemm.hpp:433-503):
+//     C[(i*bm + k), (j*bn + l)] += scale * op(A)(i, j) * op(B)(k, l),   C = c (stride already added), pitch cn
+// as whole 2-D windows instead of one GEMM per row.
+extern "C" int b2g_tensor_product_execute(b2g_context *ctx, int64_t count, const b2g_tp_term *terms,
+                                          int operand_space, int flags, b2g_blocking_stats *stats) {
+    if (!ctx || (count > 0 && !terms)) {
+        b2g_set_error("b2g_tensor_product_execute: null argument");
+        return 1;
+    }
+    if (operand_space != B2G_OPERANDS_HOST && operand_space != B2G_OPERANDS_DEVICE) {
+        b2g_set_error("b2g_tensor_product_execute: unknown operand space");
+        return 1;
+    }
+    B2G_CUDA(cudaSetDevice(ctx->device));
+    b2g_blocking_stats st;
+    memset(&st, 0, sizeof(st));
+    auto t_begin = std::chrono::steady_clock::now();
+    std::vector<HostEntry> he;
+    he.reserve((size_t)count);
+    int64_t order = 0;
+    for (int64_t t = 0; t < count; t++) {
+        const b2g_tp_term &q = terms[t];
+        if (q.am <= 0 || q.an <= 0 || q.bm <= 0 || q.bn <= 0)
+            continue;
+        const bool ca = q.conja != 0, cb = q.conjb != 0;
+        // shape of op(A), op(B)
+        const int32_t ar = ca ? q.an : q.am, ac = ca ? q.am : q.an, br = cb ? q.bn : q.bm, bc = cb ? q.bm : q.bn;
+        if ((int64_t)ac * bc > q.cn) {
+            b2g_set_error("b2g_tensor_product_execute: term " + std::to_string(t) + ": window wider than the pitch of c");
+            return 1;
+        }
+        st.entries += 1;
+        st.nflop_mnk += (int64_t)q.am * q.an * q.bm * q.bn;
+        HostEntry h;
+        h.e.alpha = q.scale, h.e.beta = 1.0, h.e.k = 1, h.e.nd = 0;
+        h.e.sa_k = h.e.sb_k = 0;
+        if (q.bm == 1 && q.bn == 1) { // C(i, j) += scale * b * op(A)(i, j)
+            h.e.a = q.a, h.e.b = q.b;
+            h.e.sa_i = ca ? 1 : q.an, h.e.sa_j = ca ? q.an : 1, h.e.sb_i = h.e.sb_j = 0;
+            h.dst = q.c, h.m = ar, h.n = ac, h.ldc = q.cn, h.order = order++;
+            he.push_back(h);
+        } else if (q.am == 1 && q.an == 1) { // C(k, l) += scale * a * op(B)(k, l)
+            h.e.a = q.b, h.e.b = q.a;
+            h.e.sa_i = cb ? 1 : q.bn, h.e.sa_j = cb ? q.bn : 1, h.e.sb_i = h.e.sb_j = 0;
+            h.dst = q.c, h.m = br, h.n = bc, h.ldc = q.cn, h.order = order++;
+            he.push_back(h);
+        } else { // Kronecker product: one op(B) window per element of op(A)
+            for (int32_t i = 0; i < ar; i++)
+                for (int32_t j = 0; j < ac; j++) {
+                    HostEntry g = h;
+                    g.e.a = q.b, g.e.b = q.a + (ca ? (int64_t)j * q.an + i : (int64_t)i * q.an + j);
+                    g.e.sa_i = cb ? 1 : q.bn, g.e.sa_j = cb ? q.bn : 1, g.e.sb_i = g.e.sb_j = 0;
+                    g.dst = q.c + ((int64_t)i * br) * q.cn + (int64_t)j * bc;
+                    g.m = br, g.n = bc, g.ldc = q.cn, g.order = order++;
+                    he.push_back(g);
+                }
+        }
+    }
+    return execute_entries(ctx, he, operand_space, (flags & B2G_DST_ZERO) != 0, st, stats, t_begin,
+                           "b2g_tensor_product_execute");
+}

@@ -696,3 +696,111 @@ extern "C" int b2g_pairs_execute(b2g_context *ctx, const b2g_batch *b0, const b2
     b2g_plan_destroy(p);
     return 0;
 }
+
+// ------------------------------------------------------------------ shared range helpers
+
+void b2g_merge_ranges(std::vector<B2GRange> &rg, size_t &total) {
+    std::sort(rg.begin(), rg.end(), [](const B2GRange &x, const B2GRange &y) { return x.lo < y.lo; });
+    std::vector<B2GRange> ar;
+    for (const B2GRange &r : rg) {
+        if (!ar.empty() && r.lo <= ar.back().hi)
+            ar.back().hi = std::max(ar.back().hi, r.hi);
+        else
+            ar.push_back(r);
+    }
+    total = 0;
+    for (B2GRange &r : ar) {
+        r.dev_off = total;
+        total += (r.hi - r.lo) / sizeof(double);
+        total = (total + 1) & ~(size_t)1;
+    }
+    rg.swap(ar);
+}
+
+const B2GRange &b2g_locate_range(const std::vector<B2GRange> &ar, uintptr_t ptr) {
+    size_t lo = 0, hi = ar.size();
+    while (hi - lo > 1) {
+        const size_t mid = (lo + hi) / 2;
+        if (ar[mid].lo <= ptr)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return ar[lo];
+}
+
+int b2g_mirror_ranges(b2g_context *ctx, const std::vector<B2GRange> &rg, double *dev_base) {
+    if (ensure_upload_buffers(ctx))
+        return 1;
+    MirrorWriter mw{ctx, (char *)dev_base};
+    B2G_CUDA(cudaEventSynchronize(ctx->up_done[0]));
+    B2G_CUDA(cudaEventSynchronize(ctx->up_done[1]));
+    for (const B2GRange &r : rg)
+        if (mw.add(r.dev_off * sizeof(double), (const void *)r.lo, r.hi - r.lo))
+            return 1;
+    return mw.flush();
+}
+
+int b2g_download_ranges(b2g_context *ctx, const std::vector<B2GRange> &rg, const double *dev_base, bool add) {
+    if (ensure_upload_buffers(ctx))
+        return 1;
+    B2G_CUDA(cudaStreamSynchronize(ctx->stream));
+    const size_t CH = B2G_UP_CHUNK / sizeof(double);
+    // neighbouring small ranges travel in one DMA: [i, j) is a run whose device span fits one staging buffer
+    for (size_t i = 0; i < rg.size();) {
+        const size_t span_lo = rg[i].dev_off;
+        const size_t len_i = (rg[i].hi - rg[i].lo) / sizeof(double);
+        if (len_i > CH) { // one large range: chunked
+            double *host = (double *)rg[i].lo;
+            for (size_t off = 0; off < len_i; off += CH) {
+                const size_t m = std::min(CH, len_i - off);
+                B2G_CUDA(cudaMemcpyAsync(ctx->h_up[0], dev_base + span_lo + off, m * sizeof(double),
+                                         cudaMemcpyDeviceToHost, ctx->stream));
+                B2G_CUDA(cudaStreamSynchronize(ctx->stream));
+                const double *src = (const double *)ctx->h_up[0];
+                const int nt = m > ((size_t)1 << 16) ? ctx->up_threads : 1;
+                const size_t slice = (m + nt - 1) / nt;
+                std::vector<std::thread> th;
+                auto work = [=](size_t lo, size_t hi) {
+                    if (add)
+                        for (size_t j = lo; j < hi; j++)
+                            host[off + j] += src[j];
+                    else
+                        memcpy(host + off + lo, src + lo, (hi - lo) * sizeof(double));
+                };
+                for (int t = 1; t < nt; t++) {
+                    const size_t lo = std::min(m, slice * t), hi = std::min(m, slice * (t + 1));
+                    if (hi > lo)
+                        th.emplace_back(work, lo, hi);
+                }
+                work(0, std::min(m, slice));
+                for (auto &x : th)
+                    x.join();
+            }
+            i++;
+            continue;
+        }
+        size_t j = i, span_hi = span_lo;
+        while (j < rg.size()) {
+            const size_t e = rg[j].dev_off + (rg[j].hi - rg[j].lo) / sizeof(double);
+            if (e - span_lo > CH)
+                break;
+            span_hi = e, j++;
+        }
+        B2G_CUDA(cudaMemcpyAsync(ctx->h_up[0], dev_base + span_lo, (span_hi - span_lo) * sizeof(double),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+        B2G_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (size_t r = i; r < j; r++) {
+            double *host = (double *)rg[r].lo;
+            const double *src = (const double *)ctx->h_up[0] + (rg[r].dev_off - span_lo);
+            const size_t m = (rg[r].hi - rg[r].lo) / sizeof(double);
+            if (add)
+                for (size_t q = 0; q < m; q++)
+                    host[q] += src[q];
+            else
+                memcpy(host, src, m * sizeof(double));
+        }
+        i = j;
+    }
+    return 0;
+}

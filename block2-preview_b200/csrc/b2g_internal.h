@@ -79,6 +79,24 @@ int b2g_upload(b2g_context *ctx, void *dst, const void *src, size_t bytes);
         }                                                                                \
     } while (0)
 
+// host address ranges mirrored into one device allocation (b2g_core.cu)
+struct B2GRange {
+    uintptr_t lo, hi; // host bytes [lo, hi)
+    size_t dev_off;   // doubles from the device base
+};
+// sort + merge touching ranges, assign 16-byte aligned device offsets; total = doubles needed
+void b2g_merge_ranges(std::vector<B2GRange> &rg, size_t &total);
+// range that holds ptr (rg merged and sorted)
+const B2GRange &b2g_locate_range(const std::vector<B2GRange> &rg, uintptr_t ptr);
+inline double *b2g_translate(const std::vector<B2GRange> &rg, double *dev_base, const void *host) {
+    const B2GRange &r = b2g_locate_range(rg, (uintptr_t)host);
+    return dev_base + r.dev_off + ((uintptr_t)host - r.lo) / sizeof(double);
+}
+// host ranges -> device (pinned staging, small neighbours packed into one DMA); asynchronous
+int b2g_mirror_ranges(b2g_context *ctx, const std::vector<B2GRange> &rg, double *dev_base);
+// device -> host ranges through pinned staging; add = true: host += device, else host = device. Synchronous.
+int b2g_download_ranges(b2g_context *ctx, const std::vector<B2GRange> &rg, const double *dev_base, bool add);
+
 // kernels (b2g_kernels.cu)
 int b2g_launch_matvec(b2g_plan *plan, const double *c_dev, double *v_dev, double scale);
 // two-phase DMMA path (b2g_tiled.cu)

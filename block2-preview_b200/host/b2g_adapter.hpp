@@ -11,6 +11,10 @@
 //       tensor_product_multiply  -> reference recording, then marks the device plan stale
 //                                   (this is the call EffectiveHamiltonian::precompute() makes,
 //                                    dmrg/effective_hamiltonian.hpp:226-246)
+//       left_contract / right_contract (tensor_functions.hpp:2842-2885, 2941-2984)
+//                                -> reference recording of the tensor_product list (SeqTypes::Auto),
+//                                   executed by b2g_batch_execute instead of seq->auto_perform()
+//       left_rotate / right_rotate (:2365-2403) -> recorded tensor_rotate list, b2g_pairs_execute
 //       copy()                   -> keeps the dynamic type (EffectiveHamiltonian stores ptf->copy(), :137)
 //   GPUDMRG<S>             : DMRG<S,double,double>        (dmrg/sweep_algorithm.hpp:71)
 //       two_dot_eigs_and_perturb (virtual, :1183) -> H_eff built by the reference,
@@ -47,6 +51,11 @@ struct Session {
     double t_rotate = 0, max_rotate_err = 0;
     size_t n_rotate = 0, rotate_pairs = 0;
     double rotate_flops = 0;
+    // blocking (left_contract / right_contract) on the device
+    bool gpu_contract = false;
+    double t_contract = 0, max_contract_err = 0, contract_kernel_ms = 0, contract_bytes = 0;
+    double t_contract_record = 0, t_contract_plan = 0, t_contract_upload = 0, t_contract_download = 0;
+    size_t n_contract = 0, contract_entries = 0;
     explicit Session(int device = 0) {
         if (b2g_context_create(device, &ctx) != 0)
             throw std::runtime_error(std::string("b2g_context_create: ") + b2g_last_error());
@@ -73,6 +82,69 @@ inline b2g_batch as_b2g_batch(const BatchGEMM<double> &b) {
     r.a = b.a.data(), r.b = b.b.data(), r.c = b.c.data();
     return r;
 }
+
+// Term collector shared by an OperatorFunctions object and its per-thread copies.
+struct TermCollector {
+    bool active = false;
+    vector<vector<b2g_tp_term>> per_thread;
+    TermCollector() : per_thread(max(1, threading->n_threads_global)) {}
+    void clear() {
+        for (auto &v : per_thread)
+            v.clear();
+    }
+    size_t size() const {
+        size_t n = 0;
+        for (auto &v : per_thread)
+            n += v.size();
+        return n;
+    }
+};
+
+// OperatorFunctions whose tensor_product (core/operator_functions.hpp:672-711) can emit, instead of the
+// per-row GEMM groups of AdvancedGEMM::tensor_product, one b2g_tp_term per connection-info entry - the
+// arguments of the eager GMatrixFunctions::tensor_product call the stock method would make
+// (core/matrix_functions.hpp:1269).  OperatorFunctions subclasses dispatch on every thread of
+// TensorFunctions::parallel_for (the opf pointer survives the base-class slice), unlike
+// fine-grained TensorFunctions overrides.
+template <typename S> struct GPUOperatorFunctions : OperatorFunctions<S, double> {
+    typedef double FL;
+    typedef OperatorFunctions<S, double> Base;
+    using Base::cg;
+    using Base::seq;
+    shared_ptr<TermCollector> collector;
+    GPUOperatorFunctions(const shared_ptr<CG<S>> &cg, const shared_ptr<TermCollector> &collector)
+        : Base(cg), collector(collector) {}
+    shared_ptr<OperatorFunctions<S, FL>> copy() const override {
+        shared_ptr<GPUOperatorFunctions<S>> r = make_shared<GPUOperatorFunctions<S>>(cg, collector);
+        r->seq = seq->copy();
+        return r;
+    }
+    void tensor_product(uint8_t conj, const shared_ptr<SparseMatrix<S, FL>> &a, const shared_ptr<SparseMatrix<S, FL>> &b,
+                        const shared_ptr<SparseMatrix<S, FL>> &c, FL scale = 1.0) const override {
+        if (!collector->active)
+            return Base::tensor_product(conj, a, b, c, scale);
+        scale = scale * a->factor * b->factor;
+        if (abs(scale) < TINY)
+            return;
+        const S adq = a->info->delta_quantum, bdq = b->info->delta_quantum, cdq = c->info->delta_quantum;
+        const auto &ci = c->info->cinfo;
+        // the (conj, a (x) b quantum) range of the connection table, as the stock method finds it
+        const S abdq = cdq.combine((conj & 1) ? -adq : adq, (conj & 2) ? bdq : -bdq);
+        const int ik = (int)(lower_bound(ci->quanta + ci->n[conj], ci->quanta + ci->n[conj + 1], abdq) - ci->quanta);
+        assert(ik < ci->n[conj + 1]);
+        const int lo = ci->idx[ik], hi = ik == ci->n[4] - 1 ? ci->nc : ci->idx[ik + 1];
+        vector<b2g_tp_term> &out = collector->per_thread[threading->get_thread_id()];
+        for (int il = lo; il < hi; il++) {
+            const GMatrix<FL> ma = (*a)[ci->ia[il]], mb = (*b)[ci->ib[il]], mc = (*c)[ci->ic[il]];
+            b2g_tp_term t;
+            t.a = ma.data, t.b = mb.data, t.c = mc.data + ci->stride[il];
+            t.am = ma.m, t.an = ma.n, t.bm = mb.m, t.bn = mb.n, t.cn = mc.n;
+            t.conja = conj & 1, t.conjb = (conj & 2) >> 1, t.reserved = 0;
+            t.scale = scale * (FL)ci->factor[il];
+            out.push_back(t);
+        }
+    }
+};
 
 // Base = TensorFunctions<S,double> (serial) or ParallelTensorFunctions<S,double> (one process per
 // GPU under ParallelRuleQC: the base keeps the reference's distributed blocking logic, the matvec
@@ -182,6 +254,197 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
         }
         seq->clear();
         session->t_rotate += t.get_time(), session->n_rotate++;
+    }
+    // Record-only walk of one blocking expression, the Auto-mode counterpart of
+    // TensorFunctions::tensor_product (core/tensor_functions.hpp:2184-2288).  Products go to the
+    // recorder of `opf` through the reference's own OperatorFunctions::tensor_product.  A SumProd
+    // term whose pre-sum is not stored as an intermediate needs a temporary tmp = sum_i f_i op_i
+    // BEFORE the product that reads it: the stock method frees tmp right after recording, which is
+    // only valid when the list is executed at record time (Simple), so here the iadd entries go to
+    // a second recorder (`pre`, executed first) and the temporaries stay alive in `temps` until
+    // both lists have run.
+    typedef unordered_map<shared_ptr<OpExpr<S>>, shared_ptr<SparseMatrix<S, FL>>> OpMap;
+    void record_blocking_expr(const shared_ptr<OpExpr<S>> &expr, const OpMap &lop, const OpMap &rop,
+                              const shared_ptr<SparseMatrix<S, FL>> &mat,
+                              const shared_ptr<OperatorFunctions<S, FL>> &pre,
+                              vector<shared_ptr<SparseMatrix<S, FL>>> &temps) const {
+        const OpTypes ty = expr->get_type();
+        if (ty == OpTypes::Zero)
+            return;
+        if (ty == OpTypes::Sum) {
+            for (auto &x : dynamic_pointer_cast<OpSum<S, FL>>(expr)->strings)
+                record_blocking_expr(x->get_type() == OpTypes::Prod && x->b == nullptr
+                                         ? (shared_ptr<OpExpr<S>>)x->get_op()
+                                         : (shared_ptr<OpExpr<S>>)x,
+                                     lop, rop, mat, pre, temps);
+            return;
+        }
+        if (ty == OpTypes::Elem) { // singlet embedding: the partner is the identity of the other block
+            auto op = dynamic_pointer_cast<OpElement<S, FL>>(expr);
+            const shared_ptr<OpExpr<S>> ident = make_shared<OpExpr<S>>();
+            opf->tensor_product(0, lop.count(op) ? lop.at(op) : lop.at(ident), rop.count(op) ? rop.at(op) : rop.at(ident),
+                                mat, op->factor);
+            return;
+        }
+        if (ty == OpTypes::Prod) {
+            auto op = dynamic_pointer_cast<OpProduct<S, FL>>(expr);
+            opf->tensor_product(op->conj, lop.at(op->a), rop.at(op->b), mat, op->factor);
+            return;
+        }
+        if (ty != OpTypes::SumProd)
+            throw std::runtime_error("b2g: unexpected expression type in a blocking expression");
+        auto op = dynamic_pointer_cast<OpSumProd<S, FL>>(expr);
+        const bool sum_right = op->b == nullptr; // a (x) (sum of right operators), else (sum of left) (x) b
+        const OpMap &side = sum_right ? rop : lop;
+        shared_ptr<SparseMatrix<S, FL>> sum;
+        if (op->c != nullptr && side.count(op->c))
+            sum = side.at(op->c); // stored intermediate
+        else {
+            sum = make_shared<SparseMatrix<S, FL>>(make_shared<VectorAllocator<FL>>());
+            sum->allocate(side.at(abs_value((shared_ptr<OpExpr<S>>)op->ops[0]))->info);
+            for (size_t i = 0; i < op->ops.size(); i++)
+                pre->iadd(sum, side.at(abs_value((shared_ptr<OpExpr<S>>)op->ops[i])), op->ops[i]->factor,
+                          op->conjs[i]);
+            temps.push_back(sum);
+        }
+        if (sum_right)
+            opf->tensor_product(op->conj, lop.at(op->a), sum, mat, op->factor);
+        else
+            opf->tensor_product(op->conj, sum, rop.at(op->b), mat, op->factor);
+    }
+    int run_blocking_list(BatchGEMM<FL> &bt, b2g_blocking_stats &st) const {
+        static_assert(sizeof(CBLAS_TRANSPOSE) == sizeof(int32_t) && sizeof(MKL_INT) == sizeof(int32_t), "");
+        return b2g_batch_execute(session->ctx, (int64_t)bt.gp.size(), (const int32_t *)bt.ta.data(),
+                                 (const int32_t *)bt.tb.data(), bt.m.data(), bt.n.data(), bt.k.data(), bt.alpha.data(),
+                                 bt.a.data(), bt.lda.data(), bt.b.data(), bt.ldb.data(), bt.beta.data(), bt.c.data(),
+                                 bt.ldc.data(), bt.gp.data(), B2G_OPERANDS_HOST, B2G_DST_ZERO, &st);
+    }
+    // Blocking c[op] = sum a[x] (x) b[y] (core/tensor_functions.hpp:2842-2885 / 2941-2984): allocate the
+    // non-delayed, not yet cached operators as the stock method does, walk every expression in record-only
+    // mode, and execute on the device what the walk produced: b2g_tp_term descriptors when opf is a
+    // GPUOperatorFunctions (b2g_tensor_product_execute), otherwise the recorded GEMM list
+    // (b2g_batch_execute, in place of seq->auto_perform()).
+    void contract_on_device(const shared_ptr<OperatorTensor<S, FL>> &a, const shared_ptr<OperatorTensor<S, FL>> &b,
+                            shared_ptr<OperatorTensor<S, FL>> &c, const shared_ptr<Symbolic<S>> &exprs,
+                            const shared_ptr<Symbolic<S>> &names, OpNamesSet delayed, bool right) const {
+        Timer t, tr;
+        t.get_time();
+        auto &seq = opf->seq;
+        if (seq->batch[0]->gp.size() != 0 || seq->batch[1]->gp.size() != 0)
+            throw std::runtime_error("b2g: recorder not empty at contract");
+        assert(exprs->data.size() == names->data.size());
+        const SeqTypes saved = seq->mode;
+        shared_ptr<GPUOperatorFunctions<S>> gopf = dynamic_pointer_cast<GPUOperatorFunctions<S>>(opf);
+        const OpMap &lop = right ? b->ops : a->ops, &rop = right ? a->ops : b->ops;
+        vector<size_t> todo;
+        for (size_t i = 0; i < exprs->data.size(); i++) {
+            shared_ptr<OpElement<S, FL>> cop = dynamic_pointer_cast<OpElement<S, FL>>(names->data[i]);
+            shared_ptr<SparseMatrix<S, FL>> &m = c->ops.at(abs_value(names->data[i]));
+            if (delayed(cop->name) || m->alloc != nullptr) // delayed, or the cached part
+                continue;
+            m->alloc = make_shared<VectorAllocator<FL>>();
+            m->allocate(m->info);
+            todo.push_back(i);
+        }
+        // record-only walk; the SumProd pre-sums go to `pre`, their temporaries to `temps`
+        auto walk = [&](const shared_ptr<OperatorFunctions<S, FL>> &pre, vector<shared_ptr<SparseMatrix<S, FL>>> &temps) {
+            seq->mode = SeqTypes::Auto;
+            pre->seq->mode = SeqTypes::Auto;
+            for (size_t i : todo) {
+                shared_ptr<OpElement<S, FL>> cop = dynamic_pointer_cast<OpElement<S, FL>>(names->data[i]);
+                record_blocking_expr(exprs->data[i] * ((FL)1.0 / cop->factor), lop, rop,
+                                     c->ops.at(abs_value(names->data[i])), pre, temps);
+            }
+            seq->mode = saved;
+            if (seq->batch[0]->gp.size() != 0 || pre->seq->batch[0]->gp.size() != 0)
+                throw std::runtime_error("b2g: blocking list has chained pairs");
+        };
+        auto account = [&](const b2g_blocking_stats &st) {
+            session->contract_entries += (size_t)st.entries, session->contract_kernel_ms += st.kernel_ms;
+            session->contract_bytes += (double)(st.bytes_in + st.bytes_out);
+            session->t_contract_plan += st.plan_seconds, session->t_contract_upload += st.upload_seconds;
+            session->t_contract_download += st.download_seconds;
+            seq->cumulative_nflop += (size_t)st.nflop_mnk;
+        };
+        b2g_blocking_stats st;
+        vector<shared_ptr<SparseMatrix<S, FL>>> temps;
+        shared_ptr<OperatorFunctions<S, FL>> pre = make_shared<OperatorFunctions<S, FL>>(opf->cg);
+        if (gopf != nullptr)
+            gopf->collector->clear(), gopf->collector->active = true;
+        tr.get_time();
+        walk(pre, temps);
+        session->t_contract_record += tr.get_time();
+        if (gopf != nullptr)
+            gopf->collector->active = false;
+        if (pre->seq->batch[1]->gp.size() != 0) {
+            if (run_blocking_list(*pre->seq->batch[1], st) != 0)
+                throw std::runtime_error(std::string("b2g_batch_execute: ") + b2g_last_error());
+            account(st);
+        }
+        if (gopf != nullptr) {
+            vector<b2g_tp_term> &terms = gopf->collector->per_thread[0];
+            for (size_t k = 1; k < gopf->collector->per_thread.size(); k++)
+                terms.insert(terms.end(), gopf->collector->per_thread[k].begin(), gopf->collector->per_thread[k].end());
+            if (terms.size() != 0) {
+                if (b2g_tensor_product_execute(session->ctx, (int64_t)terms.size(), terms.data(), B2G_OPERANDS_HOST,
+                                               B2G_DST_ZERO, &st) != 0)
+                    throw std::runtime_error(std::string("b2g_tensor_product_execute: ") + b2g_last_error());
+                account(st);
+            }
+            gopf->collector->clear();
+        } else if (seq->batch[1]->gp.size() != 0) {
+            if (run_blocking_list(*seq->batch[1], st) != 0)
+                throw std::runtime_error(std::string("b2g_batch_execute: ") + b2g_last_error());
+            account(st);
+        }
+        seq->clear(), pre->seq->clear();
+        if (session->verify && todo.size() != 0) {
+            // the reference's own executor on the list its own recorder makes of the same expressions
+            vector<vector<double>> gpu;
+            for (size_t i : todo) {
+                auto &m = c->ops.at(abs_value(names->data[i]));
+                gpu.emplace_back(m->data, m->data + m->total_memory);
+                memset(m->data, 0, sizeof(double) * m->total_memory);
+            }
+            vector<shared_ptr<SparseMatrix<S, FL>>> temps2;
+            shared_ptr<OperatorFunctions<S, FL>> pre2 = make_shared<OperatorFunctions<S, FL>>(opf->cg);
+            walk(pre2, temps2);
+            pre2->seq->auto_perform();
+            seq->mode = SeqTypes::Auto;
+            seq->auto_perform();
+            seq->mode = saved;
+            seq->clear(), pre2->seq->clear();
+            double num = 0, den = 0;
+            size_t z = 0;
+            for (size_t i : todo) {
+                auto &m = c->ops.at(abs_value(names->data[i]));
+                for (size_t j = 0; j < m->total_memory; j++)
+                    num += (gpu[z][j] - m->data[j]) * (gpu[z][j] - m->data[j]), den += m->data[j] * m->data[j];
+                memcpy(m->data, gpu[z++].data(), sizeof(double) * m->total_memory);
+            }
+            session->max_contract_err = max(session->max_contract_err, den > 0 ? sqrt(num / den) : sqrt(num));
+            for (auto &m : temps2)
+                m->deallocate();
+        }
+        for (auto &m : temps)
+            m->deallocate();
+        session->t_contract += t.get_time(), session->n_contract++;
+    }
+    void left_contract(const shared_ptr<OperatorTensor<S, FL>> &a, const shared_ptr<OperatorTensor<S, FL>> &b,
+                       shared_ptr<OperatorTensor<S, FL>> &c, const shared_ptr<Symbolic<S>> &cexprs = nullptr,
+                       OpNamesSet delayed = OpNamesSet()) const override {
+        if (!session->gpu_contract || session->recording || a == nullptr || prule != nullptr ||
+            frame_<FL>()->use_main_stack)
+            return Base::left_contract(a, b, c, cexprs, delayed);
+        contract_on_device(a, b, c, cexprs == nullptr ? a->lmat * b->lmat : cexprs, c->lmat, delayed, false);
+    }
+    void right_contract(const shared_ptr<OperatorTensor<S, FL>> &a, const shared_ptr<OperatorTensor<S, FL>> &b,
+                        shared_ptr<OperatorTensor<S, FL>> &c, const shared_ptr<Symbolic<S>> &cexprs = nullptr,
+                        OpNamesSet delayed = OpNamesSet()) const override {
+        if (!session->gpu_contract || session->recording || a == nullptr || prule != nullptr ||
+            frame_<FL>()->use_main_stack)
+            return Base::right_contract(a, b, c, cexprs, delayed);
+        contract_on_device(a, b, c, cexprs == nullptr ? b->rmat * a->rmat : cexprs, c->rmat, delayed, true);
     }
     void left_rotate(const shared_ptr<OperatorTensor<S, FL>> &a, const shared_ptr<SparseMatrix<S, FL>> &mpst_bra,
                      const shared_ptr<SparseMatrix<S, FL>> &mpst_ket,
@@ -310,7 +573,10 @@ template <typename S> struct GPUDMRG : DMRG<S, double, double> {
 template <typename S>
 inline shared_ptr<Session> install(const shared_ptr<MPO<S, double>> &mpo, int device = 0) {
     shared_ptr<Session> session = make_shared<Session>(device);
-    mpo->tf = make_shared<GPUTensorFunctions<S>>(mpo->tf->opf, session);
+    shared_ptr<GPUOperatorFunctions<S>> gopf =
+        make_shared<GPUOperatorFunctions<S>>(mpo->tf->opf->cg, make_shared<TermCollector>());
+    gopf->seq = mpo->tf->opf->seq;
+    mpo->tf = make_shared<GPUTensorFunctions<S>>(gopf, session);
     return session;
 }
 

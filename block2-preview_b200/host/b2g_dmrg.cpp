@@ -21,7 +21,7 @@ struct Args {
     string fcidump, pg = "d2h", occ = "", scratch = "/tmp/b2g_scratch", davidson = "device";
     int bond = 250, n_sweeps = 6, threads = 8, seed = 0, device = 0, ranks = 1, rank = 0;
     string shm = "b2g";
-    bool compare = false, verify = false, gpu_rotate = false;
+    bool compare = false, verify = false, gpu_rotate = false, gpu_contract = false;
     double conv = 1e-7, noise = 1e-5;
     size_t dsize_gb = 8;
 };
@@ -113,12 +113,13 @@ int main(int argc, char **argv) {
         else if (k == "--compare") a.compare = true;
         else if (k == "--verify") a.verify = true;
         else if (k == "--gpu-rotate") a.gpu_rotate = true;
+        else if (k == "--gpu-contract") a.gpu_contract = true;
         else if (k == "--ranks") a.ranks = atoi(nxt().c_str());
         else if (k == "--rank") a.rank = atoi(nxt().c_str());
         else if (k == "--shm") a.shm = nxt();
         else {
             fprintf(stderr, "usage: b2g_dmrg --fcidump F [--pg d2h] [--bond M] [--nsweeps n] [--threads t] "
-                            "[--davidson host|device] [--compare] [--verify] [--gpu-rotate] [--occ F] [--noise x] [--conv x]\n");
+                            "[--davidson host|device] [--compare] [--verify] [--gpu-rotate] [--gpu-contract] [--occ F] [--noise x] [--conv x]\n");
             return 2;
         }
     }
@@ -169,6 +170,7 @@ int main(int argc, char **argv) {
         a.ranks > 1 ? b2g_host::install_parallel<S>(mpo, a.device) : b2g_host::install<S>(mpo, a.device);
     session->verify = a.verify;
     session->gpu_rotate = a.gpu_rotate;
+    session->gpu_contract = a.gpu_contract;
     RunResult gpu = run_dmrg<S>(a, mpo, hamil, target, true);
     for (size_t i = 0; i < gpu.energies.size(); i++) {
         if (a.compare && i < ref.energies.size())
@@ -189,13 +191,20 @@ int main(int argc, char **argv) {
            "\"t_ref\": %.3f, \"threads\": %d, \"e_gpu\": %.12f, \"e_ref\": %.12f, \"max_sweep_diff\": %.3e, "
            "\"plans\": %zu, \"host_matvecs\": %zu, \"t_plan\": %.3f, \"t_host_matvec\": %.3f, \"launches\": %lld, "
            "\"matvec_sites_verified\": %zu, \"max_matvec_rel_err\": %.3e, \"gpu_rotate\": %d, \"rotations\": %zu, "
-           "\"t_rotate\": %.3f, \"rotate_gflop\": %.3f, \"max_rotate_rel_err\": %.3e}\n",
+           "\"t_rotate\": %.3f, \"rotate_gflop\": %.3f, \"max_rotate_rel_err\": %.3e, \"gpu_contract\": %d, "
+           "\"contractions\": %zu, \"t_contract\": %.3f, \"contract_entries\": %zu, \"contract_kernel_ms\": %.3f, "
+           "\"contract_gbytes\": %.4f, \"max_contract_rel_err\": %.3e, "
+           "\"t_contract_record\": %.3f, \"t_contract_plan\": %.3f, \"t_contract_upload\": %.3f, "
+           "\"t_contract_download\": %.3f}\n",
            a.ranks, a.davidson.c_str(), a.bond, gpu.energies.size(), gpu.total, ref.total, a.threads,
            gpu.energies.empty() ? 0.0 : gpu.energies.back(), ref.energies.empty() ? 0.0 : ref.energies.back(),
            maxdiff, session->n_plan, session->n_matvec, session->t_plan, session->t_matvec,
            (long long)b2g_context_launches(session->ctx), session->n_verified, session->max_matvec_err,
            (int)a.gpu_rotate, session->n_rotate, session->t_rotate, session->rotate_flops * 1e-9,
-           session->max_rotate_err);
+           session->max_rotate_err, (int)a.gpu_contract, session->n_contract, session->t_contract,
+           session->contract_entries, session->contract_kernel_ms, session->contract_bytes * 1e-9,
+           session->max_contract_err, session->t_contract_record, session->t_contract_plan,
+           session->t_contract_upload, session->t_contract_download);
     fflush(stdout);
     _exit(0);
 }

@@ -15,6 +15,16 @@
  *   b2g_pairs_execute    <- OperatorFunctions::tensor_rotate lists executed by BatchGEMMSeq::auto_perform /
  *                           simple_perform (left_rotate / right_rotate, core/tensor_functions.hpp:2365-2403)
  *   b2g_dgemm_batch      <- cblas_xgemm_batch / BatchGEMM::perform  core/batch_gemm.hpp:81-111, 339-357
+ *   b2g_batch_execute    <- BatchGEMMSeq::auto_perform / simple_perform on a single-batch (batch[1]-only) list
+ *                           core/batch_gemm.hpp:1417-1530: the blocking lists TensorFunctions::left_contract /
+ *                           right_contract record (core/tensor_functions.hpp:2842-2885, 2941-2984) through
+ *                           OperatorFunctions::tensor_product (core/operator_functions.hpp:672-711) and
+ *                           AdvancedGEMM::tensor_product (core/batch_gemm.hpp:433-503), plus iadd / iscale /
+ *                           tensor_product_diagonal entries (:1110-1135, 327-336, 506-511)
+ *   b2g_tensor_product_execute
+ *                        <- the same blocking step one level up: the GMatrixFunctions::tensor_product calls
+ *                           (core/matrix_functions.hpp:1269-1397) OperatorFunctions::tensor_product makes per
+ *                           connection-info entry (core/operator_functions.hpp:672-711)
  *   b2g_davidson         <- IterativeMatrixFunctions<double>::davidson (k = 1, Normal type,
  *                           Olsen preconditioner)  core/iterative_matrix_functions.hpp:864-1173, 93-108
  *   b2g_comm_* / b2g_allreduce_sum
@@ -118,6 +128,59 @@ int b2g_dgemm_batch(b2g_context *ctx, int64_t group_count, const int32_t *ta, co
                     const double *const *a, const int32_t *lda, const double *const *b,
                     const int32_t *ldb, const double *beta, double *const *c, const int32_t *ldc,
                     const int32_t *group_size);
+
+/* per-call record of b2g_batch_execute */
+typedef struct b2g_blocking_stats {
+    int64_t entries;        /* GEMMs of the list after group expansion */
+    int64_t merged;         /* entries after constant-stride rows were folded into 2-D windows */
+    int64_t clusters;       /* distinct output windows (each written once, contributions summed in registers) */
+    int64_t units;          /* warp work units */
+    int64_t serial_entries; /* entries of irregularly overlapping windows (executed in list order by one CTA) */
+    int64_t nflop_mnk;      /* sum m*n*k (reference units) */
+    int64_t bytes_in;       /* 8 * source elements read (algorithmic) */
+    int64_t bytes_out;      /* 8 * destination elements written (algorithmic) */
+    int64_t launches;
+    double kernel_ms;       /* CUDA events around the kernels on the context stream */
+    double upload_seconds, download_seconds, plan_seconds;
+} b2g_blocking_stats;
+
+#define B2G_DST_ZERO 1 /* caller guarantees every output block is zero on entry (freshly allocate()d operators):
+                          outputs are not uploaded, the device result is added into the host blocks */
+
+/* Execute a recorded single-batch GEMM list (cblas_dgemm_batch group signature, exactly the arrays of
+ * BatchGEMM<double>: per-group parameters, per-entry pointers) whose entries may write the SAME output
+ * blocks - the conflict-carrying list BatchGEMMSeq::auto_perform resolves with work arrays and a
+ * post-batch reduction.  Entry semantics: C = alpha * op(A) * op(B) + beta * C, applied per output
+ * element IN LIST ORDER (the order simple_perform would execute them), each output element by one thread:
+ * deterministic, no atomics.  operand_space = B2G_OPERANDS_HOST: all pointers are host addresses, inputs
+ * are mirrored, results copied back (synchronous).  B2G_OPERANDS_DEVICE: all pointers are device
+ * addresses, asynchronous on the context stream apart from the plan upload. */
+int b2g_batch_execute(b2g_context *ctx, int64_t group_count, const int32_t *ta, const int32_t *tb,
+                      const int32_t *m, const int32_t *n, const int32_t *k, const double *alpha,
+                      const double *const *a, const int32_t *lda, const double *const *b,
+                      const int32_t *ldb, const double *beta, double *const *c, const int32_t *ldc,
+                      const int32_t *group_size, int operand_space, int flags, b2g_blocking_stats *stats);
+
+/* One eager tensor-product call of the blocking step, GMatrixFunctions<double>::tensor_product(a, conja, b,
+ * conjb, c, scale, stride) (core/matrix_functions.hpp:1269-1397) as emitted per connection-info entry by
+ * OperatorFunctions::tensor_product (core/operator_functions.hpp:672-711):
+ *     C[(i*bm' + k), (j*bn' + l)] += scale * op(A)(i, j) * op(B)(k, l)
+ * a: am x an row-major block, b: bm x bn row-major block, op = transpose when conj != 0,
+ * c: address of the window's first element (block base + stride), cn: pitch of the output block. */
+typedef struct b2g_tp_term {
+    const double *a;
+    const double *b;
+    double *c;
+    int32_t am, an, bm, bn, cn;
+    int32_t conja, conjb, reserved;
+    double scale;
+} b2g_tp_term;
+
+/* Execute a list of tensor-product terms; terms that write the same window are applied in list order by
+ * the thread that owns the output element (same back end and flags as b2g_batch_execute).  This is the
+ * compact form of the blocking list: one descriptor per (a-block, b-block) pair instead of one GEMM per row. */
+int b2g_tensor_product_execute(b2g_context *ctx, int64_t count, const b2g_tp_term *terms, int operand_space,
+                               int flags, b2g_blocking_stats *stats);
 
 /* Davidson ground state with device-resident vectors; H applied through the plan.
  * ket_host: in = initial guess, out = eigenvector.  diag_host: H_eff diagonal.

@@ -47,7 +47,7 @@ struct Args {
         dav_max = 4000, seed = 0;
     bool with_data = true, structure_only = false, run_eigs = true;
     double conv = 1e-7, noise = 1e-5, max_gflop = 0;
-    int warmup = 1, ranks = 1, rank = 0;
+    int warmup = 1, ranks = 1, rank = 0, blk_call = 0;
     string shm = "";
     size_t dsize_gb = 8;
 };
@@ -93,6 +93,7 @@ static Args parse(int argc, char **argv) {
         else if (k == "--ranks") a.ranks = atoi(nxt().c_str());
         else if (k == "--rank") a.rank = atoi(nxt().c_str());
         else if (k == "--shm") a.shm = nxt();
+        else if (k == "--blk-call") a.blk_call = atoi(nxt().c_str());
         else if (k == "--nodata") a.with_data = false;
         else if (k == "--noeigs") a.run_eigs = false;
         else if (k == "--struct") a.structure_only = true, a.with_data = false, a.run_eigs = false;
@@ -274,6 +275,181 @@ struct StructTensorFunctions : Base {
                                  S opdq) const override {}
 };
 
+template <typename T> static void wr(FILE *f, const vector<T> &v);
+
+/* ---------- blkdump: the blocking list of one left_contract / right_contract call ----------
+ * The N-th blocking call with a renormalised environment (a != nullptr) is recorded in
+ * SeqTypes::Auto through the reference's own TensorFunctions::tensor_product ->
+ * OperatorFunctions::tensor_product -> AdvancedGEMM::tensor_product (tensor_functions.hpp:2842-2885,
+ * operator_functions.hpp:672-711, batch_gemm.hpp:433-503), written to a .b2blk file together with the
+ * operand data, and then executed by the reference's own BatchGEMMSeq::auto_perform
+ * (batch_gemm.hpp:1417); the resulting blocked operators are stored as the expected output.
+ *
+ * .b2blk (little endian): magic "B2BLK\0\0\1"; u64[8] ngroups nentries n_in n_out nflop is_right call 0;
+ * i32[ngroups] x 9: ta tb m n k lda ldb ldc gp; f64[ngroups] x 2: alpha beta;
+ * i64[nentries] x 6: a_arena a_off b_arena b_off c_arena c_off; u64[n_in] input arena sizes;
+ * u64[n_out] output arena sizes; f64 input arenas; f64 output arenas before; f64 output arenas after. */
+struct BlkInterval {
+    uintptr_t lo, hi;
+};
+static vector<BlkInterval> blk_merge(vector<BlkInterval> iv) {
+    sort(iv.begin(), iv.end(), [](const BlkInterval &x, const BlkInterval &y) { return x.lo < y.lo; });
+    vector<BlkInterval> ar;
+    for (auto &x : iv) {
+        if (x.hi == x.lo)
+            continue;
+        if (ar.size() && x.lo <= ar.back().hi)
+            ar.back().hi = max(ar.back().hi, x.hi);
+        else
+            ar.push_back(x);
+    }
+    return ar;
+}
+static void blk_locate(const vector<BlkInterval> &ar, uintptr_t p, int64_t &ia, int64_t &off) {
+    size_t lo = 0, hi = ar.size();
+    while (hi - lo > 1) {
+        size_t mid = (lo + hi) / 2;
+        if (ar[mid].lo <= p)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    ia = (int64_t)lo, off = (int64_t)((p - ar[lo].lo) / 8);
+}
+template <typename S, typename FL> struct BlkDumpTensorFunctions : TensorFunctions<S, FL> {
+    typedef TensorFunctions<S, FL> Base;
+    using Base::opf;
+    const Args *args;
+    mutable int counter = 0;
+    BlkDumpTensorFunctions(const shared_ptr<OperatorFunctions<S, FL>> &opf, const Args *args)
+        : Base(opf), args(args) {}
+    shared_ptr<TensorFunctions<S, FL>> copy() const override {
+        return make_shared<BlkDumpTensorFunctions<S, FL>>(opf->copy(), args);
+    }
+    void record_and_dump(const shared_ptr<OperatorTensor<S, FL>> &a, const shared_ptr<OperatorTensor<S, FL>> &b,
+                         shared_ptr<OperatorTensor<S, FL>> &c, const shared_ptr<Symbolic<S>> &exprs,
+                         const shared_ptr<Symbolic<S>> &names, OpNamesSet delayed, bool right) const {
+        auto &seq = opf->seq;
+        const SeqTypes saved = seq->mode;
+        seq->mode = SeqTypes::Auto; // record only
+        for (size_t i = 0; i < exprs->data.size(); i++) {
+            shared_ptr<OpElement<S, FL>> cop = dynamic_pointer_cast<OpElement<S, FL>>(names->data[i]);
+            shared_ptr<OpExpr<S>> op = abs_value(names->data[i]);
+            shared_ptr<OpExpr<S>> expr = exprs->data[i] * ((FL)1.0 / cop->factor);
+            if (delayed(cop->name) || c->ops.at(op)->alloc != nullptr)
+                continue;
+            c->ops.at(op)->alloc = make_shared<VectorAllocator<FL>>();
+            c->ops.at(op)->allocate(c->ops.at(op)->info);
+            if (right)
+                this->tensor_product(expr, b->ops, a->ops, c->ops.at(op));
+            else
+                this->tensor_product(expr, a->ops, b->ops, c->ops.at(op));
+        }
+        auto &bt = *seq->batch[1];
+        if (seq->batch[0]->gp.size() != 0) {
+            fprintf(stderr, "blkdump: unexpected batch[0] entries\n");
+            exit(1);
+        }
+        const size_t ng = bt.gp.size(), ne = bt.c.size();
+        vector<BlkInterval> iin, iout;
+        for (size_t g = 0, z = 0; g < ng; g++)
+            for (int q = 0; q < bt.gp[g]; q++, z++) {
+                const bool ta = bt.ta[g] != CblasNoTrans, tb = bt.tb[g] != CblasNoTrans;
+                size_t ea = op_extent_blk(ta ? bt.k[g] : bt.m[g], ta ? bt.m[g] : bt.k[g], bt.lda[g]);
+                size_t eb = op_extent_blk(tb ? bt.n[g] : bt.k[g], tb ? bt.k[g] : bt.n[g], bt.ldb[g]);
+                size_t ec = op_extent_blk(bt.m[g], bt.n[g], bt.ldc[g]);
+                iin.push_back(BlkInterval{(uintptr_t)bt.a[z], (uintptr_t)bt.a[z] + 8 * ea});
+                iin.push_back(BlkInterval{(uintptr_t)bt.b[z], (uintptr_t)bt.b[z] + 8 * eb});
+                iout.push_back(BlkInterval{(uintptr_t)bt.c[z], (uintptr_t)bt.c[z] + 8 * ec});
+            }
+        vector<BlkInterval> ain = blk_merge(iin), aout = blk_merge(iout);
+        vector<int32_t> i32[9];
+        vector<double> f64[2];
+        vector<int64_t> i64[6];
+        for (auto &v : i32) v.resize(ng);
+        for (auto &v : f64) v.resize(ng);
+        for (auto &v : i64) v.resize(ne);
+        for (size_t g = 0; g < ng; g++) {
+            i32[0][g] = bt.ta[g] != CblasNoTrans, i32[1][g] = bt.tb[g] != CblasNoTrans;
+            i32[2][g] = bt.m[g], i32[3][g] = bt.n[g], i32[4][g] = bt.k[g];
+            i32[5][g] = bt.lda[g], i32[6][g] = bt.ldb[g], i32[7][g] = bt.ldc[g], i32[8][g] = bt.gp[g];
+            f64[0][g] = bt.alpha[g], f64[1][g] = bt.beta[g];
+        }
+        for (size_t z = 0; z < ne; z++) {
+            blk_locate(ain, (uintptr_t)bt.a[z], i64[0][z], i64[1][z]);
+            blk_locate(ain, (uintptr_t)bt.b[z], i64[2][z], i64[3][z]);
+            blk_locate(aout, (uintptr_t)bt.c[z], i64[4][z], i64[5][z]);
+        }
+        // A SumProd term without a stored intermediate makes the stock walker record iadd entries into
+        // a temporary it frees right away (tensor_functions.hpp:2228-2270): such a list is only valid
+        // when executed at record time, not under Auto.  Its freed outputs show up as non-zero output
+        // memory here; refuse to make a fixture of it.
+        for (size_t i = 0; i < aout.size(); i++)
+            for (const double *p = (const double *)aout[i].lo; p < (const double *)aout[i].hi; p++)
+                if (*p != 0.0) {
+                    printf("BLKDUMP call=%d skipped: list writes a freed temporary (SumProd without intermediate)\n",
+                           args->blk_call);
+                    fflush(stdout);
+                    _exit(3);
+                }
+        FILE *f = fopen(args->out.c_str(), "wb");
+        if (!f) {
+            perror("fopen");
+            exit(1);
+        }
+        const char magic[8] = {'B', '2', 'B', 'L', 'K', 0, 0, 1};
+        fwrite(magic, 1, 8, f);
+        vector<uint64_t> hdr(8, 0);
+        hdr[0] = ng, hdr[1] = ne, hdr[2] = ain.size(), hdr[3] = aout.size(), hdr[4] = bt.nflop;
+        hdr[5] = right ? 1 : 0, hdr[6] = (uint64_t)args->blk_call;
+        wr(f, hdr);
+        for (auto &v : i32) wr(f, v);
+        for (auto &v : f64) wr(f, v);
+        for (auto &v : i64) wr(f, v);
+        vector<uint64_t> szin(ain.size()), szout(aout.size());
+        size_t tin = 0, tout = 0;
+        for (size_t i = 0; i < ain.size(); i++)
+            szin[i] = (ain[i].hi - ain[i].lo) / 8, tin += szin[i];
+        for (size_t i = 0; i < aout.size(); i++)
+            szout[i] = (aout[i].hi - aout[i].lo) / 8, tout += szout[i];
+        wr(f, szin);
+        wr(f, szout);
+        for (size_t i = 0; i < ain.size(); i++)
+            fwrite((const void *)ain[i].lo, 8, szin[i], f);
+        for (size_t i = 0; i < aout.size(); i++)
+            fwrite((const void *)aout[i].lo, 8, szout[i], f);
+        // the reference's own executor on the list it just recorded
+        seq->auto_perform();
+        seq->mode = saved;
+        for (size_t i = 0; i < aout.size(); i++)
+            fwrite((const void *)aout[i].lo, 8, szout[i], f);
+        fclose(f);
+        printf("BLKDUMP %s call=%d %s groups=%zu entries=%zu in_arenas=%zu (%zu doubles) out_arenas=%zu (%zu doubles) "
+               "nflop_mnk=%zu\n",
+               args->out.c_str(), args->blk_call, right ? "right_contract" : "left_contract", ng, ne, ain.size(), tin,
+               aout.size(), tout, (size_t)hdr[4]);
+        fflush(stdout);
+        _exit(0);
+    }
+    static size_t op_extent_blk(int rows, int cols, int ld) {
+        return rows == 0 || cols == 0 ? 0 : (size_t)(rows - 1) * ld + cols;
+    }
+    void left_contract(const shared_ptr<OperatorTensor<S, FL>> &a, const shared_ptr<OperatorTensor<S, FL>> &b,
+                       shared_ptr<OperatorTensor<S, FL>> &c, const shared_ptr<Symbolic<S>> &cexprs = nullptr,
+                       OpNamesSet delayed = OpNamesSet()) const override {
+        if (a == nullptr || counter++ != args->blk_call)
+            return Base::left_contract(a, b, c, cexprs, delayed);
+        record_and_dump(a, b, c, cexprs == nullptr ? a->lmat * b->lmat : cexprs, c->lmat, delayed, false);
+    }
+    void right_contract(const shared_ptr<OperatorTensor<S, FL>> &a, const shared_ptr<OperatorTensor<S, FL>> &b,
+                        shared_ptr<OperatorTensor<S, FL>> &c, const shared_ptr<Symbolic<S>> &cexprs = nullptr,
+                        OpNamesSet delayed = OpNamesSet()) const override {
+        if (a == nullptr || counter++ != args->blk_call)
+            return Base::right_contract(a, b, c, cexprs, delayed);
+        record_and_dump(a, b, c, cexprs == nullptr ? b->rmat * a->rmat : cexprs, c->rmat, delayed, true);
+    }
+};
+
 /* ---------- one rank of a P-rank ParallelRuleQC run, without MPI ----------
  * --ranks P --rank r builds the reference's own ParallelMPO (parallel_mpo.hpp:150, NewScheme)
  * over ParallelRuleQC (qc_parallel_rule.hpp:44-80) for rank r of P.  Under NewScheme the blocking
@@ -452,7 +628,7 @@ template <typename S> struct StopDMRG : DMRG<S, double, double> {
                              const double davidson_conv_thrd,
                              const double noise,
                              shared_ptr<SparseMatrixGroup<S, double>> &pket) override {
-        if (args.mode == "dmrg" || this->isweep != args.sweeps ||
+        if (args.mode == "dmrg" || args.mode == "blkdump" || this->isweep != args.sweeps ||
             i != target_site)
             return Base::two_dot_eigs_and_perturb(forward, i,
                                                   davidson_conv_thrd, noise, pket);
@@ -732,6 +908,9 @@ template <typename S> static int run(const Args &args) {
             mpo->tf = make_shared<StructTensorFunctions<S, FL>>(mpo->tf->opf);
     }
 
+    if (args.mode == "blkdump")
+        mpo->tf = make_shared<BlkDumpTensorFunctions<S, FL>>(mpo->tf->opf, &args);
+
     ubond_t bond_dim = (ubond_t)args.bond;
     shared_ptr<MPSInfo<S>> mps_info =
         make_shared<MPSInfo<S>>(norb, vacuum, target, hamil->basis);
@@ -741,7 +920,7 @@ template <typename S> static int run(const Args &args) {
     } else
         mps_info->set_bond_dimension(bond_dim);
     int site = args.site < 0 ? norb / 2 - 1 : args.site;
-    int center = (args.mode != "dmrg" && args.sweeps == 0) ? site : 0;
+    int center = (args.mode != "dmrg" && args.mode != "blkdump" && args.sweeps == 0) ? site : 0;
     Random::rand_seed(args.seed);
     shared_ptr<MPS<S, FL>> mps = make_shared<MPS<S, FL>>(norb, center, 2);
     mps->initialize(mps_info);
@@ -772,7 +951,7 @@ template <typename S> static int run(const Args &args) {
     dmrg->noise_type = NoiseTypes::DensityMatrix;
     dmrg->decomp_type = DecompositionTypes::DensityMatrix;
     dmrg->davidson_soft_max_iter = args.dav_max;
-    int n_sweeps = args.mode == "dmrg" ? args.n_sweeps : args.sweeps + 1;
+    int n_sweeps = (args.mode == "dmrg" || args.mode == "blkdump") ? args.n_sweeps : args.sweeps + 1;
     Timer ts;
     ts.get_time();
     double energy = (double)dmrg->solve(n_sweeps, mps->center == 0, args.conv * 0.1);

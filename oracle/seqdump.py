@@ -240,3 +240,40 @@ def replay_numpy(d: SeqDump, c: np.ndarray | None = None, scale: float = 1.0,
         C = view(v, int(P["c1_off"][i]), m1, n1, int(P["ldc1"][i]))
         C += (P["alpha1"][i] * scale) * (A1 @ W)
     return v
+
+
+def batch_perform(ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, group_size) -> None:
+    """Sequential execution of a grouped GEMM list on host pointers (integer addresses) through
+    the plain-C restatement b2o_dgemm_batch (oracle/replay.c; cblas_xgemm_batch semantics,
+    batch_gemm.hpp:81-111): entry by entry in list order, which is what BatchGEMMSeq::simple_perform
+    produces and what auto_perform reproduces up to the order of additions."""
+    i32 = lambda x: np.ascontiguousarray(x, dtype=np.int32)
+    f64 = lambda x: np.ascontiguousarray(x, dtype=np.float64)
+    u64 = lambda x: np.ascontiguousarray(x, dtype=np.uint64)
+    ta, tb, m, n, k, lda, ldb, ldc, gs = map(i32, (np.asarray(ta) == 112, np.asarray(tb) == 112, m, n, k, lda, ldb,
+                                                   ldc, group_size))
+    alpha, beta, a, b, c = f64(alpha), f64(beta), u64(a), u64(b), u64(c)
+    L = lib()
+    L.b2o_dgemm_batch.restype = None
+    L.b2o_dgemm_batch.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 14
+    L.b2o_dgemm_batch(len(gs), ta.ctypes.data, tb.ctypes.data, m.ctypes.data, n.ctypes.data, k.ctypes.data,
+                      alpha.ctypes.data, a.ctypes.data, lda.ctypes.data, b.ctypes.data, ldb.ctypes.data,
+                      beta.ctypes.data, c.ctypes.data, ldc.ctypes.data, gs.ctypes.data)
+
+
+def tensor_product_terms(terms, read, write) -> None:
+    """numpy restatement of a list of eager GMatrixFunctions<double>::tensor_product calls
+    (matrix_functions.hpp:1269-1397): for every term, in list order,
+        C[(i*bm' + k), (j*bn' + l)] += scale * op(A)(i, j) * op(B)(k, l)
+    terms: iterable of dicts (a, b, c = element offsets; am an bm bn cn conja conjb scale);
+    read(off, n) -> view of n source doubles; write(off, rows, cols, pitch) -> 2-D output view."""
+    for t in terms:
+        A = read(t["a"], t["am"] * t["an"]).reshape(t["am"], t["an"])
+        B = read(t["b"], t["bm"] * t["bn"]).reshape(t["bm"], t["bn"])
+        if t["conja"]:
+            A = A.T
+        if t["conjb"]:
+            B = B.T
+        K = np.kron(A, B)
+        W = write(t["c"], K.shape[0], K.shape[1], t["cn"])
+        W += t["scale"] * K
