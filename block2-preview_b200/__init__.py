@@ -26,6 +26,7 @@ import numpy as np
 
 from .blkfile import BlkFile, load_blkfile  # noqa: F401
 from .seqfile import SeqFile, load_seqfile  # noqa: F401
+from .tpfile import TPFile, load_tpfile  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2g.so")

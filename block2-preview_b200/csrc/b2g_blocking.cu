@@ -19,6 +19,7 @@
 #include "b2g_internal.h"
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -36,10 +37,9 @@ static_assert(sizeof(BlkEntry) == 64, "BlkEntry layout");
 
 struct BlkUnit { // one warp: `len` consecutive logical elements of one output window
     double *dst;
-    int64_t e0;
-    int32_t len, n, ldc, first, count, pad;
+    int32_t e0, len, n, ldc, first, count;
 };
-static_assert(sizeof(BlkUnit) == 40, "BlkUnit layout");
+static_assert(sizeof(BlkUnit) == 32, "BlkUnit layout");
 
 struct BlkSerial { // entry of an irregularly overlapping component, with its own window
     BlkEntry e;
@@ -47,8 +47,8 @@ struct BlkSerial { // entry of an irregularly overlapping component, with its ow
     int32_t m, n, ldc, comp;
 };
 
-constexpr int UNIT_ELEMS = 128; // 4 per lane
-constexpr int PER_LANE = UNIT_ELEMS / 32;
+constexpr int UNIT_ELEMS = 2048; // elements per warp unit
+constexpr int PER_LANE = 4;      // elements per lane and sub-chunk
 constexpr int BLK_THREADS = 256;
 
 __device__ __forceinline__ double blk_apply(const BlkEntry &E, double acc, int64_t i, int64_t j) {
@@ -73,44 +73,203 @@ __device__ __forceinline__ double blk_apply(const BlkEntry &E, double acc, int64
 }
 
 // AXPY windows (every contribution is k = 1 with one scalar B): one warp per unit, persistent
-// grid-stride over units, 4 elements per lane held in registers across the contributions.
+// grid-stride over units.  A unit is up to UNIT_ELEMS consecutive logical elements of one output window;
+// the warp walks it in sub-chunks of 128 elements (4 per lane, running values in registers across the
+// contributions), so the unit / entry descriptors are fetched once per UNIT_ELEMS elements and the
+// loads of a sub-chunk are independent.  Index arithmetic is 32-bit, and the division by the window
+// width is only done for windows / sources that are not linear in the element index.
 // dst_zero: outputs start from 0 (not read).
-__global__ void __launch_bounds__(BLK_THREADS, 4)
+__device__ __forceinline__ int64_t blk_src_index(const BlkEntry &E, int32_t e, int32_t n) {
+    // e: logical element of the window; n: window width (1 = flat)
+    if (E.nd) { // flat window, this entry's own width
+        const uint32_t i = (uint32_t)e / (uint32_t)E.nd, j = (uint32_t)e - i * (uint32_t)E.nd;
+        return (int64_t)i * E.sa_i + (int64_t)j * E.sa_j;
+    }
+    if (n == 1)
+        return (int64_t)e * E.sa_i;
+    const uint32_t i = (uint32_t)e / (uint32_t)n, j = (uint32_t)e - i * (uint32_t)n;
+    return (int64_t)i * E.sa_i + (int64_t)j * E.sa_j;
+}
+
+constexpr int ROW_MIN = 128;   // windows at least this wide are cut into row-aligned units
+constexpr int STREAM_PER = 8;  // elements per lane and step
+constexpr int RING_STAGES = 4; // cp.async ring depth of the streaming kernel
+constexpr size_t RING_BYTES = (size_t)(BLK_THREADS / 32) * RING_STAGES * STREAM_PER * 32 * sizeof(double);
+constexpr int ACC_STAGES = 3;             // ring depth of the accumulating kernel (4 measured slower)
+constexpr int ACC_SLOT = STREAM_PER + 3;  // per lane and stage: 8 source values, b, alpha, beta
+constexpr size_t ACC_RING_BYTES = (size_t)(BLK_THREADS / 32) * ACC_STAGES * ACC_SLOT * 32 * sizeof(double);
+
+__device__ __forceinline__ void cp_async8(double *smem, const double *gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+
+// Accumulating kernel: windows with several contributions, narrow 2-D windows, transposed sources.
+// One warp per unit.  The unit is walked as a flat sequence of steps (sub-chunk of 256 elements x
+// contribution); the source values of step q + ACC_STAGES - 1 are copied into the warp's cp.async ring
+// while step q is folded into the running values (8 per lane, in registers from the first to the last
+// contribution of a sub-chunk), so the loads of different contributions overlap.  The descriptor of the
+// next contribution is fetched one step ahead.  dst_zero: outputs start from 0 (not read).
+__global__ void __launch_bounds__(BLK_THREADS, 2)
 b2g_blocking_kernel(const BlkUnit *__restrict__ units, int64_t nunits, const BlkEntry *__restrict__ entries,
                     int dst_zero) {
+    extern __shared__ double ring[];
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * BLK_THREADS + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * BLK_THREADS) >> 5;
+    double *my = ring + ((size_t)(threadIdx.x >> 5) * ACC_STAGES * ACC_SLOT) * 32 + lane;
     for (int64_t u = warp; u < nunits; u += nwarps) {
         const BlkUnit U = units[u];
-        double acc[PER_LANE];
-        int32_t ei[PER_LANE], ej[PER_LANE]; // m, n < 2^31
+        const bool rowu = U.n >= ROW_MIN; // unit lies inside one row of a wide window
+        const bool lin = rowu || U.n == 1; // destination (and untransposed sources) linear in the position
+        uint32_t i0 = 0, j0 = 0;
+        if (rowu)
+            i0 = (uint32_t)U.e0 / (uint32_t)U.n, j0 = (uint32_t)U.e0 - i0 * (uint32_t)U.n;
+        double *__restrict__ dptr = U.dst + (rowu ? (int64_t)i0 * U.ldc + j0 : (lin ? (int64_t)U.e0 * U.ldc : 0));
+        const int64_t dstep = rowu ? 1 : U.ldc;
+        auto dst_index = [&](int l) -> int64_t {
+            if (lin)
+                return l * dstep;
+            const uint32_t e = (uint32_t)(U.e0 + l), i = e / (uint32_t)U.n, j = e - i * (uint32_t)U.n;
+            return (int64_t)i * U.ldc + j;
+        };
+        const int nchunks = (U.len + 32 * STREAM_PER - 1) / (32 * STREAM_PER);
+        const int steps = nchunks * U.count;
+        BlkEntry Ep = entries[U.first]; // descriptor of the next step to issue
+        int qi = 0, ci = 0, ti = 0;     // issue cursor: step, sub-chunk, contribution
+        auto issue = [&]() {
+            if (qi < steps) {
+                const BlkEntry E = Ep;
+                const int tn = ti + 1 == U.count ? 0 : ti + 1;
+                if (qi + 1 < steps && U.count > 1)
+                    Ep = entries[U.first + tn]; // in flight until the next issue
+                double *slot = my + (size_t)(qi % ACC_STAGES) * ACC_SLOT * 32;
+                slot[STREAM_PER * 32 + 32] = E.alpha, slot[STREAM_PER * 32 + 64] = E.beta;
+                if (E.alpha != 0.0) {
+                    cp_async8(slot + STREAM_PER * 32, E.b);
+                    const bool slin = lin && E.nd == 0;
+                    const int64_t sbase = rowu ? (int64_t)i0 * E.sa_i + (int64_t)j0 * E.sa_j : (int64_t)U.e0 * E.sa_i;
+                    const int64_t sstep = rowu ? E.sa_j : E.sa_i;
 #pragma unroll
-        for (int r = 0; r < PER_LANE; r++) {
-            const int l = r * 32 + lane;
-            const int64_t e = U.e0 + l;
-            ei[r] = (int32_t)(U.n == 1 ? e : e / U.n);
-            ej[r] = (int32_t)(U.n == 1 ? 0 : e - (int64_t)ei[r] * U.n);
-            acc[r] = (l < U.len && !dst_zero) ? U.dst[(int64_t)ei[r] * U.ldc + ej[r]] : 0.0;
-        }
-        for (int t = 0; t < U.count; t++) {
-            const BlkEntry E = entries[U.first + t];
-            const double s = E.alpha == 0.0 ? 0.0 : __ldg(E.b);
-#pragma unroll
-            for (int r = 0; r < PER_LANE; r++)
-                if (r * 32 + lane < U.len) {
-                    const double base = E.beta == 1.0 ? acc[r] : (E.beta == 0.0 ? 0.0 : E.beta * acc[r]);
-                    int32_t i = ei[r], j = ej[r];
-                    if (E.nd)
-                        i = ei[r] / E.nd, j = ei[r] - i * E.nd;
-                    acc[r] = E.alpha == 0.0 ? base
-                                            : fma(E.alpha, __ldg(E.a + (int64_t)i * E.sa_i + (int64_t)j * E.sa_j) * s, base);
+                    for (int r = 0; r < STREAM_PER; r++) {
+                        const int l = ci * 32 * STREAM_PER + r * 32 + lane;
+                        if (l < U.len)
+                            cp_async8(slot + r * 32, E.a + (slin ? sbase + l * sstep : blk_src_index(E, U.e0 + l, U.n)));
+                    }
                 }
-        }
+                qi++, ti = tn, ci += tn == 0 ? 1 : 0;
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        };
 #pragma unroll
-        for (int r = 0; r < PER_LANE; r++)
-            if (r * 32 + lane < U.len)
-                U.dst[(int64_t)ei[r] * U.ldc + ej[r]] = acc[r];
+        for (int p = 0; p < ACC_STAGES - 1; p++)
+            issue();
+        double acc[STREAM_PER];
+        int tc = 0, cc = 0;
+        for (int q = 0; q < steps; q++) {
+            issue();
+            asm volatile("cp.async.wait_group %0;\n" ::"n"(ACC_STAGES - 1) : "memory");
+            const double *slot = my + (size_t)(q % ACC_STAGES) * ACC_SLOT * 32;
+            if (tc == 0) {
+#pragma unroll
+                for (int r = 0; r < STREAM_PER; r++) {
+                    const int l = cc * 32 * STREAM_PER + r * 32 + lane;
+                    acc[r] = (!dst_zero && l < U.len) ? dptr[dst_index(l)] : 0.0;
+                }
+            }
+            const double alpha = slot[STREAM_PER * 32 + 32], beta = slot[STREAM_PER * 32 + 64];
+            if (alpha != 0.0) {
+                const double f = alpha * slot[STREAM_PER * 32];
+#pragma unroll
+                for (int r = 0; r < STREAM_PER; r++) {
+                    const int l = cc * 32 * STREAM_PER + r * 32 + lane;
+                    if (l < U.len)
+                        acc[r] = fma(f, slot[r * 32], beta == 1.0 ? acc[r] : (beta == 0.0 ? 0.0 : beta * acc[r]));
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < STREAM_PER; r++)
+                    acc[r] = beta == 1.0 ? acc[r] : (beta == 0.0 ? 0.0 : beta * acc[r]);
+            }
+            if (++tc == U.count) {
+#pragma unroll
+                for (int r = 0; r < STREAM_PER; r++) {
+                    const int l = cc * 32 * STREAM_PER + r * 32 + lane;
+                    if (l < U.len)
+                        dptr[dst_index(l)] = acc[r];
+                }
+                tc = 0, cc++;
+            }
+        }
+    }
+}
+
+// Streaming units: windows (or window rows) with ONE contribution whose addresses are linear in the
+// position inside the unit - 80-90 % of the bytes of a blocking step.  The descriptor is self-contained
+// (pre-offset pointers), the next unit's descriptor and scalar are fetched while the current unit
+// streams, and the source goes through the per-thread cp.async ring.
+struct StreamUnit { // 64 bytes
+    double *dst;
+    const double *src;
+    const double *b;
+    double alpha;
+    int32_t len, dstep, sstep, pad;
+    int64_t pad2[2];
+};
+static_assert(sizeof(StreamUnit) == 64, "StreamUnit layout");
+
+__global__ void __launch_bounds__(BLK_THREADS, 3)
+b2g_blocking_stream_kernel(const StreamUnit *__restrict__ units, int64_t nunits) {
+    extern __shared__ double ring[];
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * BLK_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * BLK_THREADS) >> 5;
+    if (warp >= nunits)
+        return;
+    double *my = ring + ((size_t)(threadIdx.x >> 5) * RING_STAGES * STREAM_PER) * 32 + lane;
+    StreamUnit U = units[warp];
+    double bval = __ldg(U.b);
+    for (int64_t u = warp; u < nunits; u += nwarps) {
+        const bool more = u + nwarps < nunits;
+        StreamUnit N = U;
+        if (more)
+            N = units[u + nwarps]; // in flight while this unit streams
+        double bnext = 0.0;
+        const double f = U.alpha * bval;
+        const double *__restrict__ sptr = U.src;
+        double *__restrict__ dptr = U.dst;
+        const int64_t sstep = U.sstep, dstep = U.dstep;
+        const int len = U.len;
+        const int nchunks = (len + 32 * STREAM_PER - 1) / (32 * STREAM_PER);
+        auto issue = [&](int c) {
+            if (c < nchunks) {
+                double *slot = my + (size_t)(c % RING_STAGES) * STREAM_PER * 32;
+#pragma unroll
+                for (int r = 0; r < STREAM_PER; r++) {
+                    const int l = c * 32 * STREAM_PER + r * 32 + lane;
+                    if (l < len)
+                        cp_async8(slot + r * 32, sptr + l * sstep);
+                }
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        };
+#pragma unroll
+        for (int c = 0; c < RING_STAGES - 1; c++)
+            issue(c);
+        for (int c = 0; c < nchunks; c++) {
+            issue(c + RING_STAGES - 1);
+            asm volatile("cp.async.wait_group %0;\n" ::"n"(RING_STAGES - 1) : "memory");
+            const double *slot = my + (size_t)(c % RING_STAGES) * STREAM_PER * 32;
+#pragma unroll
+            for (int r = 0; r < STREAM_PER; r++) {
+                const int l = c * 32 * STREAM_PER + r * 32 + lane;
+                if (l < len)
+                    dptr[l * dstep] = f * slot[r * 32];
+            }
+            if (c == 0 && more)
+                bnext = __ldg(N.b); // N has arrived by now; its scalar is ready when this unit ends
+        }
+        U = N, bval = bnext;
     }
 }
 
@@ -232,6 +391,23 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
             const int64_t nb = (int64_t)(h.e.sb_i ? h.m : 1) * (h.e.sb_j ? h.n : 1) * h.e.k;
             st.bytes_in += 8 * (na + nb);
         }
+    // host operand space: the address ranges to mirror, from the entries' own (unflattened) shapes
+    std::vector<B2GRange> in_rg, out_rg;
+    if (operand_space == B2G_OPERANDS_HOST) {
+        auto add = [](std::vector<B2GRange> &v, const void *ptr, size_t ext) {
+            if (ext)
+                v.push_back(B2GRange{(uintptr_t)ptr, (uintptr_t)ptr + ext * sizeof(double), 0});
+        };
+        for (const HostEntry &h : he) {
+            add(out_rg, h.dst, window_extent(h.m, h.n, h.ldc));
+            if (h.e.alpha == 0.0 || h.e.k == 0)
+                continue;
+            add(in_rg, h.e.a,
+                (size_t)(h.m - 1) * h.e.sa_i + (size_t)(h.n - 1) * h.e.sa_j + (size_t)(h.e.k - 1) * h.e.sa_k + 1);
+            add(in_rg, h.e.b,
+                (size_t)(h.m - 1) * h.e.sb_i + (size_t)(h.n - 1) * h.e.sb_j + (size_t)(h.e.k - 1) * h.e.sb_k + 1);
+        }
+    }
     // dense windows (whole rows of their block, or a single row) are addressed as one contiguous vector
     // whatever logical shape the contributing entry has: a term and its transposed partner, or the
     // recorder's whole-block AXPY (a.n == c.n branch), then share one cluster
@@ -239,6 +415,11 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
         if (h.n > 1 && (h.ldc == h.n || h.m == 1) && (int64_t)h.m * h.n < INT32_MAX) {
             h.e.nd = h.n;
             h.m = h.m * h.n, h.n = 1, h.ldc = 1;
+            // sources that are themselves linear in the flat element index need no (i, j) split
+            if ((int64_t)h.e.sa_i == (int64_t)h.e.nd * h.e.sa_j && (int64_t)h.e.sb_i == (int64_t)h.e.nd * h.e.sb_j) {
+                h.e.sa_i = h.e.sa_j, h.e.sb_i = h.e.sb_j;
+                h.e.sa_j = h.e.sb_j = 0, h.e.nd = 0;
+            }
         }
 
     // ---- 2. clusters = identical output windows, members in list order
@@ -318,9 +499,23 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
         }
         const int64_t total = (int64_t)w.m * w.n;
         std::vector<BlkUnit> &dstu = axpy ? units : gunits;
-        for (int64_t e0 = 0; e0 < total; e0 += UNIT_ELEMS)
-            dstu.push_back(BlkUnit{w.dst, e0, (int32_t)std::min<int64_t>(UNIT_ELEMS, total - e0), w.n, w.ldc, first,
-                                    cl[ci].count, 0});
+        if (total >= INT32_MAX) {
+            b2g_set_error(std::string(who) + ": output window of 2^31 or more elements");
+            return 1;
+        }
+        // unit size by cost (elements x contributions) so that a window with many contributions is
+        // spread over many warps; wide 2-D windows are cut into row-aligned units (linear addressing)
+        const int64_t cap = std::max<int64_t>(128, std::min<int64_t>(UNIT_ELEMS, (4 * UNIT_ELEMS) / cl[ci].count) / 128 * 128);
+        if (!axpy || w.n < ROW_MIN) {
+            for (int64_t e0 = 0; e0 < total; e0 += cap)
+                dstu.push_back(BlkUnit{w.dst, (int32_t)e0, (int32_t)std::min<int64_t>(cap, total - e0), w.n, w.ldc, first,
+                                       cl[ci].count});
+        } else {
+            for (int64_t i = 0; i < w.m; i++)
+                for (int64_t j0 = 0; j0 < w.n; j0 += cap)
+                    dstu.push_back(BlkUnit{w.dst, (int32_t)(i * w.n + j0), (int32_t)std::min<int64_t>(cap, w.n - j0), w.n,
+                                           w.ldc, first, cl[ci].count});
+        }
         st.bytes_out += total * 8;
     }
     // serial entries: by component, then list order (order kept in a side array: pad is 31-bit only)
@@ -350,7 +545,7 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
         for (const BlkSerial &s : serial)
             st.bytes_out += (int64_t)s.m * s.n * 8;
     }
-    st.units = (int64_t)(units.size() + gunits.size());
+    st.units = (int64_t)(units.size() + gunits.size()); // before the streaming split
     st.serial_entries = (int64_t)serial.size();
     if (dst_zero && operand_space == B2G_OPERANDS_DEVICE && !serial.empty()) {
         b2g_set_error("" + std::string(who) + ": B2G_DST_ZERO with device operands needs regular (identical or disjoint) output windows");
@@ -362,11 +557,12 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
     double *d_in = nullptr, *d_out = nullptr;
     BlkEntry *d_entries = nullptr;
     BlkUnit *d_units = nullptr, *d_gunits = nullptr;
+    StreamUnit *d_sunits = nullptr;
     BlkSerial *d_serial = nullptr;
     int64_t *d_comp = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     auto cleanup = [&]() {
-        b2g_dfree(ctx, d_in), b2g_dfree(ctx, d_out), b2g_dfree(ctx, d_entries), b2g_dfree(ctx, d_units), b2g_dfree(ctx, d_gunits);
+        b2g_dfree(ctx, d_in), b2g_dfree(ctx, d_out), b2g_dfree(ctx, d_entries), b2g_dfree(ctx, d_units), b2g_dfree(ctx, d_gunits), b2g_dfree(ctx, d_sunits);
         b2g_dfree(ctx, d_serial), b2g_dfree(ctx, d_comp);
         if (ev0)
             cudaEventDestroy(ev0);
@@ -380,22 +576,8 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
         cleanup();
         return 1;
     };
-    std::vector<B2GRange> in_rg, out_rg;
     auto t_up = std::chrono::steady_clock::now();
     if (operand_space == B2G_OPERANDS_HOST) {
-        auto add = [](std::vector<B2GRange> &v, const void *ptr, size_t ext) {
-            if (ext)
-                v.push_back(B2GRange{(uintptr_t)ptr, (uintptr_t)ptr + ext * sizeof(double), 0});
-        };
-        for (const HostEntry &h : he) {
-            add(out_rg, h.dst, window_extent(h.m, h.n, h.ldc));
-            if (h.e.alpha == 0.0 || h.e.k == 0)
-                continue;
-            add(in_rg, h.e.a,
-                (size_t)(h.m - 1) * h.e.sa_i + (size_t)(h.n - 1) * h.e.sa_j + (size_t)(h.e.k - 1) * h.e.sa_k + 1);
-            add(in_rg, h.e.b,
-                (size_t)(h.m - 1) * h.e.sb_i + (size_t)(h.n - 1) * h.e.sb_j + (size_t)(h.e.k - 1) * h.e.sb_k + 1);
-        }
         size_t in_total = 0, out_total = 0;
         b2g_merge_ranges(in_rg, in_total), b2g_merge_ranges(out_rg, out_total);
         for (const B2GRange &o : out_rg) // an output block must not also be an input of the same list
@@ -428,6 +610,28 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
             s.dst = b2g_translate(out_rg, d_out, s.dst);
         }
     }
+    // single-contribution linear units become self-contained streaming units
+    std::vector<StreamUnit> sunits;
+    {
+        std::vector<BlkUnit> rest;
+        rest.reserve(units.size());
+        for (const BlkUnit &u : units) {
+            const BlkEntry &E = dev_entries[u.first];
+            const bool rowu = u.n >= ROW_MIN, flat = u.n == 1;
+            if (u.count == 1 && E.nd == 0 && (rowu || flat) && E.alpha != 0.0 && E.k == 1 && (dst_zero || E.beta == 0.0)) {
+                const int64_t i0 = rowu ? u.e0 / u.n : 0, j0 = rowu ? u.e0 - i0 * u.n : 0;
+                StreamUnit su;
+                su.dst = u.dst + (rowu ? i0 * u.ldc + j0 : (int64_t)u.e0 * u.ldc);
+                su.src = E.a + (rowu ? i0 * E.sa_i + j0 * E.sa_j : (int64_t)u.e0 * E.sa_i);
+                su.b = E.b, su.alpha = E.alpha;
+                su.len = u.len, su.dstep = rowu ? 1 : u.ldc, su.sstep = rowu ? E.sa_j : E.sa_i, su.pad = 0;
+                su.pad2[0] = su.pad2[1] = 0;
+                sunits.push_back(su);
+            } else
+                rest.push_back(u);
+        }
+        units.swap(rest);
+    }
     // descriptors (pageable -> device; synchronised below before the vectors die)
     if (!dev_entries.empty()) {
         if (b2g_dmalloc(ctx, (void **)&d_entries, dev_entries.size() * sizeof(BlkEntry)) ||
@@ -441,6 +645,13 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
             cudaMemcpyAsync(d_gunits, gunits.data(), gunits.size() * sizeof(BlkUnit), cudaMemcpyHostToDevice,
                             ctx->stream) != cudaSuccess)
             return fail("" + std::string(who) + ": descriptor upload failed");
+    }
+    if (!sunits.empty()) {
+        if (b2g_dmalloc(ctx, (void **)&d_sunits, sunits.size() * sizeof(StreamUnit)))
+            return fail("");
+        if (cudaMemcpyAsync(d_sunits, sunits.data(), sunits.size() * sizeof(StreamUnit), cudaMemcpyHostToDevice,
+                            ctx->stream) != cudaSuccess)
+            return fail(std::string(who) + ": descriptor upload failed");
     }
     if (!serial.empty()) {
         if (b2g_dmalloc(ctx, (void **)&d_serial, serial.size() * sizeof(BlkSerial)) ||
@@ -460,10 +671,31 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
     if (cudaEventCreate(&ev0) != cudaSuccess || cudaEventCreate(&ev1) != cudaSuccess)
         return fail("" + std::string(who) + ": event creation failed");
     cudaEventRecord(ev0, ctx->stream);
+    static bool ring_attr = false;
+    if (!ring_attr) {
+        if (cudaFuncSetAttribute(b2g_blocking_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACC_RING_BYTES) !=
+                cudaSuccess ||
+            cudaFuncSetAttribute(b2g_blocking_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)RING_BYTES) != cudaSuccess)
+            return fail(std::string(who) + ": cudaFuncSetAttribute failed");
+        ring_attr = true;
+    }
+    if (!sunits.empty()) {
+        const int64_t want = ((int64_t)sunits.size() * 32 + BLK_THREADS - 1) / BLK_THREADS;
+        const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 3); // 3 resident CTAs per SM
+        b2g_blocking_stream_kernel<<<grid, BLK_THREADS, RING_BYTES, ctx->stream>>>(d_sunits, (int64_t)sunits.size());
+        ctx->launches++, st.launches++;
+    }
+    cudaEvent_t evs = nullptr;
+    const bool verbose = getenv("B2G_VERBOSE") != nullptr;
+    if (verbose) {
+        cudaEventCreate(&evs);
+        cudaEventRecord(evs, ctx->stream);
+    }
     if (!units.empty()) {
         const int64_t want = ((int64_t)units.size() * 32 + BLK_THREADS - 1) / BLK_THREADS;
-        const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 8);
-        b2g_blocking_kernel<<<grid, BLK_THREADS, 0, ctx->stream>>>(d_units, (int64_t)units.size(), d_entries,
+        const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 2); // 2 resident CTAs per SM
+        b2g_blocking_kernel<<<grid, BLK_THREADS, ACC_RING_BYTES, ctx->stream>>>(d_units, (int64_t)units.size(), d_entries,
                                                                    dst_zero ? 1 : 0);
         ctx->launches++, st.launches++;
     }
@@ -486,6 +718,19 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
     float ms = 0;
     cudaEventElapsedTime(&ms, ev0, ev1);
     st.kernel_ms = ms;
+    if (verbose) {
+        float ms_s = 0;
+        cudaEventElapsedTime(&ms_s, ev0, evs);
+        size_t se = 0, re = 0;
+        for (const StreamUnit &u : sunits)
+            se += (size_t)u.len;
+        for (const BlkUnit &u : units)
+            re += (size_t)u.len;
+        fprintf(stderr, "[b2g] blocking: stream %zu units %zu elements %.3f ms | regular %zu units %zu elements, general %zu units, "
+                        "serial %zu entries %.3f ms\n",
+                sunits.size(), se, ms_s, units.size(), re, gunits.size(), serial.size(), ms - ms_s);
+        cudaEventDestroy(evs);
+    }
 
     // ---- 7. results
     if (operand_space == B2G_OPERANDS_HOST) {

@@ -1,0 +1,146 @@
+// b2g_blocking_record.hpp — reference-side recording of the blocking step (left_contract /
+// right_contract) in the compact term form of include/b2g.h (b2g_tp_term).  Compiled together with
+// block2's own headers; no CUDA, no library calls: it only produces descriptors.
+#pragma once
+#include "b2g.h"
+#include "block2_core.hpp"
+#include <functional>
+#include <stdexcept>
+
+namespace b2g_host {
+
+using namespace block2;
+
+// Term collector shared by an OperatorFunctions object and its per-thread copies.
+struct TermCollector {
+    bool active = false;
+    vector<vector<b2g_tp_term>> per_thread;
+    TermCollector() : per_thread(max(1, threading->n_threads_global)) {}
+    void clear() {
+        for (auto &v : per_thread)
+            v.clear();
+    }
+    size_t size() const {
+        size_t n = 0;
+        for (auto &v : per_thread)
+            n += v.size();
+        return n;
+    }
+};
+
+// OperatorFunctions whose tensor_product (core/operator_functions.hpp:672-711) can emit, instead of the
+// per-row GEMM groups of AdvancedGEMM::tensor_product, one b2g_tp_term per connection-info entry - the
+// arguments of the eager GMatrixFunctions::tensor_product call the stock method would make
+// (core/matrix_functions.hpp:1269).  OperatorFunctions subclasses dispatch on every thread of
+// TensorFunctions::parallel_for (the opf pointer survives the base-class slice), unlike
+// fine-grained TensorFunctions overrides.
+template <typename S> struct GPUOperatorFunctions : OperatorFunctions<S, double> {
+    typedef double FL;
+    typedef OperatorFunctions<S, double> Base;
+    using Base::cg;
+    using Base::seq;
+    shared_ptr<TermCollector> collector;
+    GPUOperatorFunctions(const shared_ptr<CG<S>> &cg, const shared_ptr<TermCollector> &collector)
+        : Base(cg), collector(collector) {}
+    shared_ptr<OperatorFunctions<S, FL>> copy() const override {
+        shared_ptr<GPUOperatorFunctions<S>> r = make_shared<GPUOperatorFunctions<S>>(cg, collector);
+        r->seq = seq->copy();
+        return r;
+    }
+    void tensor_product(uint8_t conj, const shared_ptr<SparseMatrix<S, FL>> &a, const shared_ptr<SparseMatrix<S, FL>> &b,
+                        const shared_ptr<SparseMatrix<S, FL>> &c, FL scale = 1.0) const override {
+        if (!collector->active)
+            return Base::tensor_product(conj, a, b, c, scale);
+        scale = scale * a->factor * b->factor;
+        if (abs(scale) < TINY)
+            return;
+        const S adq = a->info->delta_quantum, bdq = b->info->delta_quantum, cdq = c->info->delta_quantum;
+        const auto &ci = c->info->cinfo;
+        // the (conj, a (x) b quantum) range of the connection table, as the stock method finds it
+        const S abdq = cdq.combine((conj & 1) ? -adq : adq, (conj & 2) ? bdq : -bdq);
+        const int ik = (int)(lower_bound(ci->quanta + ci->n[conj], ci->quanta + ci->n[conj + 1], abdq) - ci->quanta);
+        assert(ik < ci->n[conj + 1]);
+        const int lo = ci->idx[ik], hi = ik == ci->n[4] - 1 ? ci->nc : ci->idx[ik + 1];
+        vector<b2g_tp_term> &out = collector->per_thread[threading->get_thread_id()];
+        for (int il = lo; il < hi; il++) {
+            const GMatrix<FL> ma = (*a)[ci->ia[il]], mb = (*b)[ci->ib[il]], mc = (*c)[ci->ic[il]];
+            b2g_tp_term t;
+            t.a = ma.data, t.b = mb.data, t.c = mc.data + ci->stride[il];
+            t.am = ma.m, t.an = ma.n, t.bm = mb.m, t.bn = mb.n, t.cn = mc.n;
+            t.conja = conj & 1, t.conjb = (conj & 2) >> 1, t.reserved = 0;
+            t.scale = scale * (FL)ci->factor[il];
+            out.push_back(t);
+        }
+    }
+};
+
+// Record-only walk of one blocking expression, the Auto-mode counterpart of
+// TensorFunctions::tensor_product (core/tensor_functions.hpp:2184-2288).  Products go to the
+// recorder of `opf` through the reference's own OperatorFunctions::tensor_product.  A SumProd
+// term whose pre-sum is not stored as an intermediate needs a temporary tmp = sum_i f_i op_i
+// BEFORE the product that reads it: the stock method frees tmp right after recording, which is
+// only valid when the list is executed at record time (Simple), so here the iadd entries go to
+// a second recorder (`pre`, executed first) and the temporaries stay alive in `temps` until
+// both lists have run.
+template <typename S>
+inline void record_blocking_expr(const shared_ptr<OperatorFunctions<S, double>> &opf, const shared_ptr<OpExpr<S>> &expr,
+                                 const unordered_map<shared_ptr<OpExpr<S>>, shared_ptr<SparseMatrix<S, double>>> &lop,
+                                 const unordered_map<shared_ptr<OpExpr<S>>, shared_ptr<SparseMatrix<S, double>>> &rop,
+                                 const shared_ptr<SparseMatrix<S, double>> &mat,
+                                 const shared_ptr<OperatorFunctions<S, double>> &pre,
+                                 vector<shared_ptr<SparseMatrix<S, double>>> &temps,
+                                 const std::function<void(const shared_ptr<SparseMatrix<S, double>> &,
+                                                          const shared_ptr<SparseMatrixInfo<S>> &)> *alloc_tmp = nullptr) {
+    typedef double FL;
+    typedef unordered_map<shared_ptr<OpExpr<S>>, shared_ptr<SparseMatrix<S, FL>>> OpMap;
+    const OpTypes ty = expr->get_type();
+    if (ty == OpTypes::Zero)
+        return;
+    if (ty == OpTypes::Sum) {
+        for (auto &x : dynamic_pointer_cast<OpSum<S, FL>>(expr)->strings)
+            record_blocking_expr<S>(opf, x->get_type() == OpTypes::Prod && x->b == nullptr
+                                     ? (shared_ptr<OpExpr<S>>)x->get_op()
+                                     : (shared_ptr<OpExpr<S>>)x,
+                                 lop, rop, mat, pre, temps, alloc_tmp);
+        return;
+    }
+    if (ty == OpTypes::Elem) { // singlet embedding: the partner is the identity of the other block
+        auto op = dynamic_pointer_cast<OpElement<S, FL>>(expr);
+        const shared_ptr<OpExpr<S>> ident = make_shared<OpExpr<S>>();
+        opf->tensor_product(0, lop.count(op) ? lop.at(op) : lop.at(ident), rop.count(op) ? rop.at(op) : rop.at(ident),
+                            mat, op->factor);
+        return;
+    }
+    if (ty == OpTypes::Prod) {
+        auto op = dynamic_pointer_cast<OpProduct<S, FL>>(expr);
+        opf->tensor_product(op->conj, lop.at(op->a), rop.at(op->b), mat, op->factor);
+        return;
+    }
+    if (ty != OpTypes::SumProd)
+        throw std::runtime_error("b2g: unexpected expression type in a blocking expression");
+    auto op = dynamic_pointer_cast<OpSumProd<S, FL>>(expr);
+    const bool sum_right = op->b == nullptr; // a (x) (sum of right operators), else (sum of left) (x) b
+    const OpMap &side = sum_right ? rop : lop;
+    shared_ptr<SparseMatrix<S, FL>> sum;
+    if (op->c != nullptr && side.count(op->c))
+        sum = side.at(op->c); // stored intermediate
+    else {
+        sum = make_shared<SparseMatrix<S, FL>>(make_shared<VectorAllocator<FL>>());
+        const shared_ptr<SparseMatrixInfo<S>> &sinfo = side.at(abs_value((shared_ptr<OpExpr<S>>)op->ops[0]))->info;
+        if (alloc_tmp != nullptr) // structure-only recording: storage from the caller, pre-sums not recorded
+            (*alloc_tmp)(sum, sinfo);
+        else {
+            sum->allocate(sinfo);
+            for (size_t i = 0; i < op->ops.size(); i++)
+                pre->iadd(sum, side.at(abs_value((shared_ptr<OpExpr<S>>)op->ops[i])), op->ops[i]->factor,
+                          op->conjs[i]);
+        }
+        temps.push_back(sum);
+    }
+    if (sum_right)
+        opf->tensor_product(op->conj, lop.at(op->a), sum, mat, op->factor);
+    else
+        opf->tensor_product(op->conj, sum, rop.at(op->b), mat, op->factor);
+}
+
+} // namespace b2g_host

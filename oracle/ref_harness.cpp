@@ -32,6 +32,8 @@
 #include "block2_dmrg.hpp"
 // MPI stand-in shared with the host driver (POSIX shared memory); infrastructure, not product logic
 #include "../block2-preview_b200/host/b2g_shm_comm.hpp"
+// tpdump only: the term recorder of the host binding (descriptors, no library calls)
+#include "../block2-preview_b200/host/b2g_blocking_record.hpp"
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -141,6 +143,14 @@ struct VirtualArena {
     }
 };
 static VirtualArena g_varena;
+static const Args *g_tp_args = nullptr; // tpdump mode
+static int g_tp_counter = 0;
+template <typename T> static void wr(FILE *f, const vector<T> &v);
+struct BlkInterval {
+    uintptr_t lo, hi;
+};
+static vector<BlkInterval> blk_merge(vector<BlkInterval> iv);
+static void blk_locate(const vector<BlkInterval> &ar, uintptr_t p, int64_t &ia, int64_t &off);
 
 /* Allocate-only TensorFunctions for --struct: same bookkeeping as the stock
  * methods (which operators get storage, tensor_functions.hpp:2842-2984,
@@ -184,6 +194,89 @@ struct StructTensorFunctions : Base {
                 valloc(c->ops.at(op));
         }
     }
+    // tpdump: the N-th blocking call is also walked with the term recorder of the host binding and
+    // written as a .b2tp workload: magic "B2TP\0\0\0\1"; u64[8] nterms n_in n_out is_right call nflop 0 0;
+    // i32[nterms] x 7 am an bm bn cn conja conjb; f64[nterms] scale; i64[nterms] x 6 a_arena a_off b_arena
+    // b_off c_arena c_off; u64[n_in], u64[n_out] arena sizes (doubles).  Shapes only, no operator values.
+    void dump_terms(const shared_ptr<OperatorTensor<S, FL>> &a, const shared_ptr<OperatorTensor<S, FL>> &b,
+                    shared_ptr<OperatorTensor<S, FL>> &c, const shared_ptr<Symbolic<S>> &exprs,
+                    const shared_ptr<Symbolic<S>> &names, OpNamesSet delayed, bool right) const {
+        auto coll = make_shared<b2g_host::TermCollector>();
+        shared_ptr<OperatorFunctions<S, FL>> gopf = make_shared<b2g_host::GPUOperatorFunctions<S>>(opf->cg, coll);
+        coll->active = true;
+        vector<shared_ptr<SparseMatrix<S, FL>>> temps;
+        std::function<void(const shared_ptr<SparseMatrix<S, FL>> &, const shared_ptr<SparseMatrixInfo<S>> &)> at =
+            [](const shared_ptr<SparseMatrix<S, FL>> &m, const shared_ptr<SparseMatrixInfo<S>> &info) {
+                m->info = info;
+                m->alloc = nullptr;
+                valloc(m);
+                m->factor = 1.0;
+            };
+        const auto &lop = right ? b->ops : a->ops, &rop = right ? a->ops : b->ops;
+        for (size_t i = 0; i < exprs->data.size(); i++) {
+            shared_ptr<OpElement<S, FL>> cop = dynamic_pointer_cast<OpElement<S, FL>>(names->data[i]);
+            if (cop == nullptr || delayed(cop->name))
+                continue;
+            shared_ptr<OpExpr<S>> op = abs_value(names->data[i]);
+            b2g_host::record_blocking_expr<S>(gopf, exprs->data[i] * ((FL)1.0 / cop->factor), lop, rop, c->ops.at(op),
+                                              nullptr, temps, &at);
+        }
+        vector<b2g_tp_term> &terms = coll->per_thread[0];
+        vector<BlkInterval> iin, iout;
+        size_t nflop = 0;
+        for (auto &t : terms) {
+            iin.push_back(BlkInterval{(uintptr_t)t.a, (uintptr_t)t.a + 8 * (size_t)t.am * t.an});
+            iin.push_back(BlkInterval{(uintptr_t)t.b, (uintptr_t)t.b + 8 * (size_t)t.bm * t.bn});
+            const size_t wr = (size_t)(t.conja ? t.an : t.am) * (t.conjb ? t.bn : t.bm),
+                         wc = (size_t)(t.conja ? t.am : t.an) * (t.conjb ? t.bm : t.bn);
+            iout.push_back(BlkInterval{(uintptr_t)t.c, (uintptr_t)t.c + 8 * ((wr - 1) * t.cn + wc)});
+            nflop += (size_t)t.am * t.an * t.bm * t.bn;
+        }
+        vector<BlkInterval> ain = blk_merge(iin), aout = blk_merge(iout);
+        const size_t nt = terms.size();
+        vector<int32_t> i32[7];
+        vector<double> sc(nt);
+        vector<int64_t> i64[6];
+        for (auto &v : i32) v.resize(nt);
+        for (auto &v : i64) v.resize(nt);
+        for (size_t z = 0; z < nt; z++) {
+            const b2g_tp_term &t = terms[z];
+            i32[0][z] = t.am, i32[1][z] = t.an, i32[2][z] = t.bm, i32[3][z] = t.bn, i32[4][z] = t.cn;
+            i32[5][z] = t.conja, i32[6][z] = t.conjb, sc[z] = t.scale;
+            blk_locate(ain, (uintptr_t)t.a, i64[0][z], i64[1][z]);
+            blk_locate(ain, (uintptr_t)t.b, i64[2][z], i64[3][z]);
+            blk_locate(aout, (uintptr_t)t.c, i64[4][z], i64[5][z]);
+        }
+        FILE *f = fopen(g_tp_args->out.c_str(), "wb");
+        if (!f) {
+            perror("fopen");
+            exit(1);
+        }
+        const char magic[8] = {'B', '2', 'T', 'P', 0, 0, 0, 1};
+        fwrite(magic, 1, 8, f);
+        vector<uint64_t> hdr(8, 0);
+        hdr[0] = nt, hdr[1] = ain.size(), hdr[2] = aout.size(), hdr[3] = right ? 1 : 0;
+        hdr[4] = (uint64_t)g_tp_args->blk_call, hdr[5] = nflop;
+        wr(f, hdr);
+        for (auto &v : i32) wr(f, v);
+        wr(f, sc);
+        for (auto &v : i64) wr(f, v);
+        vector<uint64_t> szin(ain.size()), szout(aout.size());
+        size_t tin = 0, tout = 0;
+        for (size_t i = 0; i < ain.size(); i++)
+            szin[i] = (ain[i].hi - ain[i].lo) / 8, tin += szin[i];
+        for (size_t i = 0; i < aout.size(); i++)
+            szout[i] = (aout[i].hi - aout[i].lo) / 8, tout += szout[i];
+        wr(f, szin);
+        wr(f, szout);
+        fclose(f);
+        printf("TPDUMP %s call=%d %s terms=%zu in_arenas=%zu (%zu doubles) out_arenas=%zu (%zu doubles) nflop=%zu "
+               "temps=%zu\n",
+               g_tp_args->out.c_str(), g_tp_args->blk_call, right ? "right_contract" : "left_contract", nt, ain.size(),
+               tin, aout.size(), tout, nflop, temps.size());
+        fflush(stdout);
+        _exit(0);
+    }
     void left_contract(const shared_ptr<OperatorTensor<S, FL>> &a,
                        const shared_ptr<OperatorTensor<S, FL>> &b,
                        shared_ptr<OperatorTensor<S, FL>> &c,
@@ -191,8 +284,14 @@ struct StructTensorFunctions : Base {
                        OpNamesSet delayed = OpNamesSet()) const override {
         if (a == nullptr) // first site: tiny site operators, stock code
             Base::left_assign(b, c);
-        else
+        else {
             alloc_named(c->lmat, c, delayed);
+            if (g_tp_args != nullptr && g_tp_args->blk_call < 0)
+                printf("TPCALL %d left_contract ops=%zu doubles=%zu\n", g_tp_counter, c->ops.size(),
+                       (size_t)c->get_total_memory());
+            if (g_tp_args != nullptr && g_tp_counter++ == g_tp_args->blk_call)
+                dump_terms(a, b, c, cexprs == nullptr ? a->lmat * b->lmat : cexprs, c->lmat, delayed, false);
+        }
     }
     void right_contract(const shared_ptr<OperatorTensor<S, FL>> &a,
                         const shared_ptr<OperatorTensor<S, FL>> &b,
@@ -201,8 +300,14 @@ struct StructTensorFunctions : Base {
                         OpNamesSet delayed = OpNamesSet()) const override {
         if (a == nullptr)
             Base::right_assign(b, c);
-        else
+        else {
             alloc_named(c->rmat, c, delayed);
+            if (g_tp_args != nullptr && g_tp_args->blk_call < 0)
+                printf("TPCALL %d right_contract ops=%zu doubles=%zu\n", g_tp_counter, c->ops.size(),
+                       (size_t)c->get_total_memory());
+            if (g_tp_args != nullptr && g_tp_counter++ == g_tp_args->blk_call)
+                dump_terms(a, b, c, cexprs == nullptr ? b->rmat * a->rmat : cexprs, c->rmat, delayed, true);
+        }
     }
     void left_rotate(const shared_ptr<OperatorTensor<S, FL>> &a,
                      const shared_ptr<SparseMatrix<S, FL>> &mpst_bra,
@@ -289,9 +394,6 @@ template <typename T> static void wr(FILE *f, const vector<T> &v);
  * i32[ngroups] x 9: ta tb m n k lda ldb ldc gp; f64[ngroups] x 2: alpha beta;
  * i64[nentries] x 6: a_arena a_off b_arena b_off c_arena c_off; u64[n_in] input arena sizes;
  * u64[n_out] output arena sizes; f64 input arenas; f64 output arenas before; f64 output arenas after. */
-struct BlkInterval {
-    uintptr_t lo, hi;
-};
 static vector<BlkInterval> blk_merge(vector<BlkInterval> iv) {
     sort(iv.begin(), iv.end(), [](const BlkInterval &x, const BlkInterval &y) { return x.lo < y.lo; });
     vector<BlkInterval> ar;
@@ -628,7 +730,7 @@ template <typename S> struct StopDMRG : DMRG<S, double, double> {
                              const double davidson_conv_thrd,
                              const double noise,
                              shared_ptr<SparseMatrixGroup<S, double>> &pket) override {
-        if (args.mode == "dmrg" || args.mode == "blkdump" || this->isweep != args.sweeps ||
+        if (args.mode == "dmrg" || args.mode == "blkdump" || args.mode == "tpdump" || this->isweep != args.sweeps ||
             i != target_site)
             return Base::two_dot_eigs_and_perturb(forward, i,
                                                   davidson_conv_thrd, noise, pket);
@@ -899,6 +1001,8 @@ template <typename S> static int run(const Args &args) {
         printf("MPO parallelised: rank %d of %d (ParallelRuleQC, NewScheme) T=%.3f\n", args.rank, args.ranks,
                t.get_time());
     }
+    if (args.mode == "tpdump")
+        g_tp_args = &args;
     if (args.structure_only) {
         g_varena.init((size_t)1 << 44);
         if (args.ranks > 1)

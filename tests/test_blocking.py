@@ -238,12 +238,15 @@ def synthetic_terms(rng, n_blocks=6, maxdim=30, kron=True):
         rgs = [int(x) for x in rng.integers(1, maxdim, int(rng.integers(1, 4)))]
         cgs = [int(x) for x in rng.integers(1, maxdim, int(rng.integers(1, 4)))]
         rows, cols = sum(rgs), sum(cgs)
+        # a window belongs to one (a sector, b sector) pair: every term that writes it has the same block
+        # shapes up to transposition
+        kinds = rng.integers(3 if kron else 2, size=(len(rgs), len(cgs)))
         for _ in range(int(rng.integers(2, 14))):
             ri, ci = int(rng.integers(len(rgs))), int(rng.integers(len(cgs)))
             wr, wc = rgs[ri], cgs[ci]
             c = ooff + sum(rgs[:ri]) * cols + sum(cgs[:ci])
             conja, conjb = int(rng.integers(2)), int(rng.integers(2))
-            kind = int(rng.integers(3 if kron else 2))
+            kind = int(kinds[ri, ci])
             if kind == 0:    # b is 1 x 1
                 am, an, bm, bn = (wc, wr, 1, 1) if conja else (wr, wc, 1, 1)
             elif kind == 1:  # a is 1 x 1
