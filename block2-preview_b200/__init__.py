@@ -38,7 +38,8 @@ EXPORTS = [
     "b2g_last_error", "b2g_device_count", "b2g_context_create", "b2g_context_destroy",
     "b2g_context_launches", "b2g_context_stream", "b2g_context_synchronize",
     "b2g_plan_create", "b2g_plan_destroy", "b2g_plan_get_stats", "b2g_seq_matvec",
-    "b2g_seq_matvec_dev", "b2g_plan_profile", "b2g_pairs_execute", "b2g_dgemm_batch", "b2g_batch_execute", "b2g_tensor_product_execute", "b2g_davidson", "b2g_comm_unique_id",
+    "b2g_seq_matvec_dev", "b2g_plan_profile", "b2g_pairs_execute", "b2g_dgemm_batch", "b2g_batch_execute", "b2g_tensor_product_execute", "b2g_resident_vouch", "b2g_resident_cover", "b2g_resident_drop",
+    "b2g_resident_stats", "b2g_davidson", "b2g_comm_unique_id",
     "b2g_comm_init", "b2g_comm_destroy", "b2g_allreduce_sum", "b2g_malloc", "b2g_free",
     "b2g_memcpy_h2d", "b2g_memcpy_d2h", "b2g_memset_zero",
 ]
@@ -71,6 +72,8 @@ class BlockingStats(ctypes.Structure):
 
 
 DST_ZERO = 1
+KEEP_RESIDENT = 2
+DST_COVERED = 4
 
 
 class TPTerm(ctypes.Structure):
@@ -120,6 +123,10 @@ def lib() -> ctypes.CDLL:
         L.b2g_dgemm_batch.argtypes = [c_void_p, c_int64] + [c_void_p] * 13
         L.b2g_batch_execute.argtypes = [c_void_p, c_int64] + [c_void_p] * 14 + [c_int, c_int, POINTER(BlockingStats)]
         L.b2g_tensor_product_execute.argtypes = [c_void_p, c_int64, c_void_p, c_int, c_int, POINTER(BlockingStats)]
+        L.b2g_resident_vouch.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
+        L.b2g_resident_cover.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
+        L.b2g_resident_drop.argtypes = [c_void_p]
+        L.b2g_resident_stats.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int64)]
         L.b2g_davidson.argtypes = [c_void_p, c_void_p, c_void_p, c_double, c_double, c_int, c_int, c_int, c_int,
                                    POINTER(c_double), POINTER(c_int)]
         L.b2g_comm_unique_id.argtypes = [c_void_p]
@@ -275,6 +282,35 @@ def _ctx_tensor_product_execute(self, terms: np.ndarray, operand_space: int = OP
 
 
 Context.tensor_product_execute = _ctx_tensor_product_execute
+
+
+def _ctx_resident_vouch(self, host_ptrs, doubles) -> None:
+    """State that these host blocks are unchanged since the KEEP_RESIDENT call that produced them:
+    the next call that mirrors operands takes them from HBM instead of the host (one shot)."""
+    hp, nd = _ptrs(host_ptrs), np.ascontiguousarray(doubles, dtype=np.int64)
+    _check(lib().b2g_resident_vouch(self._h, len(hp), hp.ctypes.data, nd.ctypes.data), "b2g_resident_vouch")
+
+
+def _ctx_resident_cover(self, host_ptrs, doubles) -> None:
+    """Full extents of the zero-initialised blocks the next KEEP_RESIDENT | DST_ZERO call writes (one shot)."""
+    hp, nd = _ptrs(host_ptrs), np.ascontiguousarray(doubles, dtype=np.int64)
+    _check(lib().b2g_resident_cover(self._h, len(hp), hp.ctypes.data, nd.ctypes.data), "b2g_resident_cover")
+
+
+def _ctx_resident_drop(self) -> None:
+    _check(lib().b2g_resident_drop(self._h), "b2g_resident_drop")
+
+
+def _ctx_resident_stats(self):
+    held, hit = c_int64(), c_int64()
+    _check(lib().b2g_resident_stats(self._h, byref(held), byref(hit)), "b2g_resident_stats")
+    return held.value, hit.value
+
+
+Context.resident_vouch = _ctx_resident_vouch
+Context.resident_cover = _ctx_resident_cover
+Context.resident_drop = _ctx_resident_drop
+Context.resident_stats = _ctx_resident_stats
 
 
 class SeqPlan:

@@ -376,9 +376,17 @@ struct UF {
 
 // Back end shared by the list and the term entry points: entries -> output-window clusters -> warp
 // units -> kernels, with the operand mirroring of the host operand space around it.
-static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int operand_space, bool dst_zero,
+static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int operand_space, int flags,
                            b2g_blocking_stats &st, b2g_blocking_stats *stats,
                            std::chrono::steady_clock::time_point t_begin, const char *who) {
+    const bool dst_zero = (flags & B2G_DST_ZERO) != 0;
+    const bool keep_resident = (flags & B2G_KEEP_RESIDENT) != 0 && operand_space == B2G_OPERANDS_HOST;
+    const bool covered = (flags & B2G_DST_COVERED) != 0 && dst_zero && operand_space == B2G_OPERANDS_HOST;
+    if ((flags & B2G_DST_COVERED) && (!covered || ctx->cover.empty())) {
+        b2g_set_error(std::string(who) + ": B2G_DST_COVERED needs B2G_DST_ZERO, host operands and b2g_resident_cover extents");
+        return 1;
+    }
+    size_t out_total_doubles = 0;
     st.merged = (int64_t)he.size();
     if (he.empty()) {
         if (stats)
@@ -579,7 +587,12 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
     auto t_up = std::chrono::steady_clock::now();
     if (operand_space == B2G_OPERANDS_HOST) {
         size_t in_total = 0, out_total = 0;
+        if ((keep_resident || covered) && dst_zero) // whole output blocks, as announced by b2g_resident_cover
+            for (const auto &c : ctx->cover)
+                out_rg.push_back(B2GRange{c.first, c.second, 0});
+        ctx->cover.clear();
         b2g_merge_ranges(in_rg, in_total), b2g_merge_ranges(out_rg, out_total);
+        out_total_doubles = out_total;
         for (const B2GRange &o : out_rg) // an output block must not also be an input of the same list
             if (!in_rg.empty()) {
                 const B2GRange &r = b2g_locate_range(in_rg, o.lo);
@@ -735,9 +748,13 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
     // ---- 7. results
     if (operand_space == B2G_OPERANDS_HOST) {
         auto t_dn = std::chrono::steady_clock::now();
-        if (b2g_download_ranges(ctx, out_rg, d_out, dst_zero))
+        if (b2g_download_ranges(ctx, out_rg, d_out, dst_zero && !covered))
             return fail("");
         st.download_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_dn).count();
+        if (keep_resident) { // the host copy now equals the device copy
+            b2g_resident_keep(ctx, d_out, out_rg, out_total_doubles);
+            d_out = nullptr;
+        }
     }
     cleanup();
     if (stats)
@@ -768,8 +785,6 @@ extern "C" int b2g_batch_execute(b2g_context *ctx, int64_t group_count, const in
     b2g_blocking_stats st;
     memset(&st, 0, sizeof(st));
     auto t_begin = std::chrono::steady_clock::now();
-    const bool dst_zero = (flags & B2G_DST_ZERO) != 0;
-
     // ---- 1. expand the groups, fold constant-stride AXPY rows of one group into 2-D windows
     std::vector<HostEntry> he;
     int64_t z = 0, order = 0;
@@ -824,7 +839,7 @@ extern "C" int b2g_batch_execute(b2g_context *ctx, int64_t group_count, const in
         }
         z += gs;
     }
-    return execute_entries(ctx, he, operand_space, dst_zero, st, stats, t_begin, "b2g_batch_execute");
+    return execute_entries(ctx, he, operand_space, flags, st, stats, t_begin, "b2g_batch_execute");
 }
 
 // One GMatrixFunctions::tensor_product call (block2 src/core/matrix_functions.hpp:1269-1397, recorded
@@ -886,6 +901,5 @@ extern "C" int b2g_tensor_product_execute(b2g_context *ctx, int64_t count, const
                 }
         }
     }
-    return execute_entries(ctx, he, operand_space, (flags & B2G_DST_ZERO) != 0, st, stats, t_begin,
-                           "b2g_tensor_product_execute");
+    return execute_entries(ctx, he, operand_space, flags, st, stats, t_begin, "b2g_tensor_product_execute");
 }

@@ -159,6 +159,7 @@ extern "C" int b2g_context_destroy(b2g_context *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->nccl_comm)
         b2g_comm_destroy(ctx);
+    b2g_resident_drop(ctx);
     if (ctx->h_stage)
         cudaFreeHost(ctx->h_stage);
     for (int i = 0; i < 2; i++) {
@@ -350,22 +351,15 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
             delete p;
             return 1;
         }
-        if (ensure_upload_buffers(ctx)) {
-            delete p;
-            return 1;
-        }
-        MirrorWriter mw{ctx, (char *)p->d_operands};
-        B2G_CUDA(cudaEventSynchronize(ctx->up_done[0]));
-        B2G_CUDA(cudaEventSynchronize(ctx->up_done[1]));
-        for (const Range &r : ar)
-            if (mw.add(r.dev_off * sizeof(double), (const void *)r.lo, r.hi - r.lo) != 0) {
+        {
+            std::vector<B2GRange> brg(ar.size());
+            for (size_t i = 0; i < ar.size(); i++)
+                brg[i] = B2GRange{ar[i].lo, ar[i].hi, ar[i].dev_off};
+            if (b2g_mirror_ranges(ctx, brg, p->d_operands)) {
                 b2g_dfree(ctx, p->d_operands);
                 delete p;
                 return 1;
             }
-        if (mw.flush()) {
-            delete p;
-            return 1;
         }
         auto locate = [&ar](uintptr_t ptr) -> const Range & {
             size_t lo = 0, hi = ar.size();
@@ -629,12 +623,10 @@ extern "C" int b2g_pairs_execute(b2g_context *ctx, const b2g_batch *b0, const b2
     if (cudaMemsetAsync(d_out, 0, out_total * sizeof(double), ctx->stream) != cudaSuccess)
         return fail("b2g_pairs_execute: memset failed");
     {
-        MirrorWriter mw{ctx, (char *)d_in};
-        cudaEventSynchronize(ctx->up_done[0]), cudaEventSynchronize(ctx->up_done[1]);
-        for (const Range &r : in_rg)
-            if (mw.add(r.dev_off * sizeof(double), (const void *)r.lo, r.hi - r.lo))
-                return fail("");
-        if (mw.flush())
+        std::vector<B2GRange> brg(in_rg.size());
+        for (size_t i = 0; i < in_rg.size(); i++)
+            brg[i] = B2GRange{in_rg[i].lo, in_rg[i].hi, in_rg[i].dev_off};
+        if (b2g_mirror_ranges(ctx, brg, d_in))
             return fail("");
     }
     for (B2GPair &q : hp) {
@@ -729,16 +721,154 @@ const B2GRange &b2g_locate_range(const std::vector<B2GRange> &ar, uintptr_t ptr)
     return ar[lo];
 }
 
+// resident copy of the host range [lo, hi), if the caller vouched for it
+static const double *resident_lookup(b2g_context *ctx, uintptr_t lo, uintptr_t hi) {
+    if (ctx->vouched.empty() || ctx->resident.empty())
+        return nullptr;
+    // vouched: sorted, disjoint
+    size_t a = 0, b = ctx->vouched.size();
+    while (b - a > 1) {
+        const size_t mid = (a + b) / 2;
+        if (ctx->vouched[mid].first <= lo)
+            a = mid;
+        else
+            b = mid;
+    }
+    if (!(ctx->vouched[a].first <= lo && hi <= ctx->vouched[a].second))
+        return nullptr;
+    for (const B2GResident &R : ctx->resident) {
+        if (R.ranges.empty() || lo < R.ranges.front().lo || hi > R.ranges.back().hi)
+            continue;
+        const B2GRange &r = b2g_locate_range(R.ranges, lo);
+        if (r.lo <= lo && hi <= r.hi)
+            return R.dev + r.dev_off + (lo - r.lo) / sizeof(double);
+    }
+    return nullptr;
+}
+
 int b2g_mirror_ranges(b2g_context *ctx, const std::vector<B2GRange> &rg, double *dev_base) {
     if (ensure_upload_buffers(ctx))
         return 1;
     MirrorWriter mw{ctx, (char *)dev_base};
     B2G_CUDA(cudaEventSynchronize(ctx->up_done[0]));
     B2G_CUDA(cudaEventSynchronize(ctx->up_done[1]));
-    for (const B2GRange &r : rg)
+    for (const B2GRange &r : rg) {
+        if (const double *res = resident_lookup(ctx, r.lo, r.hi)) {
+            // a staging slice is shipped as ONE contiguous device span: close it so that it cannot
+            // cover (and overwrite) the span this range is copied into device to device
+            if (mw.flush())
+                return 1;
+            static const bool check = getenv("B2G_RESIDENT_CHECK") != nullptr;
+            if (check) { // debugging aid: the vouched host block must equal its resident copy
+                std::vector<double> tmp((r.hi - r.lo) / sizeof(double));
+                B2G_CUDA(cudaMemcpyAsync(tmp.data(), res, r.hi - r.lo, cudaMemcpyDeviceToHost, ctx->stream));
+                B2G_CUDA(cudaStreamSynchronize(ctx->stream));
+                const double *h = (const double *)r.lo;
+                size_t bad = 0, first = 0;
+                for (size_t i = 0; i < tmp.size(); i++)
+                    if (tmp[i] != h[i] && !(tmp[i] != tmp[i] && h[i] != h[i])) {
+                        if (!bad)
+                            first = i;
+                        bad++;
+                    }
+                if (bad)
+                    fprintf(stderr, "[b2g] resident mismatch: host %p + %zu doubles, %zu differ, first at %zu (dev %.17g host %.17g)\n",
+                            (const void *)r.lo, tmp.size(), bad, first, tmp[first], h[first]);
+            }
+            B2G_CUDA(cudaMemcpyAsync(dev_base + r.dev_off, res, r.hi - r.lo, cudaMemcpyDeviceToDevice, ctx->stream));
+            ctx->resident_hits++, ctx->resident_hit_bytes += (int64_t)(r.hi - r.lo);
+            continue;
+        }
         if (mw.add(r.dev_off * sizeof(double), (const void *)r.lo, r.hi - r.lo))
             return 1;
-    return mw.flush();
+    }
+    const int rc = mw.flush();
+    ctx->vouched.clear(); // one shot
+    return rc;
+}
+
+void b2g_resident_keep(b2g_context *ctx, double *dev, const std::vector<B2GRange> &rg, size_t doubles) {
+    // a new mirror of a host range supersedes older ones that overlap it
+    for (size_t i = 0; i < ctx->resident.size();) {
+        B2GResident &R = ctx->resident[i];
+        bool overlap = false;
+        if (!R.ranges.empty() && !rg.empty() && R.ranges.front().lo < rg.back().hi && rg.front().lo < R.ranges.back().hi)
+            for (const B2GRange &r : rg) {
+                const B2GRange &q = b2g_locate_range(R.ranges, r.lo);
+                const B2GRange *nx = (&q + 1 < R.ranges.data() + R.ranges.size()) ? &q + 1 : nullptr;
+                if ((q.lo < r.hi && r.lo < q.hi) || (nx && nx->lo < r.hi && r.lo < nx->hi)) {
+                    overlap = true;
+                    break;
+                }
+            }
+        if (overlap) {
+            b2g_dfree(ctx, R.dev);
+            ctx->resident.erase(ctx->resident.begin() + (long)i);
+        } else
+            i++;
+    }
+    B2GResident R;
+    R.dev = dev, R.ranges = rg, R.doubles = doubles;
+    ctx->resident.push_back(std::move(R));
+}
+
+extern "C" int b2g_resident_vouch(b2g_context *ctx, int64_t count, const double *const *host, const int64_t *doubles) {
+    if (!ctx || (count > 0 && (!host || !doubles))) {
+        b2g_set_error("b2g_resident_vouch: null argument");
+        return 1;
+    }
+    for (int64_t i = 0; i < count; i++)
+        if (host[i] && doubles[i] > 0)
+            ctx->vouched.emplace_back((uintptr_t)host[i], (uintptr_t)host[i] + (uintptr_t)doubles[i] * sizeof(double));
+    std::sort(ctx->vouched.begin(), ctx->vouched.end());
+    std::vector<std::pair<uintptr_t, uintptr_t>> m;
+    for (auto &v : ctx->vouched) {
+        if (!m.empty() && v.first <= m.back().second)
+            m.back().second = std::max(m.back().second, v.second);
+        else
+            m.push_back(v);
+    }
+    ctx->vouched.swap(m);
+    return 0;
+}
+
+extern "C" int b2g_resident_cover(b2g_context *ctx, int64_t count, const double *const *host, const int64_t *doubles) {
+    if (!ctx || (count > 0 && (!host || !doubles))) {
+        b2g_set_error("b2g_resident_cover: null argument");
+        return 1;
+    }
+    ctx->cover.clear();
+    for (int64_t i = 0; i < count; i++)
+        if (host[i] && doubles[i] > 0)
+            ctx->cover.emplace_back((uintptr_t)host[i], (uintptr_t)host[i] + (uintptr_t)doubles[i] * sizeof(double));
+    return 0;
+}
+
+extern "C" int b2g_resident_drop(b2g_context *ctx) {
+    if (!ctx)
+        return 0;
+    B2G_CUDA(cudaSetDevice(ctx->device));
+    for (B2GResident &R : ctx->resident)
+        b2g_dfree(ctx, R.dev);
+    ctx->resident.clear();
+    ctx->vouched.clear();
+    ctx->cover.clear();
+    return 0;
+}
+
+extern "C" int b2g_resident_stats(const b2g_context *ctx, int64_t *bytes_held, int64_t *bytes_hit) {
+    if (!ctx) {
+        b2g_set_error("b2g_resident_stats: null context");
+        return 1;
+    }
+    int64_t held = 0;
+    for (const B2GResident &R : ctx->resident)
+        held += (int64_t)(R.doubles * sizeof(double));
+    if (bytes_held)
+        *bytes_held = held;
+    if (bytes_hit)
+        *bytes_hit = ctx->resident_hit_bytes;
+    return 0;
 }
 
 int b2g_download_ranges(b2g_context *ctx, const std::vector<B2GRange> &rg, const double *dev_base, bool add) {

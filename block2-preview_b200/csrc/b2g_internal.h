@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <string>
+#include <utility>
 #include <vector>
 
 // One GEMM pair of the H.C replay list, device layout (88 bytes).
@@ -26,6 +27,19 @@ static_assert(sizeof(B2GPair) == 88, "B2GPair layout");
 #define B2G_F_TB0 2u
 #define B2G_F_TA1 4u
 
+// host address ranges mirrored into one device allocation (b2g_core.cu)
+struct B2GRange {
+    uintptr_t lo, hi; // host bytes [lo, hi)
+    size_t dev_off;   // doubles from the device base
+};
+// Output blocks of a blocking call kept in HBM after their download (B2G_KEEP_RESIDENT): the next
+// calls that mirror host ranges the caller vouches for (b2g_resident_vouch) copy them device to device.
+struct B2GResident {
+    double *dev = nullptr;                // one allocation (cudaMalloc'ed through the stream pool)
+    std::vector<B2GRange> ranges;       // host ranges it mirrors, with their offsets
+    size_t doubles = 0;
+};
+
 struct b2g_context {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -45,6 +59,10 @@ struct b2g_context {
     cudaStream_t side[N_SIDE] = {};
     cudaEvent_t side_done[N_SIDE] = {};
     cudaEvent_t fork_ev = nullptr;
+    std::vector<B2GResident> resident;
+    std::vector<std::pair<uintptr_t, uintptr_t>> vouched; // host byte ranges valid for the NEXT mirror (one shot)
+    int64_t resident_hits = 0, resident_hit_bytes = 0;
+    std::vector<std::pair<uintptr_t, uintptr_t>> cover; // full extents of the blocks the next KEEP_RESIDENT call writes
     void *h_up[2] = {nullptr, nullptr};
     cudaEvent_t up_done[2] = {nullptr, nullptr};
     size_t up_bytes = 0;
@@ -79,11 +97,6 @@ int b2g_upload(b2g_context *ctx, void *dst, const void *src, size_t bytes);
         }                                                                                \
     } while (0)
 
-// host address ranges mirrored into one device allocation (b2g_core.cu)
-struct B2GRange {
-    uintptr_t lo, hi; // host bytes [lo, hi)
-    size_t dev_off;   // doubles from the device base
-};
 // sort + merge touching ranges, assign 16-byte aligned device offsets; total = doubles needed
 void b2g_merge_ranges(std::vector<B2GRange> &rg, size_t &total);
 // range that holds ptr (rg merged and sorted)
@@ -94,6 +107,8 @@ inline double *b2g_translate(const std::vector<B2GRange> &rg, double *dev_base, 
 }
 // host ranges -> device (pinned staging, small neighbours packed into one DMA); asynchronous
 int b2g_mirror_ranges(b2g_context *ctx, const std::vector<B2GRange> &rg, double *dev_base);
+// keep `dev` (ownership passes to the context) as the resident mirror of the host ranges rg
+void b2g_resident_keep(b2g_context *ctx, double *dev, const std::vector<B2GRange> &rg, size_t doubles);
 // device -> host ranges through pinned staging; add = true: host += device, else host = device. Synchronous.
 int b2g_download_ranges(b2g_context *ctx, const std::vector<B2GRange> &rg, const double *dev_base, bool add);
 

@@ -56,6 +56,37 @@ struct Session {
     bool gpu_contract = false;
     double t_contract = 0, max_contract_err = 0, contract_kernel_ms = 0, contract_bytes = 0;
     double t_contract_record = 0, t_contract_plan = 0, t_contract_upload = 0, t_contract_download = 0;
+    // blocks the latest blocking calls left resident in HBM (b2g KEEP_RESIDENT): the operator, the host
+    // address and size it had when it was produced.  An entry is vouched for (b2g_resident_vouch) only
+    // while the operator object is alive and still owns exactly that storage.
+    bool keep_resident = true;
+    struct ResidentOp {
+        std::weak_ptr<void> owner;
+        const double *data;
+        size_t doubles;
+        const double *const *slot; // &SparseMatrix::data of the owner
+        const size_t *size_slot;   // &SparseMatrix::total_memory
+    };
+    std::vector<ResidentOp> resident_ops;
+    void vouch_residents() {
+        std::vector<const double *> ptrs;
+        std::vector<int64_t> sizes;
+        for (auto &r : resident_ops) {
+            std::shared_ptr<void> alive = r.owner.lock();
+            if (alive != nullptr && *r.slot == r.data && *r.size_slot == r.doubles)
+                ptrs.push_back(r.data), sizes.push_back((int64_t)r.doubles);
+        }
+        if (!ptrs.empty() && b2g_resident_vouch(ctx, (int64_t)ptrs.size(), ptrs.data(), sizes.data()) != 0)
+            throw std::runtime_error(std::string("b2g_resident_vouch: ") + b2g_last_error());
+    }
+    void drop_residents() {
+        resident_ops.clear();
+        int64_t held = 0, hit = 0;
+        b2g_resident_stats(ctx, &held, &hit);
+        resident_hit_bytes = (double)hit, resident_peak_bytes = std::max(resident_peak_bytes, (double)held);
+        b2g_resident_drop(ctx);
+    }
+    double resident_hit_bytes = 0, resident_peak_bytes = 0;
     size_t n_contract = 0, contract_entries = 0;
     explicit Session(int device = 0) {
         if (b2g_context_create(device, &ctx) != 0)
@@ -83,6 +114,21 @@ inline b2g_batch as_b2g_batch(const BatchGEMM<double> &b) {
     r.a = b.a.data(), r.b = b.b.data(), r.c = b.c.data();
     return r;
 }
+
+// Uninitialised storage for blocked operators whose every element the device result overwrites
+// (B2G_DST_COVERED): VectorAllocator + SparseMatrix::allocate would zero the block twice first.
+struct UninitAllocator : Allocator<double> {
+    double *allocate(size_t n) override {
+        double *p = (double *)malloc(std::max<size_t>(n, 1) * sizeof(double));
+        if (p == nullptr)
+            throw std::bad_alloc();
+        return p;
+    }
+    void deallocate(void *ptr, size_t) override { free(ptr); }
+    double *reallocate(double *ptr, size_t, size_t new_n) override {
+        return (double *)realloc(ptr, std::max<size_t>(new_n, 1) * sizeof(double));
+    }
+};
 
 // Base = TensorFunctions<S,double> (serial) or ParallelTensorFunctions<S,double> (one process per
 // GPU under ParallelRuleQC: the base keeps the reference's distributed blocking logic, the matvec
@@ -158,6 +204,7 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
         seq->mode = saved;
         if (seq->batch[1]->gp.size() != 0) {
             b2g_batch b0 = as_b2g_batch(*seq->batch[0]), b1 = as_b2g_batch(*seq->batch[1]);
+            session->vouch_residents(); // blocks the blocking step just produced are read from HBM
             if (session->verify) { // keep a CPU copy of the result to compare with
                 vector<vector<double>> ref;
                 for (auto &p : c->ops)
@@ -191,6 +238,7 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
             }
         }
         seq->clear();
+        session->drop_residents(); // the blocked operators are dead after their renormalisation
         session->t_rotate += t.get_time(), session->n_rotate++;
     }
     typedef unordered_map<shared_ptr<OpExpr<S>>, shared_ptr<SparseMatrix<S, FL>>> OpMap;
@@ -218,14 +266,21 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
         const SeqTypes saved = seq->mode;
         shared_ptr<GPUOperatorFunctions<S>> gopf = dynamic_pointer_cast<GPUOperatorFunctions<S>>(opf);
         const OpMap &lop = right ? b->ops : a->ops, &rop = right ? a->ops : b->ops;
+        const bool covered = gopf != nullptr && session->keep_resident;
         vector<size_t> todo;
         for (size_t i = 0; i < exprs->data.size(); i++) {
             shared_ptr<OpElement<S, FL>> cop = dynamic_pointer_cast<OpElement<S, FL>>(names->data[i]);
             shared_ptr<SparseMatrix<S, FL>> &m = c->ops.at(abs_value(names->data[i]));
             if (delayed(cop->name) || m->alloc != nullptr) // delayed, or the cached part
                 continue;
-            m->alloc = make_shared<VectorAllocator<FL>>();
-            m->allocate(m->info);
+            if (covered) { // every element is overwritten by the device result: no zero fill
+                m->alloc = make_shared<UninitAllocator>();
+                const size_t n = m->info->template get_total_memory<FL>();
+                m->allocate(m->info, n == 0 ? nullptr : m->alloc->allocate(n));
+            } else {
+                m->alloc = make_shared<VectorAllocator<FL>>();
+                m->allocate(m->info);
+            }
             todo.push_back(i);
         }
         // record-only walk; the SumProd pre-sums go to `pre`, their temporaries to `temps`
@@ -268,12 +323,33 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
             for (size_t k = 1; k < gopf->collector->per_thread.size(); k++)
                 terms.insert(terms.end(), gopf->collector->per_thread[k].begin(), gopf->collector->per_thread[k].end());
             if (terms.size() != 0) {
+                if (session->keep_resident) { // the resident mirror covers the whole fresh operators
+                    vector<const double *> cp;
+                    vector<int64_t> cn;
+                    for (size_t i : todo) {
+                        auto &m = c->ops.at(abs_value(names->data[i]));
+                        cp.push_back(m->data), cn.push_back((int64_t)m->total_memory);
+                    }
+                    b2g_resident_cover(session->ctx, (int64_t)cp.size(), cp.data(), cn.data());
+                }
                 if (b2g_tensor_product_execute(session->ctx, (int64_t)terms.size(), terms.data(), B2G_OPERANDS_HOST,
-                                               B2G_DST_ZERO, &st) != 0)
+                                               B2G_DST_ZERO | (covered ? B2G_KEEP_RESIDENT | B2G_DST_COVERED : 0), &st) != 0)
                     throw std::runtime_error(std::string("b2g_tensor_product_execute: ") + b2g_last_error());
                 account(st);
-            }
+            } else if (covered) // nothing writes the fresh operators: they are zero
+                for (size_t i : todo) {
+                    auto &m = c->ops.at(abs_value(names->data[i]));
+                    if (m->total_memory != 0)
+                        memset(m->data, 0, sizeof(double) * m->total_memory);
+                }
             gopf->collector->clear();
+            if (session->keep_resident)
+                for (size_t i : todo) {
+                    shared_ptr<SparseMatrix<S, FL>> m = c->ops.at(abs_value(names->data[i]));
+                    session->resident_ops.push_back(typename Session::ResidentOp{
+                        std::weak_ptr<void>(std::shared_ptr<void>(m)), m->data, (size_t)m->total_memory,
+                        (const double *const *)&m->data, (const size_t *)&m->total_memory});
+                }
         } else if (seq->batch[1]->gp.size() != 0) {
             if (run_blocking_list(*seq->batch[1], st) != 0)
                 throw std::runtime_error(std::string("b2g_batch_execute: ") + b2g_last_error());
@@ -348,6 +424,7 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
         drop();
         auto &seq = opf->seq;
         b2g_batch b0 = as_b2g_batch(*seq->batch[0]), b1 = as_b2g_batch(*seq->batch[1]);
+        session->vouch_residents(); // complementary operators blocked for this H_eff are still in HBM
         if (b2g_plan_create(session->ctx, &b0, &b1, (int64_t)seq->max_work, (int64_t)csize, (int64_t)vsize,
                             B2G_OPERANDS_HOST, &plan) != 0)
             throw std::runtime_error(std::string("b2g_plan_create: ") + b2g_last_error());

@@ -195,7 +195,7 @@ int main(int argc, char **argv) {
            "\"contractions\": %zu, \"t_contract\": %.3f, \"contract_entries\": %zu, \"contract_kernel_ms\": %.3f, "
            "\"contract_gbytes\": %.4f, \"max_contract_rel_err\": %.3e, "
            "\"t_contract_record\": %.3f, \"t_contract_plan\": %.3f, \"t_contract_upload\": %.3f, "
-           "\"t_contract_download\": %.3f}\n",
+           "\"t_contract_download\": %.3f, \"resident_hit_gbytes\": %.3f, \"resident_peak_gbytes\": %.3f}\n",
            a.ranks, a.davidson.c_str(), a.bond, gpu.energies.size(), gpu.total, ref.total, a.threads,
            gpu.energies.empty() ? 0.0 : gpu.energies.back(), ref.energies.empty() ? 0.0 : ref.energies.back(),
            maxdiff, session->n_plan, session->n_matvec, session->t_plan, session->t_matvec,
@@ -204,7 +204,8 @@ int main(int argc, char **argv) {
            session->max_rotate_err, (int)a.gpu_contract, session->n_contract, session->t_contract,
            session->contract_entries, session->contract_kernel_ms, session->contract_bytes * 1e-9,
            session->max_contract_err, session->t_contract_record, session->t_contract_plan,
-           session->t_contract_upload, session->t_contract_download);
+           session->t_contract_upload, session->t_contract_download, session->resident_hit_bytes * 1e-9,
+           session->resident_peak_bytes * 1e-9);
     fflush(stdout);
     _exit(0);
 }

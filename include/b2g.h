@@ -144,6 +144,11 @@ typedef struct b2g_blocking_stats {
     double upload_seconds, download_seconds, plan_seconds;
 } b2g_blocking_stats;
 
+#define B2G_KEEP_RESIDENT 2 /* host operand space: after the download the output blocks also stay in HBM (owned by
+                               the context) until b2g_resident_drop; see b2g_resident_vouch */
+#define B2G_DST_COVERED 4 /* with B2G_DST_ZERO, host operand space: the output blocks are exactly the extents
+                              announced by b2g_resident_cover and need NOT be initialised on the host - the
+                              device result (zero where no entry writes) overwrites them */
 #define B2G_DST_ZERO 1 /* caller guarantees every output block is zero on entry (freshly allocate()d operators):
                           outputs are not uploaded, the device result is added into the host blocks */
 
@@ -181,6 +186,21 @@ typedef struct b2g_tp_term {
  * compact form of the blocking list: one descriptor per (a-block, b-block) pair instead of one GEMM per row. */
 int b2g_tensor_product_execute(b2g_context *ctx, int64_t count, const b2g_tp_term *terms, int operand_space,
                                int flags, b2g_blocking_stats *stats);
+
+/* Resident blocks.  A blocking call with B2G_KEEP_RESIDENT leaves its output blocks in HBM.  The host copy
+ * stays authoritative: a later call (b2g_pairs_execute, b2g_plan_create, b2g_batch_execute,
+ * b2g_tensor_product_execute) takes an input from the resident copy instead of the host ONLY if the caller
+ * vouched for that host range since the previous mirroring call - i.e. states that the host block has not
+ * been written since the blocking call produced it.  Vouching is one-shot (cleared by the next call that
+ * mirrors operands).  b2g_resident_drop frees all resident blocks. */
+int b2g_resident_vouch(b2g_context *ctx, int64_t count, const double *const *host, const int64_t *doubles);
+/* Full extents of the (zero-initialised) output blocks of the NEXT B2G_KEEP_RESIDENT | B2G_DST_ZERO call: the
+ * resident mirror then covers whole blocks, including sectors no term writes, so that a later reader of a
+ * whole block finds it in one piece.  One shot. */
+int b2g_resident_cover(b2g_context *ctx, int64_t count, const double *const *host, const int64_t *doubles);
+int b2g_resident_drop(b2g_context *ctx);
+/* resident bytes currently held / host->device bytes avoided so far */
+int b2g_resident_stats(const b2g_context *ctx, int64_t *bytes_held, int64_t *bytes_hit);
 
 /* Davidson ground state with device-resident vectors; H applied through the plan.
  * ket_host: in = initial guess, out = eigenvector.  diag_host: H_eff diagonal.

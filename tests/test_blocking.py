@@ -289,3 +289,36 @@ def test_gpu_tensor_product_terms_match_oracle(b2g, ctx, seed, kron, zero):
     out2 = out0.copy()
     ctx.tensor_product_execute(pack_terms(b2g, terms, src, out2), b2g.OPERANDS_HOST, b2g.DST_ZERO if zero else 0)
     assert np.array_equal(out, out2)  # bit-reproducible
+
+
+@pytest.mark.gpu
+def test_gpu_resident_blocks_are_used_only_when_vouched(b2g, ctx):
+    """KEEP_RESIDENT leaves the blocked operators in HBM; a later call reads them from there only for host
+    ranges the caller vouched for since the previous mirroring call (one shot).  The host copy is made to
+    differ on purpose to see which copy was read."""
+    rng = np.random.default_rng(11)
+    n = 5000
+    src, one = rng.standard_normal(n), np.ones(1)
+    mid, out = np.zeros(n), np.zeros(n)
+    p = lambda arr: np.array([arr.ctypes.data], dtype=np.uint64)
+    axpy = lambda a, c, flags: ctx.batch_execute([111], [111], [n], [1], [1], [2.0], p(a), [1], p(one), [1], [1.0],
+                                                 p(c), [1], [1], b2g.OPERANDS_HOST, flags)
+    ctx.resident_drop()
+    axpy(src, mid, b2g.DST_ZERO | b2g.KEEP_RESIDENT)
+    assert np.array_equal(mid, 2.0 * src)
+    held, hit0 = ctx.resident_stats()
+    assert held >= 8 * n
+    mid[:] = -1.0  # host copy now differs from the resident copy
+    ctx.resident_vouch(p(mid), [n])
+    axpy(mid, out, b2g.DST_ZERO)
+    assert np.array_equal(out, 4.0 * src)  # read from HBM
+    assert ctx.resident_stats()[1] - hit0 == 8 * n
+    out[:] = 0.0
+    axpy(mid, out, b2g.DST_ZERO)  # not vouched again: the host copy is read
+    assert np.array_equal(out, np.full(n, -2.0))
+    ctx.resident_vouch(p(mid), [n])
+    ctx.resident_drop()  # dropping also forgets the vouching
+    out[:] = 0.0
+    axpy(mid, out, b2g.DST_ZERO)
+    assert np.array_equal(out, np.full(n, -2.0))
+    assert ctx.resident_stats()[0] == 0
