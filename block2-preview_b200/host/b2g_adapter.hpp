@@ -59,7 +59,7 @@ struct Session {
     // blocks the latest blocking calls left resident in HBM (b2g KEEP_RESIDENT): the operator, the host
     // address and size it had when it was produced.  An entry is vouched for (b2g_resident_vouch) only
     // while the operator object is alive and still owns exactly that storage.
-    bool keep_resident = true;
+    bool keep_resident = true, uninit_outputs = false;
     struct ResidentOp {
         std::weak_ptr<void> owner;
         const double *data;
@@ -266,7 +266,9 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
         const SeqTypes saved = seq->mode;
         shared_ptr<GPUOperatorFunctions<S>> gopf = dynamic_pointer_cast<GPUOperatorFunctions<S>>(opf);
         const OpMap &lop = right ? b->ops : a->ops, &rop = right ? a->ops : b->ops;
-        const bool covered = gopf != nullptr && session->keep_resident;
+        // uninitialised outputs + overwrite (B2G_DST_COVERED) measured slower than zero fill + add at C2 M=1000
+        // (first-touch page faults land in the download: 9.1 s against 4.0 s), so it stays off
+        const bool covered = gopf != nullptr && session->keep_resident && session->uninit_outputs;
         vector<size_t> todo;
         for (size_t i = 0; i < exprs->data.size(); i++) {
             shared_ptr<OpElement<S, FL>> cop = dynamic_pointer_cast<OpElement<S, FL>>(names->data[i]);
@@ -333,7 +335,9 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
                     b2g_resident_cover(session->ctx, (int64_t)cp.size(), cp.data(), cn.data());
                 }
                 if (b2g_tensor_product_execute(session->ctx, (int64_t)terms.size(), terms.data(), B2G_OPERANDS_HOST,
-                                               B2G_DST_ZERO | (covered ? B2G_KEEP_RESIDENT | B2G_DST_COVERED : 0), &st) != 0)
+                                               B2G_DST_ZERO | (session->keep_resident ? B2G_KEEP_RESIDENT : 0) |
+                                                   (covered ? B2G_DST_COVERED : 0),
+                                               &st) != 0)
                     throw std::runtime_error(std::string("b2g_tensor_product_execute: ") + b2g_last_error());
                 account(st);
             } else if (covered) // nothing writes the fresh operators: they are zero

@@ -322,3 +322,27 @@ def test_gpu_resident_blocks_are_used_only_when_vouched(b2g, ctx):
     axpy(mid, out, b2g.DST_ZERO)
     assert np.array_equal(out, np.full(n, -2.0))
     assert ctx.resident_stats()[0] == 0
+
+
+@pytest.mark.gpu
+def test_gpu_covered_outputs_need_no_initialisation(b2g, ctx):
+    """DST_COVERED: the announced output blocks are overwritten by the device result, zero where no entry
+    writes, so the host block may hold garbage on entry."""
+    rng = np.random.default_rng(12)
+    rows, cols = 40, 30
+    src, one = rng.standard_normal(rows * 10), np.ones(1)
+    out = np.full(rows * cols, 7.0)  # garbage
+    p = lambda arr, off=0: arr.ctypes.data + 8 * off
+    # rows-as-AXPY into the column window [5, 15) of every row
+    a = np.array([p(src, r * 10) for r in range(rows)], dtype=np.uint64)
+    c = np.array([p(out, r * cols + 5) for r in range(rows)], dtype=np.uint64)
+    b = np.full(rows, p(one), dtype=np.uint64)
+    with pytest.raises(b2g.B2GError, match="B2G_DST_COVERED"):
+        ctx.batch_execute([111], [111], [10], [1], [1], [3.0], a, [1], b, [1], [1.0], c, [1], [rows],
+                          b2g.OPERANDS_HOST, b2g.DST_ZERO | b2g.DST_COVERED)
+    ctx.resident_cover([p(out)], [rows * cols])
+    ctx.batch_execute([111], [111], [10], [1], [1], [3.0], a, [1], b, [1], [1.0], c, [1], [rows], b2g.OPERANDS_HOST,
+                      b2g.DST_ZERO | b2g.DST_COVERED)
+    ref = np.zeros((rows, cols))
+    ref[:, 5:15] = 3.0 * src.reshape(rows, 10)
+    assert np.array_equal(out.reshape(rows, cols), ref)
