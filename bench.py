@@ -335,6 +335,19 @@ def run_b200(args) -> None:
             except Exception as exc:  # the baseline is reported, never needed by the GPU path
                 line["cpu_baseline"] = {"value": None, "unit": "TFLOP/s", "cores": host_threads(), "kind": "reference",
                                         "sample": f"unavailable: {exc}"}
+        if world == 1:
+            # the blocking step that feeds this H_eff (left_contract at the same site, same recording run):
+            # HBM-bound kernels, reported beside the matvec with their own roofline
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import blocking_bench
+                from types import SimpleNamespace
+                bl = blocking_bench.run(SimpleNamespace(workload=blocking_bench.DEFAULT_WORKLOAD, steps=args.steps,
+                                                        warmup=args.warmup, check_windows=8), ctx=ctx)
+                line["blocking"] = {"workload": bl["config"]["workload"], "terms": bl["config"]["terms"],
+                                    "ms": bl["ms_per_step"], "roofline": bl["roofline"], "parity": bl["parity"]}
+            except Exception as exc:
+                line["blocking"] = {"unavailable": str(exc)}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)

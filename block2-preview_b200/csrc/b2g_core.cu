@@ -876,61 +876,87 @@ int b2g_download_ranges(b2g_context *ctx, const std::vector<B2GRange> &rg, const
         return 1;
     B2G_CUDA(cudaStreamSynchronize(ctx->stream));
     const size_t CH = B2G_UP_CHUNK / sizeof(double);
-    // neighbouring small ranges travel in one DMA: [i, j) is a run whose device span fits one staging buffer
+    // spans: contiguous device stretches of at most one staging buffer, each a list of host pieces
+    struct Piece {
+        double *host;
+        size_t off, len; // offset inside the span, doubles
+    };
+    struct Span {
+        size_t dev_lo, len;
+        size_t p0, p1; // pieces [p0, p1)
+    };
+    std::vector<Piece> pieces;
+    std::vector<Span> spans;
     for (size_t i = 0; i < rg.size();) {
-        const size_t span_lo = rg[i].dev_off;
         const size_t len_i = (rg[i].hi - rg[i].lo) / sizeof(double);
-        if (len_i > CH) { // one large range: chunked
-            double *host = (double *)rg[i].lo;
+        if (len_i > CH) { // one large range: cut
             for (size_t off = 0; off < len_i; off += CH) {
                 const size_t m = std::min(CH, len_i - off);
-                B2G_CUDA(cudaMemcpyAsync(ctx->h_up[0], dev_base + span_lo + off, m * sizeof(double),
-                                         cudaMemcpyDeviceToHost, ctx->stream));
-                B2G_CUDA(cudaStreamSynchronize(ctx->stream));
-                const double *src = (const double *)ctx->h_up[0];
-                const int nt = m > ((size_t)1 << 16) ? ctx->up_threads : 1;
-                const size_t slice = (m + nt - 1) / nt;
-                std::vector<std::thread> th;
-                auto work = [=](size_t lo, size_t hi) {
-                    if (add)
-                        for (size_t j = lo; j < hi; j++)
-                            host[off + j] += src[j];
-                    else
-                        memcpy(host + off + lo, src + lo, (hi - lo) * sizeof(double));
-                };
-                for (int t = 1; t < nt; t++) {
-                    const size_t lo = std::min(m, slice * t), hi = std::min(m, slice * (t + 1));
-                    if (hi > lo)
-                        th.emplace_back(work, lo, hi);
-                }
-                work(0, std::min(m, slice));
-                for (auto &x : th)
-                    x.join();
+                spans.push_back(Span{rg[i].dev_off + off, m, pieces.size(), pieces.size() + 1});
+                pieces.push_back(Piece{(double *)rg[i].lo + off, 0, m});
             }
             i++;
             continue;
         }
+        const size_t span_lo = rg[i].dev_off;
         size_t j = i, span_hi = span_lo;
+        const size_t p0 = pieces.size();
         while (j < rg.size()) {
-            const size_t e = rg[j].dev_off + (rg[j].hi - rg[j].lo) / sizeof(double);
+            const size_t l = (rg[j].hi - rg[j].lo) / sizeof(double), e = rg[j].dev_off + l;
             if (e - span_lo > CH)
                 break;
+            pieces.push_back(Piece{(double *)rg[j].lo, rg[j].dev_off - span_lo, l});
             span_hi = e, j++;
         }
-        B2G_CUDA(cudaMemcpyAsync(ctx->h_up[0], dev_base + span_lo, (span_hi - span_lo) * sizeof(double),
-                                 cudaMemcpyDeviceToHost, ctx->stream));
-        B2G_CUDA(cudaStreamSynchronize(ctx->stream));
-        for (size_t r = i; r < j; r++) {
-            double *host = (double *)rg[r].lo;
-            const double *src = (const double *)ctx->h_up[0] + (rg[r].dev_off - span_lo);
-            const size_t m = (rg[r].hi - rg[r].lo) / sizeof(double);
-            if (add)
-                for (size_t q = 0; q < m; q++)
-                    host[q] += src[q];
-            else
-                memcpy(host, src, m * sizeof(double));
-        }
+        spans.push_back(Span{span_lo, span_hi - span_lo, p0, pieces.size()});
         i = j;
+    }
+    auto issue = [&](size_t k) -> int {
+        const int buf = (int)(k & 1);
+        B2G_CUDA(cudaMemcpyAsync(ctx->h_up[buf], dev_base + spans[k].dev_lo, spans[k].len * sizeof(double),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+        B2G_CUDA(cudaEventRecord(ctx->up_done[buf], ctx->stream));
+        return 0;
+    };
+    if (!spans.empty() && issue(0))
+        return 1;
+    for (size_t k = 0; k < spans.size(); k++) {
+        const int buf = (int)(k & 1);
+        B2G_CUDA(cudaEventSynchronize(ctx->up_done[buf]));
+        if (k + 1 < spans.size() && issue(k + 1)) // the next span travels while this one is folded into the host
+            return 1;
+        const double *stage = (const double *)ctx->h_up[buf];
+        const Span &sp = spans[k];
+        auto fold = [&](size_t lo, size_t hi) { // element range [lo, hi) of the span
+            for (size_t q = sp.p0; q < sp.p1; q++) {
+                const Piece &pc = pieces[q];
+                const size_t a0 = std::max(lo, pc.off), a1 = std::min(hi, pc.off + pc.len);
+                if (a0 >= a1)
+                    continue;
+                double *h = pc.host + (a0 - pc.off);
+                const double *sv = stage + a0;
+                if (add)
+                    for (size_t x = 0; x < a1 - a0; x++)
+                        h[x] += sv[x];
+                else
+                    memcpy(h, sv, (a1 - a0) * sizeof(double));
+            }
+        };
+        const int nt = sp.len > ((size_t)1 << 16) ? ctx->up_threads : 1;
+        if (nt == 1)
+            fold(0, sp.len);
+        else {
+            const size_t slice = (sp.len + nt - 1) / nt;
+            std::vector<std::thread> th;
+            for (int t = 1; t < nt; t++) {
+                const size_t lo = std::min(sp.len, slice * t), hi = std::min(sp.len, slice * (t + 1));
+                if (hi > lo)
+                    th.emplace_back(fold, lo, hi);
+            }
+            fold(0, std::min(sp.len, slice));
+            for (auto &x : th)
+                x.join();
+        }
     }
     return 0;
 }

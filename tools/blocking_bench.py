@@ -16,14 +16,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+DEFAULT_WORKLOAD = os.path.join(ROOT, "workloads", "cr2_svp_m4000_blocking", "cr2_m4000_s20_call39.b2tp.gz")
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("workload", nargs="?",
-                    default=os.path.join(ROOT, "workloads", "cr2_svp_m4000_blocking", "cr2_m4000_s20_call39.b2tp.gz"))
+    ap.add_argument("workload", nargs="?", default=DEFAULT_WORKLOAD)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--check-windows", type=int, default=24)
     args = ap.parse_args()
+    print(json.dumps(run(args)))
+
+
+def run(args, ctx=None):
+    """args: .workload .steps .warmup .check_windows; returns the result line as a dict."""
     import torch
     import b2gpkg
     b2g = b2gpkg.load()
@@ -37,7 +44,7 @@ def main():
         src[lo:lo + CH].uniform_(-1.0, 1.0, generator=gen)
     out = torch.zeros(n_out, dtype=torch.float64, device="cuda")
     torch.cuda.synchronize()
-    ctx = b2g.Context(0)
+    ctx = ctx or b2g.Context(0)
     T = tp.t
     terms = np.zeros(tp.nterms, dtype=b2g.TP_DTYPE)
     terms["a"] = src.data_ptr() + 8 * a_off
@@ -103,7 +110,9 @@ def main():
         "parity": {"sampled_windows_max_rel_err": worst, "bilinearity_rel_err": lin},
         "plan_seconds_host": st.plan_seconds, "launches_per_call": int(st.launches),
     }
-    print(json.dumps(line))
+    del src, out
+    torch.cuda.empty_cache()
+    return line
 
 
 if __name__ == "__main__":

@@ -20,6 +20,8 @@ run() { local name=$1; shift
   timeout ${TMO:-900} "$@" > gpurun_out/dmrg_$name.log 2>&1; echo "exit $?" >> gpurun_out/dmrg_$name.log
   grep '"mode"' gpurun_out/dmrg_$name.log | tail -1; }
 run c2_m1000_blk $B/b2g_dmrg_su2 --fcidump $B/data/C2.CAS.PVDZ.FCIDUMP --bond 1000 --nsweeps 3 --threads $T --noise 1e-5 --gpu-contract --gpu-rotate --compare
+if [ "${CR2_VERIFY:-0}" = "1" ]; then
 run cr2_m500_verify $B/b2g_dmrg_su2 --fcidump $B/data/CR2.SVP.FCIDUMP --occ $B/data/CR2.SVP.OCC --bond 500 --nsweeps 1 --threads $T --noise 1e-5 --dsize 24 --gpu-contract --gpu-rotate --verify
+fi
 run cr2_m500_blk $B/b2g_dmrg_su2 --fcidump $B/data/CR2.SVP.FCIDUMP --occ $B/data/CR2.SVP.OCC --bond 500 --nsweeps 2 --threads $T --noise 1e-5 --dsize 24 --gpu-contract --gpu-rotate --compare
 grep -h "Time sweep\|^=== " gpurun_out/dmrg_c2_m1000_blk.log gpurun_out/dmrg_cr2_m500_blk.log | tail -20
