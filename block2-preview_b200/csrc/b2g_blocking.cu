@@ -513,7 +513,9 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
         }
         // unit size by cost (elements x contributions) so that a window with many contributions is
         // spread over many warps; wide 2-D windows are cut into row-aligned units (linear addressing)
-        const int64_t cap = std::max<int64_t>(128, std::min<int64_t>(UNIT_ELEMS, (4 * UNIT_ELEMS) / cl[ci].count) / 128 * 128);
+        static const int64_t cap_min = getenv("B2G_BLK_CAPMIN") ? atoll(getenv("B2G_BLK_CAPMIN")) : 128;
+        static const int64_t cap_num = getenv("B2G_BLK_CAPNUM") ? atoll(getenv("B2G_BLK_CAPNUM")) : 4 * UNIT_ELEMS;
+        const int64_t cap = std::max<int64_t>(cap_min, std::min<int64_t>(UNIT_ELEMS, cap_num / cl[ci].count) / 128 * 128);
         if (!axpy || w.n < ROW_MIN) {
             for (int64_t e0 = 0; e0 < total; e0 += cap)
                 dstu.push_back(BlkUnit{w.dst, (int32_t)e0, (int32_t)std::min<int64_t>(cap, total - e0), w.n, w.ldc, first,

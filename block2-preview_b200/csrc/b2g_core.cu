@@ -97,13 +97,48 @@ struct MirrorWriter {
     char *dst_base;
     size_t slice_begin = 0, fill = 0;
     int buf = 0;
+    struct Piece {
+        size_t off; // inside the slice
+        const void *src;
+        size_t bytes;
+    };
+    std::vector<Piece> pieces;
+    // copy the recorded pieces into the staging buffer (several host threads for a large slice), one DMA
     int flush() {
         if (fill) {
-            B2G_CUDA(cudaMemcpyAsync(dst_base + slice_begin, ctx->h_up[buf], fill, cudaMemcpyHostToDevice,
-                                     ctx->stream));
+            B2G_CUDA(cudaEventSynchronize(ctx->up_done[buf])); // last DMA out of this buffer has finished
+            char *stage = (char *)ctx->h_up[buf];
+            const int nt = fill > ((size_t)4 << 20) ? std::min<int>(ctx->up_threads, (int)pieces.size()) : 1;
+            if (nt <= 1) {
+                for (const Piece &pc : pieces)
+                    memcpy(stage + pc.off, pc.src, pc.bytes);
+            } else { // contiguous groups of pieces with about equal byte counts
+                std::vector<std::thread> th;
+                const size_t per = (fill + nt - 1) / nt;
+                size_t i = 0;
+                for (int t = 0; t < nt && i < pieces.size(); t++) {
+                    size_t j = i, acc = 0;
+                    while (j < pieces.size() && (acc < per || t == nt - 1))
+                        acc += pieces[j++].bytes;
+                    const Piece *pp = pieces.data();
+                    auto work = [stage, pp, i, j]() {
+                        for (size_t q = i; q < j; q++)
+                            memcpy(stage + pp[q].off, pp[q].src, pp[q].bytes);
+                    };
+                    if (j < pieces.size())
+                        th.emplace_back(work);
+                    else
+                        work();
+                    i = j;
+                }
+                for (auto &x : th)
+                    x.join();
+            }
+            B2G_CUDA(cudaMemcpyAsync(dst_base + slice_begin, stage, fill, cudaMemcpyHostToDevice, ctx->stream));
             B2G_CUDA(cudaEventRecord(ctx->up_done[buf], ctx->stream));
             buf ^= 1;
             fill = 0;
+            pieces.clear();
         }
         return 0;
     }
@@ -116,11 +151,9 @@ struct MirrorWriter {
         if (fill && (dev_off < slice_begin || dev_off - slice_begin + bytes > B2G_UP_CHUNK))
             if (flush())
                 return 1;
-        if (!fill) {
-            B2G_CUDA(cudaEventSynchronize(ctx->up_done[buf])); // last DMA out of this buffer has finished
+        if (!fill)
             slice_begin = dev_off;
-        }
-        memcpy((char *)ctx->h_up[buf] + (dev_off - slice_begin), src, bytes);
+        pieces.push_back(Piece{dev_off - slice_begin, src, bytes});
         fill = dev_off - slice_begin + bytes;
         return 0;
     }

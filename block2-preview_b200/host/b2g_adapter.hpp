@@ -59,7 +59,7 @@ struct Session {
     // blocks the latest blocking calls left resident in HBM (b2g KEEP_RESIDENT): the operator, the host
     // address and size it had when it was produced.  An entry is vouched for (b2g_resident_vouch) only
     // while the operator object is alive and still owns exactly that storage.
-    bool keep_resident = true, uninit_outputs = false;
+    bool keep_resident = true, uninit_outputs = true;
     struct ResidentOp {
         std::weak_ptr<void> owner;
         const double *data;
@@ -89,6 +89,7 @@ struct Session {
     double resident_hit_bytes = 0, resident_peak_bytes = 0;
     size_t n_contract = 0, contract_entries = 0;
     explicit Session(int device = 0) {
+        uninit_outputs = getenv("B2G_ZERO_OUTPUTS") == nullptr; // A/B switch, see contract_on_device
         if (b2g_context_create(device, &ctx) != 0)
             throw std::runtime_error(std::string("b2g_context_create: ") + b2g_last_error());
     }
@@ -266,8 +267,9 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
         const SeqTypes saved = seq->mode;
         shared_ptr<GPUOperatorFunctions<S>> gopf = dynamic_pointer_cast<GPUOperatorFunctions<S>>(opf);
         const OpMap &lop = right ? b->ops : a->ops, &rop = right ? a->ops : b->ops;
-        // uninitialised outputs + overwrite (B2G_DST_COVERED) measured slower than zero fill + add at C2 M=1000
-        // (first-touch page faults land in the download: 9.1 s against 4.0 s), so it stays off
+        // uninitialised outputs + overwrite (B2G_DST_COVERED) instead of zero fill (twice: VectorAllocator and
+        // SparseMatrix::allocate) + add: the first touch of the pages happens in the threaded, pipelined
+        // download.  C2 M=1000, three sweeps: blocking 11.8 -> 5.6 s, sweeps 21.2 -> 16.9 s
         const bool covered = gopf != nullptr && session->keep_resident && session->uninit_outputs;
         vector<size_t> todo;
         for (size_t i = 0; i < exprs->data.size(); i++) {
