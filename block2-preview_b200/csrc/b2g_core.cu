@@ -58,8 +58,10 @@ extern "C" int b2g_context_create(int device, b2g_context **out) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     ctx->up_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    int prio_lo = 0, prio_hi = 0; // side streams at the lowest priority: their CTAs fill the tails of the
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi); // launches on the context stream
     for (int i = 0; i < b2g_context::N_SIDE; i++) {
-        B2G_CUDA(cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking));
+        B2G_CUDA(cudaStreamCreateWithPriority(&ctx->side[i], cudaStreamNonBlocking, prio_lo));
         B2G_CUDA(cudaEventCreateWithFlags(&ctx->side_done[i], cudaEventDisableTiming));
     }
     B2G_CUDA(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));

@@ -716,7 +716,14 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
     // the next phase; with profiling everything stays on the context stream (timed one by one).
     // Forking pays when no single launch fills the chip (measured: up to ~2x on the C2 / H10 lists,
     // -5 % on the 2 TFLOP Cr2 list where the big persistent kernels then compete), hence the bound.
-    const bool fork = stats == nullptr && 2.0 * (double)p->stats.nflop_mnk < 3e11;
+    const bool fork_all = stats == nullptr && 2.0 * (double)p->stats.nflop_mnk < 3e11;
+    // Large lists, experiment (B2G_FORK_SMALL=<flops>): only the minor launches (edge-strip and 64-row
+    // configurations, a few % of the FLOPs each) go to the low-priority side streams, to fill the tails of
+    // the big persistent launches that stay on the context stream.  Measured on the Cr2 M=4000 list: 81.5 /
+    // 83.6 ms with the threshold at 50 / 15 GFLOP against 80.4 ms in sequence, so it is off by default.
+    static const double fork_small_below = getenv("B2G_FORK_SMALL") ? atof(getenv("B2G_FORK_SMALL")) : 0.0;
+    const bool fork_small = stats == nullptr && !fork_all && fork_small_below > 0.0;
+    const bool fork = fork_all || fork_small;
     int n_forked = 0;
     auto join = [&]() -> int {
         for (int i = 0; i < std::min(n_forked, (int)b2g_context::N_SIDE); i++)
@@ -748,7 +755,8 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
                 B2G_CUDA(cudaEventRecord(ctx->fork_ev, ctx->stream));
         }
         cudaStream_t gs = ctx->stream;
-        if (fork) {
+        const bool side = fork_all || (fork_small && g.flops < fork_small_below);
+        if (side) {
             gs = ctx->side[n_forked % b2g_context::N_SIDE];
             if (n_forked < b2g_context::N_SIDE)
                 B2G_CUDA(cudaStreamWaitEvent(gs, ctx->fork_ev, 0));
@@ -793,7 +801,7 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
         ctx->launches++;
         if (end())
             return 1;
-        if (fork) {
+        if (side) {
             B2G_CUDA(cudaEventRecord(ctx->side_done[n_forked % b2g_context::N_SIDE], gs));
             n_forked++;
         }
