@@ -95,9 +95,9 @@ constexpr int ROW_MIN = 128;   // windows at least this wide are cut into row-al
 constexpr int STREAM_PER = 8;  // elements per lane and step
 constexpr int RING_STAGES = 4; // cp.async ring depth of the streaming kernel
 constexpr size_t RING_BYTES = (size_t)(BLK_THREADS / 32) * RING_STAGES * STREAM_PER * 32 * sizeof(double);
-constexpr int ACC_STAGES = 3;             // ring depth of the accumulating kernel (4 measured slower)
+constexpr int ACC_STAGES_DEFAULT = 3;     // ring depth of the accumulating kernel
 constexpr int ACC_SLOT = STREAM_PER + 3;  // per lane and stage: 8 source values, b, alpha, beta
-constexpr size_t ACC_RING_BYTES = (size_t)(BLK_THREADS / 32) * ACC_STAGES * ACC_SLOT * 32 * sizeof(double);
+constexpr size_t acc_ring_bytes(int stages) { return (size_t)(BLK_THREADS / 32) * stages * ACC_SLOT * 32 * sizeof(double); }
 
 __device__ __forceinline__ void cp_async8(double *smem, const double *gmem) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -110,6 +110,7 @@ __device__ __forceinline__ void cp_async8(double *smem, const double *gmem) {
 // while step q is folded into the running values (8 per lane, in registers from the first to the last
 // contribution of a sub-chunk), so the loads of different contributions overlap.  The descriptor of the
 // next contribution is fetched one step ahead.  dst_zero: outputs start from 0 (not read).
+template <int ACC_STAGES>
 __global__ void __launch_bounds__(BLK_THREADS, 2)
 b2g_blocking_kernel(const BlkUnit *__restrict__ units, int64_t nunits, const BlkEntry *__restrict__ entries,
                     int dst_zero) {
@@ -270,6 +271,101 @@ b2g_blocking_stream_kernel(const StreamUnit *__restrict__ units, int64_t nunits)
                 bnext = __ldg(N.b); // N has arrived by now; its scalar is ready when this unit ends
         }
         U = N, bval = bnext;
+    }
+}
+
+// Multi-source streaming units: 2..MULTI_MAX contributions, all linear - e.g. the two-term sums that
+// make up half of the bytes of an H_eff blocking step.  Like the streaming kernel (self-contained
+// descriptor, per-thread cp.async ring with RING_STAGES - 1 steps in flight), a step being one
+// (256-element sub-chunk, contribution) pair; the running values stay in registers across the
+// contributions of a sub-chunk, in list order.
+constexpr int MULTI_MAX = 4;
+struct MultiUnit { // 160 bytes
+    double *dst;
+    const double *src[MULTI_MAX];
+    const double *b[MULTI_MAX];
+    double alpha[MULTI_MAX];
+    double beta[MULTI_MAX];
+    int32_t sstep[MULTI_MAX];
+    int32_t len, dstep, count, pad;
+};
+static_assert(sizeof(MultiUnit) == 8 + 4 * 8 * MULTI_MAX + 4 * MULTI_MAX + 16, "MultiUnit layout");
+
+__global__ void __launch_bounds__(BLK_THREADS, 3)
+b2g_blocking_multi_kernel(const MultiUnit *__restrict__ units, int64_t nunits, int dst_zero) {
+    extern __shared__ double ring[];
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * BLK_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * BLK_THREADS) >> 5;
+    double *my = ring + ((size_t)(threadIdx.x >> 5) * RING_STAGES * STREAM_PER) * 32 + lane;
+    for (int64_t u = warp; u < nunits; u += nwarps) {
+        const MultiUnit &G = units[u];
+        const int count = G.count, len = G.len;
+        const int64_t dstep = G.dstep;
+        double *__restrict__ dptr = G.dst;
+        const double *sp[MULTI_MAX];
+        double f[MULTI_MAX], bt[MULTI_MAX];
+        int64_t ss[MULTI_MAX];
+#pragma unroll
+        for (int t = 0; t < MULTI_MAX; t++) {
+            const bool on = t < count;
+            sp[t] = on ? G.src[t] : nullptr, ss[t] = on ? G.sstep[t] : 0;
+            f[t] = on ? G.alpha[t] * __ldg(G.b[t]) : 0.0, bt[t] = on ? G.beta[t] : 1.0;
+        }
+        const int nchunks = (len + 32 * STREAM_PER - 1) / (32 * STREAM_PER);
+        const int steps = nchunks * count;
+        int qi = 0, ci = 0, ti = 0;
+        auto issue = [&]() {
+            if (qi < steps) {
+                double *slot = my + (size_t)(qi % RING_STAGES) * STREAM_PER * 32;
+                const double *s0 = ti == 0 ? sp[0] : (ti == 1 ? sp[1] : (ti == 2 ? sp[2] : sp[3]));
+                const int64_t st = ti == 0 ? ss[0] : (ti == 1 ? ss[1] : (ti == 2 ? ss[2] : ss[3]));
+#pragma unroll
+                for (int r = 0; r < STREAM_PER; r++) {
+                    const int l = ci * 32 * STREAM_PER + r * 32 + lane;
+                    if (l < len)
+                        cp_async8(slot + r * 32, s0 + l * st);
+                }
+                qi++;
+                if (++ti == count)
+                    ti = 0, ci++;
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        };
+#pragma unroll
+        for (int p = 0; p < RING_STAGES - 1; p++)
+            issue();
+        double acc[STREAM_PER];
+        int tc = 0, cc = 0;
+        for (int q = 0; q < steps; q++) {
+            issue();
+            asm volatile("cp.async.wait_group %0;\n" ::"n"(RING_STAGES - 1) : "memory");
+            const double *slot = my + (size_t)(q % RING_STAGES) * STREAM_PER * 32;
+            if (tc == 0) {
+#pragma unroll
+                for (int r = 0; r < STREAM_PER; r++) {
+                    const int l = cc * 32 * STREAM_PER + r * 32 + lane;
+                    acc[r] = (!dst_zero && l < len) ? dptr[l * dstep] : 0.0;
+                }
+            }
+            const double ft = tc == 0 ? f[0] : (tc == 1 ? f[1] : (tc == 2 ? f[2] : f[3]));
+            const double be = tc == 0 ? bt[0] : (tc == 1 ? bt[1] : (tc == 2 ? bt[2] : bt[3]));
+#pragma unroll
+            for (int r = 0; r < STREAM_PER; r++) {
+                const int l = cc * 32 * STREAM_PER + r * 32 + lane;
+                if (l < len)
+                    acc[r] = fma(ft, slot[r * 32], be == 1.0 ? acc[r] : (be == 0.0 ? 0.0 : be * acc[r]));
+            }
+            if (++tc == count) {
+#pragma unroll
+                for (int r = 0; r < STREAM_PER; r++) {
+                    const int l = cc * 32 * STREAM_PER + r * 32 + lane;
+                    if (l < len)
+                        dptr[l * dstep] = acc[r];
+                }
+                tc = 0, cc++;
+            }
+        }
     }
 }
 
@@ -568,11 +664,12 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
     BlkEntry *d_entries = nullptr;
     BlkUnit *d_units = nullptr, *d_gunits = nullptr;
     StreamUnit *d_sunits = nullptr;
+    MultiUnit *d_munits = nullptr;
     BlkSerial *d_serial = nullptr;
     int64_t *d_comp = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     auto cleanup = [&]() {
-        b2g_dfree(ctx, d_in), b2g_dfree(ctx, d_out), b2g_dfree(ctx, d_entries), b2g_dfree(ctx, d_units), b2g_dfree(ctx, d_gunits), b2g_dfree(ctx, d_sunits);
+        b2g_dfree(ctx, d_in), b2g_dfree(ctx, d_out), b2g_dfree(ctx, d_entries), b2g_dfree(ctx, d_units), b2g_dfree(ctx, d_gunits), b2g_dfree(ctx, d_sunits), b2g_dfree(ctx, d_munits);
         b2g_dfree(ctx, d_serial), b2g_dfree(ctx, d_comp);
         if (ev0)
             cudaEventDestroy(ev0);
@@ -627,7 +724,17 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
     }
     // single-contribution linear units become self-contained streaming units
     std::vector<StreamUnit> sunits;
+    std::vector<MultiUnit> munits;
     {
+        // every contribution linear, read (alpha != 0) and k = 1
+        auto multi_ok = [&dev_entries](const BlkUnit &u) {
+            for (int t = 0; t < u.count; t++) {
+                const BlkEntry &Et = dev_entries[u.first + t];
+                if (Et.nd != 0 || Et.alpha == 0.0 || Et.k != 1)
+                    return false;
+            }
+            return true;
+        };
         std::vector<BlkUnit> rest;
         rest.reserve(units.size());
         for (const BlkUnit &u : units) {
@@ -642,6 +749,19 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
                 su.len = u.len, su.dstep = rowu ? 1 : u.ldc, su.sstep = rowu ? E.sa_j : E.sa_i, su.pad = 0;
                 su.pad2[0] = su.pad2[1] = 0;
                 sunits.push_back(su);
+            } else if (u.count >= 2 && u.count <= MULTI_MAX && (rowu || flat) && multi_ok(u)) {
+                const int64_t i0 = rowu ? u.e0 / u.n : 0, j0 = rowu ? u.e0 - i0 * u.n : 0;
+                MultiUnit mu;
+                memset(&mu, 0, sizeof(mu));
+                mu.dst = u.dst + (rowu ? i0 * u.ldc + j0 : (int64_t)u.e0 * u.ldc);
+                for (int t = 0; t < u.count; t++) {
+                    const BlkEntry &Et = dev_entries[u.first + t];
+                    mu.src[t] = Et.a + (rowu ? i0 * Et.sa_i + j0 * Et.sa_j : (int64_t)u.e0 * Et.sa_i);
+                    mu.b[t] = Et.b, mu.alpha[t] = Et.alpha, mu.beta[t] = Et.beta;
+                    mu.sstep[t] = rowu ? Et.sa_j : Et.sa_i;
+                }
+                mu.len = u.len, mu.dstep = rowu ? 1 : u.ldc, mu.count = u.count;
+                munits.push_back(mu);
             } else
                 rest.push_back(u);
         }
@@ -668,6 +788,13 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
                             ctx->stream) != cudaSuccess)
             return fail(std::string(who) + ": descriptor upload failed");
     }
+    if (!munits.empty()) {
+        if (b2g_dmalloc(ctx, (void **)&d_munits, munits.size() * sizeof(MultiUnit)))
+            return fail("");
+        if (cudaMemcpyAsync(d_munits, munits.data(), munits.size() * sizeof(MultiUnit), cudaMemcpyHostToDevice,
+                            ctx->stream) != cudaSuccess)
+            return fail(std::string(who) + ": descriptor upload failed");
+    }
     if (!serial.empty()) {
         if (b2g_dmalloc(ctx, (void **)&d_serial, serial.size() * sizeof(BlkSerial)) ||
             b2g_dmalloc(ctx, (void **)&d_comp, comp_first.size() * sizeof(int64_t)))
@@ -686,11 +813,18 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
     if (cudaEventCreate(&ev0) != cudaSuccess || cudaEventCreate(&ev1) != cudaSuccess)
         return fail("" + std::string(who) + ": event creation failed");
     cudaEventRecord(ev0, ctx->stream);
+    static const int acc_stages = getenv("B2G_BLK_STAGES") ? atoi(getenv("B2G_BLK_STAGES")) : ACC_STAGES_DEFAULT;
     static bool ring_attr = false;
     if (!ring_attr) {
-        if (cudaFuncSetAttribute(b2g_blocking_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACC_RING_BYTES) !=
-                cudaSuccess ||
+        if (cudaFuncSetAttribute(b2g_blocking_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)acc_ring_bytes(3)) != cudaSuccess ||
+            cudaFuncSetAttribute(b2g_blocking_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)acc_ring_bytes(4)) != cudaSuccess ||
+            cudaFuncSetAttribute(b2g_blocking_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)acc_ring_bytes(5)) != cudaSuccess ||
             cudaFuncSetAttribute(b2g_blocking_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)RING_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(b2g_blocking_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)RING_BYTES) != cudaSuccess)
             return fail(std::string(who) + ": cudaFuncSetAttribute failed");
         ring_attr = true;
@@ -699,6 +833,13 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
         const int64_t want = ((int64_t)sunits.size() * 32 + BLK_THREADS - 1) / BLK_THREADS;
         const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 3); // 3 resident CTAs per SM
         b2g_blocking_stream_kernel<<<grid, BLK_THREADS, RING_BYTES, ctx->stream>>>(d_sunits, (int64_t)sunits.size());
+        ctx->launches++, st.launches++;
+    }
+    if (!munits.empty()) {
+        const int64_t want = ((int64_t)munits.size() * 32 + BLK_THREADS - 1) / BLK_THREADS;
+        const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 3);
+        b2g_blocking_multi_kernel<<<grid, BLK_THREADS, RING_BYTES, ctx->stream>>>(d_munits, (int64_t)munits.size(),
+                                                                                  dst_zero ? 1 : 0);
         ctx->launches++, st.launches++;
     }
     cudaEvent_t evs = nullptr;
@@ -710,8 +851,15 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
     if (!units.empty()) {
         const int64_t want = ((int64_t)units.size() * 32 + BLK_THREADS - 1) / BLK_THREADS;
         const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 2); // 2 resident CTAs per SM
-        b2g_blocking_kernel<<<grid, BLK_THREADS, ACC_RING_BYTES, ctx->stream>>>(d_units, (int64_t)units.size(), d_entries,
-                                                                   dst_zero ? 1 : 0);
+        if (acc_stages == 5)
+            b2g_blocking_kernel<5><<<grid, BLK_THREADS, acc_ring_bytes(5), ctx->stream>>>(d_units, (int64_t)units.size(),
+                                                                                         d_entries, dst_zero ? 1 : 0);
+        else if (acc_stages == 4)
+            b2g_blocking_kernel<4><<<grid, BLK_THREADS, acc_ring_bytes(4), ctx->stream>>>(d_units, (int64_t)units.size(),
+                                                                                         d_entries, dst_zero ? 1 : 0);
+        else
+            b2g_blocking_kernel<3><<<grid, BLK_THREADS, acc_ring_bytes(3), ctx->stream>>>(d_units, (int64_t)units.size(),
+                                                                                         d_entries, dst_zero ? 1 : 0);
         ctx->launches++, st.launches++;
     }
     if (!gunits.empty()) {
@@ -741,9 +889,9 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
             se += (size_t)u.len;
         for (const BlkUnit &u : units)
             re += (size_t)u.len;
-        fprintf(stderr, "[b2g] blocking: stream %zu units %zu elements %.3f ms | regular %zu units %zu elements, general %zu units, "
+        fprintf(stderr, "[b2g] blocking: multi %zu units | stream %zu units %zu elements %.3f ms | regular %zu units %zu elements, general %zu units, "
                         "serial %zu entries %.3f ms\n",
-                sunits.size(), se, ms_s, units.size(), re, gunits.size(), serial.size(), ms - ms_s);
+                munits.size(), sunits.size(), se, ms_s, units.size(), re, gunits.size(), serial.size(), ms - ms_s);
         cudaEventDestroy(evs);
     }
 
