@@ -369,6 +369,100 @@ b2g_blocking_multi_kernel(const MultiUnit *__restrict__ units, int64_t nunits, i
     }
 }
 
+// Tile units: 2-D windows with several contributions of which some are TRANSPOSED sources
+// (C(i, j) += f * A(j, i): contiguous along i).  Row-shaped units would read such a source with a stride
+// of one pitch per lane; here one warp owns a TILE_R x TILE_C tile of the window, every contribution is
+// copied into a warp-shared padded tile in shared memory along ITS OWN contiguous direction (cp.async
+// ring, one contribution per step) and folded into the running values (TILE_R per lane, registers) in
+// list order.  The tile is written once, row by row.
+constexpr int TILE_R = 16, TILE_C = 32, TILE_LD = TILE_C + 1, TILE_STAGES = 3;
+constexpr int TILE_SLOT = TILE_R * TILE_LD + 4; // tile + (b, alpha, beta, pad) of the step
+constexpr size_t TILE_RING_BYTES = (size_t)(BLK_THREADS / 32) * TILE_STAGES * TILE_SLOT * sizeof(double);
+struct TileUnit { // 40 bytes
+    double *dst;  // window origin
+    int32_t i0, j0, m, n, ldc, first, count, pad;
+};
+static_assert(sizeof(TileUnit) == 40, "TileUnit layout");
+
+__global__ void __launch_bounds__(BLK_THREADS, 2)
+b2g_blocking_tile_kernel(const TileUnit *__restrict__ units, int64_t nunits, const BlkEntry *__restrict__ entries,
+                         int dst_zero) {
+    extern __shared__ double ring[];
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * BLK_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * BLK_THREADS) >> 5;
+    double *my = ring + (size_t)(threadIdx.x >> 5) * TILE_STAGES * TILE_SLOT;
+    for (int64_t u = warp; u < nunits; u += nwarps) {
+        const TileUnit U = units[u];
+        const int rows = min(TILE_R, U.m - U.i0), cols = min(TILE_C, U.n - U.j0);
+        double *__restrict__ dptr = U.dst + (int64_t)U.i0 * U.ldc + U.j0;
+        BlkEntry Ep = entries[U.first];
+        int qi = 0;
+        auto issue = [&]() {
+            if (qi < U.count) {
+                const BlkEntry E = Ep;
+                if (qi + 1 < U.count)
+                    Ep = entries[U.first + qi + 1]; // in flight until the next issue
+                double *slot = my + (size_t)(qi % TILE_STAGES) * TILE_SLOT;
+                if (lane == 0) {
+                    slot[TILE_R * TILE_LD + 1] = E.alpha, slot[TILE_R * TILE_LD + 2] = E.beta;
+                    if (E.alpha != 0.0)
+                        cp_async8(slot + TILE_R * TILE_LD, E.b);
+                }
+                if (E.alpha != 0.0) {
+                    const double *base = E.a + (int64_t)U.i0 * E.sa_i + (int64_t)U.j0 * E.sa_j;
+                    if (E.sa_i == 1 && E.sa_j != 1) { // transposed source: consecutive i are contiguous
+                        const int i = lane & (TILE_R - 1), jh = lane / TILE_R;
+#pragma unroll
+                        for (int r = 0; r < TILE_C / (32 / TILE_R); r++) {
+                            const int j = r * (32 / TILE_R) + jh;
+                            if (i < rows && j < cols)
+                                cp_async8(slot + i * TILE_LD + j, base + i + (int64_t)j * E.sa_j);
+                        }
+                    } else { // consecutive j are contiguous (or a general stride)
+#pragma unroll
+                        for (int r = 0; r < TILE_R; r++)
+                            if (r < rows && lane < cols)
+                                cp_async8(slot + r * TILE_LD + lane, base + (int64_t)r * E.sa_i + (int64_t)lane * E.sa_j);
+                    }
+                }
+                qi++;
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        };
+#pragma unroll
+        for (int p = 0; p < TILE_STAGES - 1; p++)
+            issue();
+        double acc[TILE_R];
+#pragma unroll
+        for (int r = 0; r < TILE_R; r++)
+            acc[r] = (!dst_zero && r < rows && lane < cols) ? dptr[(int64_t)r * U.ldc + lane] : 0.0;
+        for (int q = 0; q < U.count; q++) {
+            issue();
+            asm volatile("cp.async.wait_group %0;\n" ::"n"(TILE_STAGES - 1) : "memory");
+            __syncwarp(); // the copies of every lane of the warp have landed
+            const double *slot = my + (size_t)(q % TILE_STAGES) * TILE_SLOT;
+            const double alpha = slot[TILE_R * TILE_LD + 1], beta = slot[TILE_R * TILE_LD + 2];
+            if (alpha != 0.0) {
+                const double f = alpha * slot[TILE_R * TILE_LD];
+#pragma unroll
+                for (int r = 0; r < TILE_R; r++)
+                    if (r < rows && lane < cols)
+                        acc[r] = fma(f, slot[r * TILE_LD + lane], beta == 1.0 ? acc[r] : (beta == 0.0 ? 0.0 : beta * acc[r]));
+            } else {
+#pragma unroll
+                for (int r = 0; r < TILE_R; r++)
+                    acc[r] = beta == 1.0 ? acc[r] : (beta == 0.0 ? 0.0 : beta * acc[r]);
+            }
+            __syncwarp(); // all lanes are done with this stage before a later step overwrites it
+        }
+#pragma unroll
+        for (int r = 0; r < TILE_R; r++)
+            if (r < rows && lane < cols)
+                dptr[(int64_t)r * U.ldc + lane] = acc[r];
+    }
+}
+
 // Windows with a general contribution (k > 1, or B varying over the window): one thread per element.
 __global__ void __launch_bounds__(BLK_THREADS)
 b2g_blocking_general_kernel(const BlkUnit *__restrict__ units, int64_t nunits, const BlkEntry *__restrict__ entries,
@@ -583,6 +677,8 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
     // ---- 4. device descriptors
     std::vector<BlkEntry> dev_entries;
     std::vector<BlkUnit> units, gunits; // AXPY windows / windows with a general contribution
+    std::vector<TileUnit> tunits;       // AXPY windows with transposed sources among several contributions
+    static const bool tile_on = getenv("B2G_BLK_NOTILE") == nullptr;
     dev_entries.reserve(he.size());
     std::vector<BlkSerial> serial;
     for (size_t ci = 0; ci < cl.size(); ci++) {
@@ -612,7 +708,16 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
         static const int64_t cap_min = getenv("B2G_BLK_CAPMIN") ? atoll(getenv("B2G_BLK_CAPMIN")) : 128;
         static const int64_t cap_num = getenv("B2G_BLK_CAPNUM") ? atoll(getenv("B2G_BLK_CAPNUM")) : 4 * UNIT_ELEMS;
         const int64_t cap = std::max<int64_t>(cap_min, std::min<int64_t>(UNIT_ELEMS, cap_num / cl[ci].count) / 128 * 128);
-        if (!axpy || w.n < ROW_MIN) {
+        bool transposed_src = false;
+        for (int q = 0; q < cl[ci].count; q++) {
+            const BlkEntry &e = dev_entries[first + q];
+            transposed_src = transposed_src || (e.alpha != 0.0 && e.sa_j != 1);
+        }
+        if (axpy && tile_on && transposed_src && cl[ci].count >= 2 && w.n >= TILE_C && w.m >= 2) {
+            for (int64_t i0 = 0; i0 < w.m; i0 += TILE_R)
+                for (int64_t j0 = 0; j0 < w.n; j0 += TILE_C)
+                    tunits.push_back(TileUnit{w.dst, (int32_t)i0, (int32_t)j0, w.m, w.n, w.ldc, first, cl[ci].count, 0});
+        } else if (!axpy || w.n < ROW_MIN) {
             for (int64_t e0 = 0; e0 < total; e0 += cap)
                 dstu.push_back(BlkUnit{w.dst, (int32_t)e0, (int32_t)std::min<int64_t>(cap, total - e0), w.n, w.ldc, first,
                                        cl[ci].count});
@@ -651,7 +756,7 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
         for (const BlkSerial &s : serial)
             st.bytes_out += (int64_t)s.m * s.n * 8;
     }
-    st.units = (int64_t)(units.size() + gunits.size()); // before the streaming split
+    st.units = (int64_t)(units.size() + gunits.size() + tunits.size()); // before the streaming split
     st.serial_entries = (int64_t)serial.size();
     if (dst_zero && operand_space == B2G_OPERANDS_DEVICE && !serial.empty()) {
         b2g_set_error("" + std::string(who) + ": B2G_DST_ZERO with device operands needs regular (identical or disjoint) output windows");
@@ -665,11 +770,12 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
     BlkUnit *d_units = nullptr, *d_gunits = nullptr;
     StreamUnit *d_sunits = nullptr;
     MultiUnit *d_munits = nullptr;
+    TileUnit *d_tunits = nullptr;
     BlkSerial *d_serial = nullptr;
     int64_t *d_comp = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     auto cleanup = [&]() {
-        b2g_dfree(ctx, d_in), b2g_dfree(ctx, d_out), b2g_dfree(ctx, d_entries), b2g_dfree(ctx, d_units), b2g_dfree(ctx, d_gunits), b2g_dfree(ctx, d_sunits), b2g_dfree(ctx, d_munits);
+        b2g_dfree(ctx, d_in), b2g_dfree(ctx, d_out), b2g_dfree(ctx, d_entries), b2g_dfree(ctx, d_units), b2g_dfree(ctx, d_gunits), b2g_dfree(ctx, d_sunits), b2g_dfree(ctx, d_munits), b2g_dfree(ctx, d_tunits);
         b2g_dfree(ctx, d_serial), b2g_dfree(ctx, d_comp);
         if (ev0)
             cudaEventDestroy(ev0);
@@ -715,6 +821,8 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
         for (BlkUnit &u : units)
             u.dst = b2g_translate(out_rg, d_out, u.dst);
         for (BlkUnit &u : gunits)
+            u.dst = b2g_translate(out_rg, d_out, u.dst);
+        for (TileUnit &u : tunits)
             u.dst = b2g_translate(out_rg, d_out, u.dst);
         for (BlkSerial &s : serial) {
             if (s.e.alpha != 0.0 && s.e.k > 0)
@@ -788,6 +896,13 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
                             ctx->stream) != cudaSuccess)
             return fail(std::string(who) + ": descriptor upload failed");
     }
+    if (!tunits.empty()) {
+        if (b2g_dmalloc(ctx, (void **)&d_tunits, tunits.size() * sizeof(TileUnit)))
+            return fail("");
+        if (cudaMemcpyAsync(d_tunits, tunits.data(), tunits.size() * sizeof(TileUnit), cudaMemcpyHostToDevice,
+                            ctx->stream) != cudaSuccess)
+            return fail(std::string(who) + ": descriptor upload failed");
+    }
     if (!munits.empty()) {
         if (b2g_dmalloc(ctx, (void **)&d_munits, munits.size() * sizeof(MultiUnit)))
             return fail("");
@@ -825,7 +940,9 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
             cudaFuncSetAttribute(b2g_blocking_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)RING_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(b2g_blocking_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)RING_BYTES) != cudaSuccess)
+                                 (int)RING_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(b2g_blocking_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)TILE_RING_BYTES) != cudaSuccess)
             return fail(std::string(who) + ": cudaFuncSetAttribute failed");
         ring_attr = true;
     }
@@ -840,6 +957,13 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
         const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 3);
         b2g_blocking_multi_kernel<<<grid, BLK_THREADS, RING_BYTES, ctx->stream>>>(d_munits, (int64_t)munits.size(),
                                                                                   dst_zero ? 1 : 0);
+        ctx->launches++, st.launches++;
+    }
+    if (!tunits.empty()) {
+        const int64_t want = ((int64_t)tunits.size() * 32 + BLK_THREADS - 1) / BLK_THREADS;
+        const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 2);
+        b2g_blocking_tile_kernel<<<grid, BLK_THREADS, TILE_RING_BYTES, ctx->stream>>>(d_tunits, (int64_t)tunits.size(),
+                                                                                      d_entries, dst_zero ? 1 : 0);
         ctx->launches++, st.launches++;
     }
     cudaEvent_t evs = nullptr;
@@ -889,9 +1013,9 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
             se += (size_t)u.len;
         for (const BlkUnit &u : units)
             re += (size_t)u.len;
-        fprintf(stderr, "[b2g] blocking: multi %zu units | stream %zu units %zu elements %.3f ms | regular %zu units %zu elements, general %zu units, "
+        fprintf(stderr, "[b2g] blocking: tile %zu units | multi %zu units | stream %zu units %zu elements %.3f ms | regular %zu units %zu elements, general %zu units, "
                         "serial %zu entries %.3f ms\n",
-                munits.size(), sunits.size(), se, ms_s, units.size(), re, gunits.size(), serial.size(), ms - ms_s);
+                tunits.size(), munits.size(), sunits.size(), se, ms_s, units.size(), re, gunits.size(), serial.size(), ms - ms_s);
         cudaEventDestroy(evs);
     }
 
