@@ -63,6 +63,32 @@ def test_renormalisation_on_device_matches_reference_executor():
     assert r["rotations"] > 0 and abs(r["e_gpu"] - E_H10) < 1e-6, r
 
 
+def test_blocking_on_device_matches_reference_executor():
+    """--gpu-contract: left_contract / right_contract recorded by the reference's own walker / OperatorFunctions
+    and executed by b2g_tensor_product_execute (resident blocks feeding the rotation list and the H.C plan);
+    --verify re-records every call with the reference's recorder, runs its auto_perform() and compares all
+    blocked operators, and does the same for every rotation list and H.C list."""
+    r = run_driver("b2g_dmrg_su2", "--fcidump", os.path.join(BUILD, "data", "N2.STO3G.FCIDUMP"), "--bond", "250",
+                   "--nsweeps", "8", "--threads", "4", "--noise", "1e-6", "--gpu-contract", "--gpu-rotate", "--verify")
+    assert r["contractions"] > 0 and r["max_contract_rel_err"] < 1e-11, r
+    assert r["rotations"] > 0 and r["max_rotate_rel_err"] < 1e-11, r
+    assert r["max_matvec_rel_err"] < 1e-11 and r["resident_hit_gbytes"] > 0, r
+    assert abs(r["e_gpu"] - E_N2_1AG) < 1e-8, r
+    r = run_driver("b2g_dmrg_sz", "--fcidump", os.path.join(BUILD, "data", "H10.STO6G.R1.8.FCIDUMP"), "--bond",
+                   "300", "--nsweeps", "6", "--threads", "8", "--noise", "1e-6", "--gpu-contract", "--gpu-rotate",
+                   "--verify")
+    assert r["contractions"] > 0 and r["max_contract_rel_err"] < 1e-11 and r["max_rotate_rel_err"] < 1e-11, r
+    assert abs(r["e_gpu"] - E_H10) < 1e-6, r
+
+
+def test_blocking_on_device_zero_fill_route(monkeypatch):
+    """B2G_ZERO_OUTPUTS=1: zero-initialised outputs + add (B2G_DST_ZERO without B2G_DST_COVERED)."""
+    monkeypatch.setenv("B2G_ZERO_OUTPUTS", "1")
+    r = run_driver("b2g_dmrg_su2", "--fcidump", os.path.join(BUILD, "data", "N2.STO3G.FCIDUMP"), "--bond", "120",
+                   "--nsweeps", "4", "--threads", "4", "--noise", "1e-6", "--gpu-contract", "--gpu-rotate", "--verify")
+    assert r["contractions"] > 0 and r["max_contract_rel_err"] < 1e-11 and r["max_rotate_rel_err"] < 1e-11, r
+
+
 def test_two_rank_dmrg_over_parallel_rule_qc_and_nccl(b2g):
     """One process per GPU: the reference's ParallelMPO over ParallelRuleQC, host collectives through
     shared memory, sigma all-reduce over NCCL.  Needs two GPUs (NCCL refuses two ranks on one device)."""
