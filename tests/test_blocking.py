@@ -346,3 +346,27 @@ def test_gpu_covered_outputs_need_no_initialisation(b2g, ctx):
     ref = np.zeros((rows, cols))
     ref[:, 5:15] = 3.0 * src.reshape(rows, 10)
     assert np.array_equal(out.reshape(rows, cols), ref)
+
+
+def test_recorded_blocking_workloads_are_consistent(b2g):
+    """The Cr2 SVP M=4000 blocking lists bench.py / tools/blocking_bench.py replay (structure only):
+    every term is a 1 x 1 site block times an environment block (quantum-chemistry blocking), windows fit
+    their output blocks, operands fit their arenas."""
+    from conftest import ROOT
+    for name, nterms in (("cr2_m4000_s20_call39.b2tp.gz", 66630), ("cr2_m4000_s20_call18.b2tp.gz", 89932)):
+        tp = b2g.load_tpfile(os.path.join(ROOT, "workloads", "cr2_svp_m4000_blocking", name))
+        T = tp.t
+        assert tp.nterms == nterms and not tp.is_right
+        assert (((T["am"] == 1) & (T["an"] == 1)) | ((T["bm"] == 1) & (T["bn"] == 1))).all()
+        rows, cols = tp.window_shapes()
+        assert (cols <= T["cn"]).all() and (rows >= 1).all()
+        assert int((T["am"].astype(np.int64) * T["an"] * T["bm"] * T["bn"]).sum()) == tp.nflop
+        a_off, b_off, c_off, n_in, n_out = tp.offsets()
+        assert (a_off >= 0).all() and (a_off + T["am"].astype(np.int64) * T["an"] <= n_in).all()
+        assert (b_off + T["bm"].astype(np.int64) * T["bn"] <= n_in).all()
+        assert (c_off + (rows - 1) * T["cn"] + cols <= n_out).all()
+        # terms writing the same window have the same shape (identical or disjoint windows only)
+        order = np.argsort(c_off, kind="stable")
+        same = c_off[order][1:] == c_off[order][:-1]
+        assert (rows[order][1:][same] == rows[order][:-1][same]).all()
+        assert (cols[order][1:][same] == cols[order][:-1][same]).all()
