@@ -929,8 +929,7 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
         return fail("" + std::string(who) + ": event creation failed");
     cudaEventRecord(ev0, ctx->stream);
     static const int acc_stages = getenv("B2G_BLK_STAGES") ? atoi(getenv("B2G_BLK_STAGES")) : ACC_STAGES_DEFAULT;
-    static bool ring_attr = false;
-    if (!ring_attr) {
+    if (!ctx->blocking_attr_set) {
         if (cudaFuncSetAttribute(b2g_blocking_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)acc_ring_bytes(3)) != cudaSuccess ||
             cudaFuncSetAttribute(b2g_blocking_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -944,7 +943,7 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
             cudaFuncSetAttribute(b2g_blocking_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)TILE_RING_BYTES) != cudaSuccess)
             return fail(std::string(who) + ": cudaFuncSetAttribute failed");
-        ring_attr = true;
+        ctx->blocking_attr_set = true;
     }
     if (!sunits.empty()) {
         const int64_t want = ((int64_t)sunits.size() * 32 + BLK_THREADS - 1) / BLK_THREADS;

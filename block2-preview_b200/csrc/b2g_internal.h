@@ -62,6 +62,7 @@ struct b2g_context {
     std::vector<B2GResident> resident;
     std::vector<std::pair<uintptr_t, uintptr_t>> vouched; // host byte ranges valid for the NEXT mirror (one shot)
     int64_t resident_hits = 0, resident_hit_bytes = 0;
+    bool blocking_attr_set = false; // dynamic shared memory limits of the blocking kernels raised on this device
     std::vector<std::pair<uintptr_t, uintptr_t>> cover; // full extents of the blocks the next KEEP_RESIDENT call writes
     void *h_up[2] = {nullptr, nullptr};
     cudaEvent_t up_done[2] = {nullptr, nullptr};

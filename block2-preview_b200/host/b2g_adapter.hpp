@@ -309,18 +309,56 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
         };
         b2g_blocking_stats st;
         vector<shared_ptr<SparseMatrix<S, FL>>> temps;
-        shared_ptr<OperatorFunctions<S, FL>> pre = make_shared<OperatorFunctions<S, FL>>(opf->cg);
-        if (gopf != nullptr)
-            gopf->collector->clear(), gopf->collector->active = true;
+        vector<shared_ptr<OperatorFunctions<S, FL>>> pres; // pre-sum recorders (one per recording thread)
         tr.get_time();
-        walk(pre, temps);
-        session->t_contract_record += tr.get_time();
-        if (gopf != nullptr)
+        if (gopf != nullptr) {
+            // term form: the operators are walked by the operator-level threads, as the stock method does
+            // with parallel_for; every thread has its own term vector, pre-sum recorder and temporaries,
+            // and an operator is walked by one thread, so its terms stay in expression order
+            gopf->collector->clear(), gopf->collector->active = true;
+            const int nt = threading->activate_operator();
+            if ((int)gopf->collector->per_thread.size() < nt)
+                gopf->collector->per_thread.resize(nt);
+            vector<shared_ptr<OperatorFunctions<S, FL>>> opfs(nt);
+            vector<vector<shared_ptr<SparseMatrix<S, FL>>>> temps_t(nt);
+            for (int k = 0; k < nt; k++) {
+                opfs[k] = k == 0 ? opf : opf->copy();
+                pres.push_back(make_shared<OperatorFunctions<S, FL>>(opf->cg));
+                pres.back()->seq->mode = SeqTypes::Auto;
+            }
+            std::exception_ptr err = nullptr;
+#pragma omp parallel for schedule(dynamic) num_threads(nt)
+            for (int z = 0; z < (int)todo.size(); z++) {
+                const int tid = threading->get_thread_id();
+                const size_t i = todo[z];
+                try {
+                    shared_ptr<OpElement<S, FL>> cop = dynamic_pointer_cast<OpElement<S, FL>>(names->data[i]);
+                    record_blocking_expr<S>(opfs[tid], exprs->data[i] * ((FL)1.0 / cop->factor), lop, rop,
+                                            c->ops.at(abs_value(names->data[i])), pres[tid], temps_t[tid]);
+                } catch (...) {
+#pragma omp critical
+                    err = std::current_exception();
+                }
+            }
+            threading->activate_normal();
             gopf->collector->active = false;
-        if (pre->seq->batch[1]->gp.size() != 0) {
-            if (run_blocking_list(*pre->seq->batch[1], st) != 0)
-                throw std::runtime_error(std::string("b2g_batch_execute: ") + b2g_last_error());
-            account(st);
+            if (err != nullptr)
+                std::rethrow_exception(err);
+            for (auto &tt : temps_t)
+                temps.insert(temps.end(), tt.begin(), tt.end());
+        } else {
+            pres.push_back(make_shared<OperatorFunctions<S, FL>>(opf->cg));
+            walk(pres[0], temps);
+        }
+        session->t_contract_record += tr.get_time();
+        for (auto &pre : pres) {
+            if (pre->seq->batch[0]->gp.size() != 0)
+                throw std::runtime_error("b2g: blocking list has chained pairs");
+            if (pre->seq->batch[1]->gp.size() != 0) {
+                if (run_blocking_list(*pre->seq->batch[1], st) != 0)
+                    throw std::runtime_error(std::string("b2g_batch_execute: ") + b2g_last_error());
+                account(st);
+            }
         }
         if (gopf != nullptr) {
             vector<b2g_tp_term> &terms = gopf->collector->per_thread[0];
@@ -361,7 +399,9 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
                 throw std::runtime_error(std::string("b2g_batch_execute: ") + b2g_last_error());
             account(st);
         }
-        seq->clear(), pre->seq->clear();
+        seq->clear();
+        for (auto &pre : pres)
+            pre->seq->clear();
         if (session->verify && todo.size() != 0) {
             // the reference's own executor on the list its own recorder makes of the same expressions
             vector<vector<double>> gpu;
