@@ -713,7 +713,12 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
             const BlkEntry &e = dev_entries[first + q];
             transposed_src = transposed_src || (e.alpha != 0.0 && e.sa_j != 1);
         }
-        if (axpy && tile_on && transposed_src && cl[ci].count >= 2 && w.n >= TILE_C && w.m >= 2) {
+        // tile units: several contributions with transposed sources among them, and every 2-D window of
+        // 32..127 columns (too narrow for row units: the tile kernel needs no per-element division and reads
+        // transposed sources along their contiguous direction)
+        static const bool tile_narrow = getenv("B2G_BLK_NOTILE_NARROW") == nullptr;
+        if (axpy && tile_on && w.n >= TILE_C && w.m >= 2 &&
+            ((transposed_src && cl[ci].count >= 2) || (tile_narrow && w.n < ROW_MIN))) {
             for (int64_t i0 = 0; i0 < w.m; i0 += TILE_R)
                 for (int64_t j0 = 0; j0 < w.n; j0 += TILE_C)
                     tunits.push_back(TileUnit{w.dst, (int32_t)i0, (int32_t)j0, w.m, w.n, w.ldc, first, cl[ci].count, 0});
