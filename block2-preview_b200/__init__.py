@@ -74,6 +74,7 @@ class BlockingStats(ctypes.Structure):
 DST_ZERO = 1
 KEEP_RESIDENT = 2
 DST_COVERED = 4
+PLAN_ONLY = 8
 
 
 class TPTerm(ctypes.Structure):
@@ -267,6 +268,26 @@ def _ctx_batch_execute(self, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ld
 
 
 Context.batch_execute = _ctx_batch_execute
+
+
+class _NoContext:
+    """Stand-in for B2G_PLAN_ONLY calls, which need no device."""
+    _h = None
+
+
+def batch_plan(ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, group_size, flags: int = 0) -> BlockingStats:
+    """Host-side regrouping of a blocking list only (B2G_PLAN_ONLY): entries, folded windows, clusters,
+    warp units, serial components and algorithmic bytes, without a GPU."""
+    return _batch_execute(_NoContext, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, group_size,
+                          OPERANDS_HOST, flags | PLAN_ONLY)
+
+
+def tensor_product_plan(terms: np.ndarray, flags: int = 0) -> BlockingStats:
+    terms = np.ascontiguousarray(terms, dtype=TP_DTYPE)
+    st = BlockingStats()
+    _check(lib().b2g_tensor_product_execute(None, len(terms), terms.ctypes.data, OPERANDS_HOST, flags | PLAN_ONLY,
+                                            byref(st)), "b2g_tensor_product_execute")
+    return st
 
 
 def _ctx_tensor_product_execute(self, terms: np.ndarray, operand_space: int = OPERANDS_HOST,

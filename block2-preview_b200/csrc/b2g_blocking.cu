@@ -768,6 +768,12 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
         return 1;
     }
     st.plan_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+    if (flags & B2G_PLAN_ONLY) { // the regrouping alone (host work, no device): counts for tests and tools
+        st.units = (int64_t)(units.size() + gunits.size() + tunits.size());
+        if (stats)
+            *stats = st;
+        return 0;
+    }
 
     // ---- 5. operands
     double *d_in = nullptr, *d_out = nullptr;
@@ -1046,7 +1052,7 @@ extern "C" int b2g_batch_execute(b2g_context *ctx, int64_t group_count, const in
                                  const int32_t *ldb, const double *beta, double *const *c, const int32_t *ldc,
                                  const int32_t *group_size, int operand_space, int flags,
                                  b2g_blocking_stats *stats) {
-    if (!ctx) {
+    if (!ctx && !(flags & B2G_PLAN_ONLY)) {
         b2g_set_error("b2g_batch_execute: null context");
         return 1;
     }
@@ -1059,7 +1065,8 @@ extern "C" int b2g_batch_execute(b2g_context *ctx, int64_t group_count, const in
         b2g_set_error("b2g_batch_execute: unknown operand space");
         return 1;
     }
-    B2G_CUDA(cudaSetDevice(ctx->device));
+    if (!(flags & B2G_PLAN_ONLY))
+        B2G_CUDA(cudaSetDevice(ctx->device));
     b2g_blocking_stats st;
     memset(&st, 0, sizeof(st));
     auto t_begin = std::chrono::steady_clock::now();
@@ -1126,7 +1133,7 @@ extern "C" int b2g_batch_execute(b2g_context *ctx, int64_t group_count, const in
 // as whole 2-D windows instead of one GEMM per row.
 extern "C" int b2g_tensor_product_execute(b2g_context *ctx, int64_t count, const b2g_tp_term *terms,
                                           int operand_space, int flags, b2g_blocking_stats *stats) {
-    if (!ctx || (count > 0 && !terms)) {
+    if ((!ctx && !(flags & B2G_PLAN_ONLY)) || (count > 0 && !terms)) {
         b2g_set_error("b2g_tensor_product_execute: null argument");
         return 1;
     }
@@ -1134,7 +1141,8 @@ extern "C" int b2g_tensor_product_execute(b2g_context *ctx, int64_t count, const
         b2g_set_error("b2g_tensor_product_execute: unknown operand space");
         return 1;
     }
-    B2G_CUDA(cudaSetDevice(ctx->device));
+    if (!(flags & B2G_PLAN_ONLY))
+        B2G_CUDA(cudaSetDevice(ctx->device));
     b2g_blocking_stats st;
     memset(&st, 0, sizeof(st));
     auto t_begin = std::chrono::steady_clock::now();

@@ -149,6 +149,8 @@ typedef struct b2g_blocking_stats {
 #define B2G_DST_COVERED 4 /* with B2G_DST_ZERO, host operand space: the output blocks are exactly the extents
                               announced by b2g_resident_cover and need NOT be initialised on the host - the
                               device result (zero where no entry writes) overwrites them */
+#define B2G_PLAN_ONLY 8 /* regroup the list (clusters, units, serial components, algorithmic bytes) and return the
+                           stats without touching a device; ctx may be NULL */
 #define B2G_DST_ZERO 1 /* caller guarantees every output block is zero on entry (freshly allocate()d operators):
                           outputs are not uploaded, the device result is added into the host blocks */
 

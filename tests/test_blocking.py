@@ -370,3 +370,51 @@ def test_recorded_blocking_workloads_are_consistent(b2g):
         same = c_off[order][1:] == c_off[order][:-1]
         assert (rows[order][1:][same] == rows[order][:-1][same]).all()
         assert (cols[order][1:][same] == cols[order][:-1][same]).all()
+
+
+# ----------------------------------------------------------------------------- host-side regrouping (no GPU)
+
+
+@pytest.mark.parametrize("name", BLK_FILES)
+def test_plan_regroups_reference_lists_without_serial_components(b2g, name):
+    """B2G_PLAN_ONLY: the regrouping by output window runs on the host.  On the lists the reference's own
+    recorder makes, windows are identical or disjoint (no serial components), the per-row GEMM groups fold
+    into fewer 2-D windows, and the bookkeeping totals are the reference's (nflop = sum m*n*k*group size)."""
+    bf = b2g.load_blkfile(os.path.join(GOLDEN, name))
+    inp, out = bf.inputs.copy(), bf.c_in.copy()
+    a, b, c = bf.pointers(inp.ctypes.data, out.ctypes.data)
+    ta, tb, m, n, k, alpha, lda, ldb, beta, ldc, gs = bf.group_args()
+    st = b2g.batch_plan(ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, gs)
+    assert st.entries == bf.nentries and st.nflop_mnk == bf.nflop_mnk
+    assert st.serial_entries == 0 and 0 < st.clusters <= st.merged < st.entries
+    assert st.units >= st.clusters and st.launches == 0
+    # every output element is written once, every source element of every entry read once
+    G = bf.g
+    a_elems = int((G["m"].astype(np.int64) * G["k"] * G["gp"]).sum())
+    b_elems = int((G["k"].astype(np.int64) * G["n"] * G["gp"]).sum())
+    assert 8 * a_elems < st.bytes_in <= 8 * (a_elems + b_elems)  # one scalar per folded window, not per row
+    assert st.bytes_out <= 8 * out.size
+    again = b2g.batch_plan(ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, gs)
+    assert (again.clusters, again.merged, again.units) == (st.clusters, st.merged, st.units)
+    assert np.array_equal(out, bf.c_in)  # nothing executed
+
+
+@pytest.mark.parametrize("seed,overlap", [(0, False), (1, False), (2, True), (3, True)])
+def test_plan_detects_overlapping_windows(b2g, seed, overlap):
+    rng = np.random.default_rng(seed)
+    G, A, B, C, src, scal, out = synthetic_list(rng, general=True, overlap=overlap)
+    st = b2g.batch_plan(*resolve(G, A, B, C, src, scal, out))
+    assert st.entries == len(A)
+    assert (st.serial_entries > 0) == overlap
+
+
+def test_plan_of_term_lists(b2g):
+    rng = np.random.default_rng(5)
+    terms, src, osize = synthetic_terms(rng, kron=True)
+    out = np.zeros(osize)
+    st = b2g.tensor_product_plan(pack_terms(b2g, terms, src, out))
+    assert st.entries == len(terms) and st.serial_entries == 0 and st.clusters < st.merged
+    # a Kronecker term becomes one window per element of op(A); scalar terms stay one window each
+    expect = sum(t["am"] * t["an"] if (t["am"] * t["an"] > 1 and t["bm"] * t["bn"] > 1) else 1 for t in terms)
+    assert st.merged == expect
+    assert st.nflop_mnk == sum(t["am"] * t["an"] * t["bm"] * t["bn"] for t in terms)
