@@ -7,7 +7,10 @@ Little endian: 8-byte magic b"B2BLK\\0\\0\\1"; u64[8] (ngroups, nentries, n_in, 
 is_right, call, reserved); i32[ngroups] x 9 (ta tb m n k lda ldb ldc gp); f64[ngroups] x 2
 (alpha beta); i64[nentries] x 6 (a_arena a_off b_arena b_off c_arena c_off); u64[n_in] input arena
 sizes; u64[n_out] output arena sizes; f64 input arenas; f64 output arenas on entry; f64 output
-arenas after the reference's own BatchGEMMSeq::auto_perform.
+arenas after the reference's own BatchGEMMSeq::auto_perform.  Optional second section, the same
+call in term form (b2g_tp_term, include/b2g.h): 8-byte magic b"B2TERMS\1"; u64 nterms;
+i32[nterms] x 7 (am an bm bn cn conja conjb); f64[nterms] scale; i64[nterms] x 6 (a_arena a_off
+b_arena b_off c_arena c_off) over the same arenas.
 """
 from __future__ import annotations
 
@@ -33,6 +36,16 @@ class BlkFile:
     inputs: np.ndarray | None = None        # concatenated input arenas
     c_in: np.ndarray | None = None          # concatenated output arenas on entry
     c_ref: np.ndarray | None = None         # ... after the reference executor
+    terms: dict | None = None               # term form of the same call (per-term arrays), if recorded
+
+    def term_offsets(self):
+        """Element offsets (a, b into the concatenated inputs; c into the concatenated outputs) of the terms."""
+        si = np.zeros(len(self.in_sizes) + 1, dtype=np.int64)
+        np.cumsum(self.in_sizes, out=si[1:])
+        so = np.zeros(len(self.out_sizes) + 1, dtype=np.int64)
+        np.cumsum(self.out_sizes, out=so[1:])
+        T = self.terms
+        return si[T["a_arena"]] + T["a_off"], si[T["b_arena"]] + T["b_off"], so[T["c_arena"]] + T["c_off"]
 
     def pointers(self, in_base: int, out_base: int):
         """Entry pointers (a, b, c) as integer addresses for arenas laid out back to back at
@@ -87,5 +100,16 @@ def load_blkfile(path: str) -> BlkFile:
     bf.c_in = take(np.float64, tout).copy()
     bf.c_ref = take(np.float64, tout).copy()
     if pos != raw.size:
-        raise ValueError(f"{path}: {raw.size - pos} trailing bytes")
+        if bytes(raw[pos:pos + 8]) != b"B2TERMS\1":
+            raise ValueError(f"{path}: {raw.size - pos} trailing bytes")
+        pos += 8
+        nt = int(take(np.uint64, 1)[0])
+        bf.terms = {}
+        for name in ("am", "an", "bm", "bn", "cn", "conja", "conjb"):
+            bf.terms[name] = take(np.int32, nt).copy()
+        bf.terms["scale"] = take(np.float64, nt).copy()
+        for name in ("a_arena", "a_off", "b_arena", "b_off", "c_arena", "c_off"):
+            bf.terms[name] = take(np.int64, nt).copy()
+        if pos != raw.size:
+            raise ValueError(f"{path}: {raw.size - pos} trailing bytes")
     return bf

@@ -434,6 +434,17 @@ template <typename S, typename FL> struct BlkDumpTensorFunctions : TensorFunctio
         auto &seq = opf->seq;
         const SeqTypes saved = seq->mode;
         seq->mode = SeqTypes::Auto; // record only
+        // the same walk once more in the term form of the host binding (b2g_tp_term, one descriptor per
+        // connection-info entry instead of one GEMM per row): stored behind the list as a second section
+        auto coll = make_shared<b2g_host::TermCollector>();
+        shared_ptr<OperatorFunctions<S, FL>> gopf = make_shared<b2g_host::GPUOperatorFunctions<S>>(opf->cg, coll);
+        vector<shared_ptr<SparseMatrix<S, FL>>> temps, fresh_ops;
+        bool has_temp = false;
+        std::function<void(const shared_ptr<SparseMatrix<S, FL>> &, const shared_ptr<SparseMatrixInfo<S>> &)> at =
+            [&has_temp](const shared_ptr<SparseMatrix<S, FL>> &m, const shared_ptr<SparseMatrixInfo<S>> &info) {
+                has_temp = true;
+                m->allocate(info);
+            };
         for (size_t i = 0; i < exprs->data.size(); i++) {
             shared_ptr<OpElement<S, FL>> cop = dynamic_pointer_cast<OpElement<S, FL>>(names->data[i]);
             shared_ptr<OpExpr<S>> op = abs_value(names->data[i]);
@@ -442,10 +453,15 @@ template <typename S, typename FL> struct BlkDumpTensorFunctions : TensorFunctio
                 continue;
             c->ops.at(op)->alloc = make_shared<VectorAllocator<FL>>();
             c->ops.at(op)->allocate(c->ops.at(op)->info);
+            fresh_ops.push_back(c->ops.at(op));
             if (right)
                 this->tensor_product(expr, b->ops, a->ops, c->ops.at(op));
             else
                 this->tensor_product(expr, a->ops, b->ops, c->ops.at(op));
+            coll->active = true;
+            b2g_host::record_blocking_expr<S>(gopf, expr, right ? b->ops : a->ops, right ? a->ops : b->ops, c->ops.at(op),
+                                              nullptr, temps, &at);
+            coll->active = false;
         }
         auto &bt = *seq->batch[1];
         if (seq->batch[0]->gp.size() != 0) {
@@ -464,6 +480,15 @@ template <typename S, typename FL> struct BlkDumpTensorFunctions : TensorFunctio
                 iin.push_back(BlkInterval{(uintptr_t)bt.b[z], (uintptr_t)bt.b[z] + 8 * eb});
                 iout.push_back(BlkInterval{(uintptr_t)bt.c[z], (uintptr_t)bt.c[z] + 8 * ec});
             }
+        // whole blocks: the operand blocks of the term form and the freshly allocated output operators
+        // (a strided window of the term form spans the rows of its neighbours)
+        for (const b2g_tp_term &t : coll->per_thread[0]) {
+            iin.push_back(BlkInterval{(uintptr_t)t.a, (uintptr_t)t.a + 8 * (size_t)t.am * t.an});
+            iin.push_back(BlkInterval{(uintptr_t)t.b, (uintptr_t)t.b + 8 * (size_t)t.bm * t.bn});
+        }
+        for (auto &m : fresh_ops)
+            if (m->total_memory != 0)
+                iout.push_back(BlkInterval{(uintptr_t)m->data, (uintptr_t)m->data + 8 * (size_t)m->total_memory});
         vector<BlkInterval> ain = blk_merge(iin), aout = blk_merge(iout);
         vector<int32_t> i32[9];
         vector<double> f64[2];
@@ -525,7 +550,47 @@ template <typename S, typename FL> struct BlkDumpTensorFunctions : TensorFunctio
         seq->mode = saved;
         for (size_t i = 0; i < aout.size(); i++)
             fwrite((const void *)aout[i].lo, 8, szout[i], f);
+        // term section: magic "B2TERMS\1"; u64 nterms; i32[nterms] x 7 am an bm bn cn conja conjb; f64[nterms]
+        // scale; i64[nterms] x 6 a_arena a_off b_arena b_off c_arena c_off (same arenas as the list)
+        size_t nterms = 0;
+        if (!has_temp) {
+            const vector<b2g_tp_term> &terms = coll->per_thread[0];
+            nterms = terms.size();
+            auto inside = [](const vector<BlkInterval> &ar, uintptr_t lo, size_t n) {
+                int64_t ia, off;
+                blk_locate(ar, lo, ia, off);
+                return ar[ia].lo <= lo && lo + 8 * n <= ar[ia].hi;
+            };
+            vector<int32_t> t32[7];
+            vector<double> tsc(nterms);
+            vector<int64_t> t64[6];
+            for (auto &v : t32) v.resize(nterms);
+            for (auto &v : t64) v.resize(nterms);
+            for (size_t z = 0; z < nterms; z++) {
+                const b2g_tp_term &t = terms[z];
+                const size_t wr_ = (size_t)(t.conja ? t.an : t.am) * (t.conjb ? t.bn : t.bm),
+                             wc_ = (size_t)(t.conja ? t.am : t.an) * (t.conjb ? t.bm : t.bn);
+                if (!inside(ain, (uintptr_t)t.a, (size_t)t.am * t.an) || !inside(ain, (uintptr_t)t.b, (size_t)t.bm * t.bn) ||
+                    !inside(aout, (uintptr_t)t.c, (wr_ - 1) * t.cn + wc_)) {
+                    fprintf(stderr, "blkdump: term %zu outside the arenas of the list\n", z);
+                    exit(1);
+                }
+                t32[0][z] = t.am, t32[1][z] = t.an, t32[2][z] = t.bm, t32[3][z] = t.bn, t32[4][z] = t.cn;
+                t32[5][z] = t.conja, t32[6][z] = t.conjb, tsc[z] = t.scale;
+                blk_locate(ain, (uintptr_t)t.a, t64[0][z], t64[1][z]);
+                blk_locate(ain, (uintptr_t)t.b, t64[2][z], t64[3][z]);
+                blk_locate(aout, (uintptr_t)t.c, t64[4][z], t64[5][z]);
+            }
+            const char tmagic[8] = {'B', '2', 'T', 'E', 'R', 'M', 'S', 1};
+            fwrite(tmagic, 1, 8, f);
+            vector<uint64_t> th(1, nterms);
+            wr(f, th);
+            for (auto &v : t32) wr(f, v);
+            wr(f, tsc);
+            for (auto &v : t64) wr(f, v);
+        }
         fclose(f);
+        printf("BLKDUMP terms=%zu\n", nterms);
         printf("BLKDUMP %s call=%d %s groups=%zu entries=%zu in_arenas=%zu (%zu doubles) out_arenas=%zu (%zu doubles) "
                "nflop_mnk=%zu\n",
                args->out.c_str(), args->blk_call, right ? "right_contract" : "left_contract", ng, ne, ain.size(), tin,

@@ -22,7 +22,8 @@ wait
 # blocking lists: the N-th left_contract / right_contract call of a short DMRG run recorded in
 # SeqTypes::Auto by the reference's own recorder, operand data, and the blocked operators the
 # reference's own BatchGEMMSeq::auto_perform produced from it (ref_harness.cpp `blkdump`).
-# Calls whose expressions need a SumProd temporary are refused by the harness (exit 3).
+# Calls whose expressions need a SumProd temporary are refused by the harness (exit 3).  Each file also
+# carries the same call in the term form of the host binding (b2g_tp_term), recorded in the same run.
 ./b2ref_su2 blkdump --fcidump data/N2.STO3G.FCIDUMP --bond 30 --nsweeps 2 --threads 2 --blk-call 2 --out $G/n2_su2_m30_blk2_right.b2blk
 ./b2ref_su2 blkdump --fcidump data/N2.STO3G.FCIDUMP --bond 30 --nsweeps 2 --threads 2 --blk-call 14 --out $G/n2_su2_m30_blk14_left.b2blk
 ./b2ref_sz  blkdump --fcidump data/H10.STO6G.R1.8.FCIDUMP --sym sz --bond 40 --nsweeps 2 --threads 2 --blk-call 16 --out $G/h10_sz_m40_blk16_left.b2blk

@@ -418,3 +418,48 @@ def test_plan_of_term_lists(b2g):
     expect = sum(t["am"] * t["an"] if (t["am"] * t["an"] > 1 and t["bm"] * t["bn"] > 1) else 1 for t in terms)
     assert st.merged == expect
     assert st.nflop_mnk == sum(t["am"] * t["an"] * t["bm"] * t["bn"] for t in terms)
+
+
+# ----------------------------------------------------------------------------- term form of the fixtures
+
+
+def fixture_terms(bf):
+    T = bf.terms
+    a, b, c = bf.term_offsets()
+    return [dict(a=int(a[i]), b=int(b[i]), c=int(c[i]), am=int(T["am"][i]), an=int(T["an"][i]), bm=int(T["bm"][i]),
+                 bn=int(T["bn"][i]), cn=int(T["cn"][i]), conja=int(T["conja"][i]), conjb=int(T["conjb"][i]),
+                 scale=float(T["scale"][i])) for i in range(len(a))]
+
+
+@pytest.mark.parametrize("name", BLK_FILES)
+def test_term_oracle_matches_reference_blocking(b2g, name):
+    """The same left_contract / right_contract call in the term form the host binding records (one b2g_tp_term
+    per connection-info entry): the numpy restatement of GMatrixFunctions::tensor_product reproduces the
+    blocked operators of the reference's own executor bit for bit (pinned)."""
+    bf = b2g.load_blkfile(os.path.join(GOLDEN, name))
+    assert bf.terms is not None and 0 < len(bf.terms["am"]) < bf.nentries
+    terms = fixture_terms(bf)
+    out = bf.c_in.copy()
+    sd.tensor_product_terms(terms, lambda off, n: bf.inputs[off:off + n],
+                            lambda off, r, c, p: np.lib.stride_tricks.as_strided(out[off:], (r, c), (8 * p, 8)))
+    assert np.array_equal(out, bf.c_ref)
+    # and the regrouping of the term form sees the same windows as that of the list form
+    inp = bf.inputs.copy()
+    st_t = b2g.tensor_product_plan(pack_terms(b2g, terms, inp, out))
+    a, b, c = bf.pointers(inp.ctypes.data, out.ctypes.data)
+    ta, tb, m, n, k, alpha, lda, ldb, beta, ldc, gs = bf.group_args()
+    st_l = b2g.batch_plan(ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, gs)
+    assert st_t.entries == len(terms) and st_t.serial_entries == 0 and st_l.serial_entries == 0
+    assert st_t.nflop_mnk == st_l.nflop_mnk == bf.nflop_mnk
+    assert st_t.bytes_out == st_l.bytes_out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", BLK_FILES)
+def test_gpu_term_form_matches_reference_blocking(b2g, ctx, name):
+    bf = b2g.load_blkfile(os.path.join(GOLDEN, name))
+    inp, out = bf.inputs.copy(), bf.c_in.copy()
+    st = ctx.tensor_product_execute(pack_terms(b2g, fixture_terms(bf), inp, out), b2g.OPERANDS_HOST, b2g.DST_ZERO)
+    assert rel(out, bf.c_ref) < TOL
+    assert st.entries == len(bf.terms["am"]) and st.serial_entries == 0
+    assert np.array_equal(inp, bf.inputs)
