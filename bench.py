@@ -53,31 +53,129 @@ def reference_replay(max_gflop: float, reps: int, warmup: int, threads: int) -> 
     return json.loads(line)
 
 
-def cpu_sample_gflop(threads: int) -> float:
-    # ~40 GFLOP of pair work per host thread: 10-30 s of CPU time at the 2-10 GFLOP/s per core
-    # the reference reaches on these shapes, for warmup + reps = 3 passes
-    return 40.0 * threads
+def sample_text(r: dict, threads: int) -> str:
+    whole = r["pairs"] == r["pairs_total"]
+    return (f"{'the full list: ' if whole else ''}{r['pairs']} of {r['pairs_total']} GEMM pairs ({r['flops'] / 1e9:.0f} GFLOP"
+            f"{'' if whole else ', fixed-seed subset'}) through the reference BatchGEMMSeq::operator() (Tasked), "
+            f"OpenBLAS 1 thread x {threads} OpenMP threads, {r['seconds_per_matvec']:.2f} s/pass, "
+            f"{r['reps']} timed + {r['warmup']} warm-up passes, synthetic operator values (fixed seed)")
 
 
 def run_reference(args) -> None:
+    """The reference's own CPU executor on the SAME workload: the whole 44 415-pair list (about 3.5 s per pass on
+    16 threads), every step one full matvec."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = host_threads()
-    r = reference_replay(cpu_sample_gflop(threads), max(args.steps, 1), max(args.warmup, 1), threads)
-    sample = (f"{r['pairs']} of {r['pairs_total']} GEMM pairs ({r['flops'] / 1e9:.0f} GFLOP, seeded random subset) "
-              f"through the reference BatchGEMMSeq::operator() (Tasked), OpenBLAS 1 thread x {threads} OpenMP threads")
+    r = reference_replay(0.0, max(args.steps, 1), max(args.warmup, 1), threads)
+    sample = sample_text(r, threads)
+    full = load_workload_header()
     line = {
         "impl": "reference", "metric": METRIC, "value": r["tflops"], "unit": "TFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds_per_matvec"] * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAME, "sample": sample},
+        "config": workload_config(full),
         "cpu_baseline": {"value": r["tflops"], "unit": "TFLOP/s", "cores": threads, "kind": "reference",
                          "sample": sample},
         "e2e": {"value": r["tflops"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def load_workload_header():
+    import b2gpkg
+    return b2gpkg.load().load_seqfile(WORKLOAD)
+
+
+def workload_config(full) -> dict:
+    """The part of `config` both arms share (same workload, same units of work)."""
+    return {"workload": WORKLOAD_NAME, "pairs": full.npairs, "wavefunction_doubles": full.csize,
+            "operator_bytes": 8 * full.operand_doubles, "flop_per_step": full.flops}
+
+
+def sigma_parity(np, torch, sf, full, ops, c_host, v_dev, world, dist, k=8, budget_flop=3.0e11, seed=7):
+    """Checker, outside every timed region: sigma of K sampled blocks recomputed in plain numpy fp64 from the
+    operands as they sit in HBM - for every pair that writes into the block,
+    sigma_window += alpha1 * op(A1) . (alpha0 * c_window . op(B0)) (block2 batch_gemm.hpp:1634-1643) - and compared
+    with what the CUDA path produced.  A block = a connected set of overlapping sigma windows of the SERIAL list
+    (a sector block and its sub-windows), so the choice is the same on every rank; at N > 1 every rank
+    recomputes its own pairs and the per-rank results are summed before the comparison with the all-reduced sigma."""
+    def comps(P):
+        lo = P["c1_off"].astype(np.int64)
+        hi = lo + (P["m1"].astype(np.int64) - 1) * P["ldc1"] + P["n1"]
+        order = np.argsort(lo, kind="stable")
+        out, cur_lo, cur_hi = [], None, None
+        for i in order:
+            if P["m1"][i] == 0 or P["n1"][i] == 0:
+                continue
+            if cur_lo is None or lo[i] >= cur_hi:
+                if cur_lo is not None:
+                    out.append((cur_lo, cur_hi))
+                cur_lo, cur_hi = int(lo[i]), int(hi[i])
+            else:
+                cur_hi = max(cur_hi, int(hi[i]))
+        if cur_lo is not None:
+            out.append((cur_lo, cur_hi))
+        return out, lo, hi
+    regions, flo, fhi = comps(full.p)
+    fl = full.pair_flops()
+    cost = [float(fl[(flo >= a) & (fhi <= b)].sum()) for a, b in regions]
+    # the heaviest block always (70 % of the FLOPs of the M=4000 list sit in one block), the others by a seeded draw
+    rng = np.random.default_rng(seed)
+    heavy = int(np.argmax(cost))
+    chosen, spent, drawn = [heavy], cost[heavy], 0.0
+    for j in rng.permutation(len(regions)):
+        if len(chosen) < k and j != heavy and cost[j] > 0 and drawn + cost[j] <= budget_flop:
+            chosen.append(int(j))
+            spent, drawn = spent + cost[j], drawn + cost[j]
+    P = sf.p
+    _, lo, hi = comps(P)
+    b0o, a1o = sf.operand_offsets()
+    view = np.lib.stride_tricks.as_strided
+    cache = {}
+
+    def block(off, rows, cols, ld):
+        ext = (rows - 1) * ld + cols
+        key = (int(off), int(ext))
+        if key not in cache:
+            cache[key] = ops[key[0]:key[0] + key[1]].cpu().numpy()
+        return view(cache[key], (rows, cols), (8 * ld, 8))
+    worst, checked, npairs, skipped = 0.0, 0, 0, 0
+    for j in chosen:
+        a, b = regions[j]
+        ref = np.zeros(b - a)
+        idx = np.nonzero((lo < b) & (hi > a))[0]
+        for i in idx:
+            if lo[i] < a or hi[i] > b:
+                skipped += 1
+                continue
+            m0, n0, k0, m1 = int(P["m0"][i]), int(P["n0"][i]), int(P["k0"][i]), int(P["m1"][i])
+            if m0 == 0 or n0 == 0 or m1 == 0:
+                continue
+            assert P["ta0"][i] == 0 and P["tb1"][i] == 0
+            A = view(c_host[int(P["a0_off"][i]):], (m0, k0), (8 * int(P["lda0"][i]), 8))
+            B = block(b0o[i], n0, k0, int(P["ldb0"][i])).T if P["tb0"][i] else block(b0o[i], k0, n0, int(P["ldb0"][i]))
+            W = P["alpha0"][i] * (A @ B)
+            A1 = block(a1o[i], m0, m1, int(P["lda1"][i])).T if P["ta1"][i] else block(a1o[i], m1, m0, int(P["lda1"][i]))
+            win = view(ref[int(lo[i] - a):], (m1, n0), (8 * int(P["ldc1"][i]), 8))
+            win += P["alpha1"][i] * (A1 @ W)
+            npairs += 1
+        cache.clear()
+        if world > 1:
+            t = torch.from_numpy(ref).to(v_dev.device)
+            dist.all_reduce(t)
+            ref = t.cpu().numpy()
+        got = v_dev[a:b].cpu().numpy()
+        den = float(np.linalg.norm(ref))
+        err = float(np.linalg.norm(got - ref)) / den if den > 0 else float(np.linalg.norm(got))
+        worst, checked = max(worst, err), checked + 1
+    return {"blocks_checked": checked, "blocks_total": len(regions), "pairs_recomputed_this_rank": npairs,
+            "pairs_outside_serial_blocks": skipped, "gflop_recomputed": spent * 1e-9, "max_rel_err": worst,
+            "tolerance": 1e-11, "ok": bool(checked >= min(k, len(regions)) and worst <= 1e-11 and skipped == 0),
+            "how": "numpy fp64 recomputation of sampled sigma blocks from the device operands; "
+                   "seeded choice identical on every rank; summed over ranks before comparing with the all-reduced sigma"}
 
 
 class ClockSampler(threading.Thread):
@@ -170,14 +268,20 @@ def run_b200(args) -> None:
         ctx.comm_init(world, rank, uid[0])
 
     full = b2g.load_seqfile(WORKLOAD)
-    # N > 1: the pair list rank r records under the reference's own ParallelRuleQC / ParallelMPO split
-    # (workloads/README.md); falls back to splitting the serial list by left-operator index
-    rank_file = os.path.join(ROOT, "workloads", "cr2_svp_m4000_site20_ranks",
-                             f"cr2_m4000_s20_P{world}_r{rank}.b2seq.gz")
+    # N > 1: the pair list rank r records for the same site when the reference itself parallelises the MPO over
+    # ParallelRuleQC (workloads/README.md).  Default: ClassicParallelMPO (parallel_mpo.hpp:32-148) - every term of the
+    # serial list on exactly one rank (the per-rank lists partition the 44 415 pairs).  B2G_BENCH_SCHEME=new: ParallelMPO
+    # (NewScheme), where the terms of Partial operators are repeated on every rank (1.72x the serial FLOPs at P = 8).
+    scheme = os.environ.get("B2G_BENCH_SCHEME", "classic")
+    rank_dir, rank_tag = (("cr2_svp_m4000_site20_ranks_classic", "classic_") if scheme == "classic"
+                          else ("cr2_svp_m4000_site20_ranks", ""))
+    rank_file = os.path.join(ROOT, "workloads", rank_dir, f"cr2_m4000_s20_{rank_tag}P{world}_r{rank}.b2seq.gz")
     sharding = "serial list"
     if world > 1 and os.path.exists(rank_file):
         sf = b2g.load_seqfile(rank_file)
-        sharding = "per-rank lists recorded by the reference under ParallelRuleQC (ParallelMPO, NewScheme)"
+        sharding = ("per-rank lists recorded by the reference under ParallelRuleQC, "
+                    + ("ClassicParallelMPO (each term on one rank; Partial operators reduced to their owner after blocking)"
+                       if scheme == "classic" else "ParallelMPO NewScheme (Partial-operator terms repeated on every rank)"))
     elif world > 1:
         sf = full.shard(rank, world)
         sharding = "serial list split by left-operator index (emulated ParallelRuleQC ownership)"
@@ -273,8 +377,13 @@ def run_b200(args) -> None:
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = total_flops / float(te.item()) * 1e-12
-    # cross-check of the two paths (same pair list, same c)
+    # cross-check of the two public entry points on the same list and c: host-buffer call (all-reduces inside
+    # when a communicator exists) against one device-resident step (matvec + all-reduce)
+    step()
+    barrier()
     chk = float((torch.from_numpy(v_host).to(dev) - v).norm() / v.norm())
+    # oracle check of sigma at the headline size (outside the timed regions)
+    parity = sigma_parity(np, torch, sf, full, ops, c_host, v, world, dist)
 
     if rank == 0:
         st = plan.stats
@@ -299,14 +408,14 @@ def run_b200(args) -> None:
             "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME, "pairs": full.npairs, "wavefunction_doubles": full.csize,
-                       "operator_bytes": 8 * full.operand_doubles, "flop_per_step": full.flops,
-                       "l2": "inputs (operator blocks, %.1f GB per rank) larger than L2" % (8e-9 * sf.operand_doubles),
-                       "parallelism": "%d rank(s), %s, NCCL all-reduce of sigma" % (world, sharding),
-                       "executed_flop_all_ranks": executed_flops},
+            "config": dict(workload_config(full),
+                           l2="inputs (operator blocks, %.1f GB per rank) larger than L2" % (8e-9 * sf.operand_doubles),
+                           parallelism="%d rank(s), %s, NCCL all-reduce of sigma" % (world, sharding),
+                           executed_flop_all_ranks=executed_flops),
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": 8 * sf.csize,
                     "d2h_bytes_per_step": 8 * sf.vsize, "path_check_rel": chk},
+            "parity": parity,
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": dom["name"], "achieved": dom["tflops"], "peak": peak,
                          "unit": "TFLOP/s", "frac": dom["tflops"] / peak if peak else None, "traffic": traffic,
@@ -327,11 +436,9 @@ def run_b200(args) -> None:
         if world == 1 and not args.no_cpu:
             try:
                 threads = host_threads()
-                r = reference_replay(cpu_sample_gflop(threads), 2, 1, threads)
-                line["cpu_baseline"] = {
-                    "value": r["tflops"], "unit": "TFLOP/s", "cores": threads, "kind": "reference",
-                    "sample": f"{r['pairs']} of {r['pairs_total']} pairs ({r['flops'] / 1e9:.0f} GFLOP, seeded random "
-                              f"subset), reference BatchGEMMSeq::operator() Tasked, {r['seconds_per_matvec']:.2f} s/pass"}
+                r = reference_replay(0.0, 2, 1, threads)
+                line["cpu_baseline"] = {"value": r["tflops"], "unit": "TFLOP/s", "cores": threads, "kind": "reference",
+                                        "sample": sample_text(r, threads)}
             except Exception as exc:  # the baseline is reported, never needed by the GPU path
                 line["cpu_baseline"] = {"value": None, "unit": "TFLOP/s", "cores": host_threads(), "kind": "reference",
                                         "sample": f"unavailable: {exc}"}

@@ -38,8 +38,8 @@ EXPORTS = [
     "b2g_last_error", "b2g_device_count", "b2g_context_create", "b2g_context_destroy",
     "b2g_context_launches", "b2g_context_stream", "b2g_context_synchronize",
     "b2g_plan_create", "b2g_plan_destroy", "b2g_plan_get_stats", "b2g_seq_matvec",
-    "b2g_seq_matvec_dev", "b2g_plan_profile", "b2g_pairs_execute", "b2g_dgemm_batch", "b2g_batch_execute", "b2g_tensor_product_execute", "b2g_resident_vouch", "b2g_resident_cover", "b2g_resident_drop",
-    "b2g_resident_stats", "b2g_davidson", "b2g_comm_unique_id",
+    "b2g_seq_matvec_dev", "b2g_plan_profile", "b2g_pairs_execute", "b2g_dgemm_batch", "b2g_batch_execute", "b2g_tensor_product_execute", "b2g_resident_map", "b2g_resident_stats", "b2g_download",
+    "b2g_upload_blocks", "b2g_host_register", "b2g_host_unregister", "b2g_mem_info", "b2g_debug_upload_slices", "b2g_davidson", "b2g_comm_unique_id",
     "b2g_comm_init", "b2g_comm_destroy", "b2g_allreduce_sum", "b2g_malloc", "b2g_free",
     "b2g_memcpy_h2d", "b2g_memcpy_d2h", "b2g_memset_zero",
 ]
@@ -72,8 +72,6 @@ class BlockingStats(ctypes.Structure):
 
 
 DST_ZERO = 1
-KEEP_RESIDENT = 2
-DST_COVERED = 4
 PLAN_ONLY = 8
 
 
@@ -124,10 +122,14 @@ def lib() -> ctypes.CDLL:
         L.b2g_dgemm_batch.argtypes = [c_void_p, c_int64] + [c_void_p] * 13
         L.b2g_batch_execute.argtypes = [c_void_p, c_int64] + [c_void_p] * 14 + [c_int, c_int, POINTER(BlockingStats)]
         L.b2g_tensor_product_execute.argtypes = [c_void_p, c_int64, c_void_p, c_int, c_int, POINTER(BlockingStats)]
-        L.b2g_resident_vouch.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
-        L.b2g_resident_cover.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
-        L.b2g_resident_drop.argtypes = [c_void_p]
+        L.b2g_resident_map.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
         L.b2g_resident_stats.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int64)]
+        L.b2g_download.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
+        L.b2g_upload_blocks.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
+        L.b2g_host_register.argtypes = [c_void_p, c_void_p, c_size_t]
+        L.b2g_host_unregister.argtypes = [c_void_p, c_void_p]
+        L.b2g_mem_info.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int64)]
+        L.b2g_debug_upload_slices.argtypes = [c_int64, c_int, c_void_p, c_void_p]
         L.b2g_davidson.argtypes = [c_void_p, c_void_p, c_void_p, c_double, c_double, c_int, c_int, c_int, c_int,
                                    POINTER(c_double), POINTER(c_int)]
         L.b2g_comm_unique_id.argtypes = [c_void_p]
@@ -305,33 +307,79 @@ def _ctx_tensor_product_execute(self, terms: np.ndarray, operand_space: int = OP
 Context.tensor_product_execute = _ctx_tensor_product_execute
 
 
-def _ctx_resident_vouch(self, host_ptrs, doubles) -> None:
-    """State that these host blocks are unchanged since the KEEP_RESIDENT call that produced them:
-    the next call that mirrors operands takes them from HBM instead of the host (one shot)."""
-    hp, nd = _ptrs(host_ptrs), np.ascontiguousarray(doubles, dtype=np.int64)
-    _check(lib().b2g_resident_vouch(self._h, len(hp), hp.ctypes.data, nd.ctypes.data), "b2g_resident_vouch")
-
-
-def _ctx_resident_cover(self, host_ptrs, doubles) -> None:
-    """Full extents of the zero-initialised blocks the next KEEP_RESIDENT | DST_ZERO call writes (one shot)."""
-    hp, nd = _ptrs(host_ptrs), np.ascontiguousarray(doubles, dtype=np.int64)
-    _check(lib().b2g_resident_cover(self._h, len(hp), hp.ctypes.data, nd.ctypes.data), "b2g_resident_cover")
-
-
-def _ctx_resident_drop(self) -> None:
-    _check(lib().b2g_resident_drop(self._h), "b2g_resident_drop")
+def _ctx_resident_map(self, host_ptrs, doubles, dev_ptrs) -> None:
+    """Device-resident operands: host ranges whose content lives at the given device addresses.  Host-pointer
+    entry points read such inputs in place and write such outputs in place (not copied back) until the table
+    is replaced; an empty table clears it."""
+    hp, nd, dp = _ptrs(host_ptrs), np.ascontiguousarray(doubles, dtype=np.int64), _ptrs(dev_ptrs)
+    assert len(hp) == len(nd) == len(dp)
+    _check(lib().b2g_resident_map(self._h, len(hp), hp.ctypes.data, nd.ctypes.data, dp.ctypes.data),
+           "b2g_resident_map")
 
 
 def _ctx_resident_stats(self):
-    held, hit = c_int64(), c_int64()
-    _check(lib().b2g_resident_stats(self._h, byref(held), byref(hit)), "b2g_resident_stats")
-    return held.value, hit.value
+    """(host->device bytes avoided by resident inputs, bytes mirrored from the host) so far."""
+    hit, mir = c_int64(), c_int64()
+    _check(lib().b2g_resident_stats(self._h, byref(hit), byref(mir)), "b2g_resident_stats")
+    return hit.value, mir.value
 
 
-Context.resident_vouch = _ctx_resident_vouch
-Context.resident_cover = _ctx_resident_cover
-Context.resident_drop = _ctx_resident_drop
+def _ctx_malloc(self, nbytes: int) -> int:
+    p = c_void_p()
+    _check(lib().b2g_malloc(self._h, nbytes, byref(p)), "b2g_malloc")
+    return int(p.value)
+
+
+def _ctx_free(self, dev: int) -> None:
+    _check(lib().b2g_free(self._h, c_void_p(dev)), "b2g_free")
+
+
+def _ctx_memset_zero(self, dev: int, nbytes: int) -> None:
+    _check(lib().b2g_memset_zero(self._h, c_void_p(dev), nbytes), "b2g_memset_zero")
+
+
+def _ctx_download(self, host_ptrs, dev_ptrs, doubles) -> None:
+    hp, dp, nd = _ptrs(host_ptrs), _ptrs(dev_ptrs), np.ascontiguousarray(doubles, dtype=np.int64)
+    _check(lib().b2g_download(self._h, len(hp), hp.ctypes.data, dp.ctypes.data, nd.ctypes.data), "b2g_download")
+
+
+def _ctx_upload_blocks(self, dev_ptrs, host_ptrs, doubles) -> None:
+    hp, dp, nd = _ptrs(host_ptrs), _ptrs(dev_ptrs), np.ascontiguousarray(doubles, dtype=np.int64)
+    _check(lib().b2g_upload_blocks(self._h, len(hp), dp.ctypes.data, hp.ctypes.data, nd.ctypes.data),
+           "b2g_upload_blocks")
+
+
+def _ctx_host_register(self, arr: np.ndarray) -> None:
+    _check(lib().b2g_host_register(self._h, c_void_p(arr.ctypes.data), arr.nbytes), "b2g_host_register")
+
+
+def _ctx_host_unregister(self, arr: np.ndarray) -> None:
+    _check(lib().b2g_host_unregister(self._h, c_void_p(arr.ctypes.data)), "b2g_host_unregister")
+
+
+def _ctx_mem_info(self):
+    f, t = c_int64(), c_int64()
+    _check(lib().b2g_mem_info(self._h, byref(f), byref(t)), "b2g_mem_info")
+    return f.value, t.value
+
+
+Context.resident_map = _ctx_resident_map
 Context.resident_stats = _ctx_resident_stats
+Context.malloc = _ctx_malloc
+Context.free = _ctx_free
+Context.memset_zero = _ctx_memset_zero
+Context.download = _ctx_download
+Context.upload_blocks = _ctx_upload_blocks
+Context.host_register = _ctx_host_register
+Context.host_unregister = _ctx_host_unregister
+Context.mem_info = _ctx_mem_info
+
+
+def upload_slices(length: int, nt: int):
+    """Test hook: the byte ranges the staging threads of the pageable upload path copy for one chunk."""
+    lo, hi = np.zeros(nt, dtype=np.int64), np.zeros(nt, dtype=np.int64)
+    _check(lib().b2g_debug_upload_slices(length, nt, lo.ctypes.data, hi.ctypes.data), "b2g_debug_upload_slices")
+    return lo, hi
 
 
 class SeqPlan:

@@ -570,13 +570,6 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
                            b2g_blocking_stats &st, b2g_blocking_stats *stats,
                            std::chrono::steady_clock::time_point t_begin, const char *who) {
     const bool dst_zero = (flags & B2G_DST_ZERO) != 0;
-    const bool keep_resident = (flags & B2G_KEEP_RESIDENT) != 0 && operand_space == B2G_OPERANDS_HOST;
-    const bool covered = (flags & B2G_DST_COVERED) != 0 && dst_zero && operand_space == B2G_OPERANDS_HOST;
-    if ((flags & B2G_DST_COVERED) && (!covered || ctx->cover.empty())) {
-        b2g_set_error(std::string(who) + ": B2G_DST_COVERED needs B2G_DST_ZERO, host operands and b2g_resident_cover extents");
-        return 1;
-    }
-    size_t out_total_doubles = 0;
     st.merged = (int64_t)he.size();
     if (he.empty()) {
         if (stats)
@@ -596,14 +589,30 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
             if (ext)
                 v.push_back(B2GRange{(uintptr_t)ptr, (uintptr_t)ptr + ext * sizeof(double), 0});
         };
-        for (const HostEntry &h : he) {
-            add(out_rg, h.dst, window_extent(h.m, h.n, h.ldc));
+        // device-resident blocks (b2g_resident_map): sources are read in place, windows of resident
+        // output blocks are written in place and not copied back.  Those operands switch to device
+        // addresses here (unified addressing: a device address never lies inside a host range, which is
+        // what the translation of the remaining operands below relies on).
+        const bool have_map = ctx && !ctx->rmap.empty();
+        for (size_t z = 0; z < he.size(); z++) {
+            HostEntry &h = he[z];
+            const size_t e_out = window_extent(h.m, h.n, h.ldc);
+            if (double *d = have_map ? b2g_map_lookup(ctx, h.dst, e_out * 8) : nullptr)
+                h.dst = d;
+            else
+                add(out_rg, h.dst, e_out);
             if (h.e.alpha == 0.0 || h.e.k == 0)
                 continue;
-            add(in_rg, h.e.a,
-                (size_t)(h.m - 1) * h.e.sa_i + (size_t)(h.n - 1) * h.e.sa_j + (size_t)(h.e.k - 1) * h.e.sa_k + 1);
-            add(in_rg, h.e.b,
-                (size_t)(h.m - 1) * h.e.sb_i + (size_t)(h.n - 1) * h.e.sb_j + (size_t)(h.e.k - 1) * h.e.sb_k + 1);
+            const size_t e_a = (size_t)(h.m - 1) * h.e.sa_i + (size_t)(h.n - 1) * h.e.sa_j + (size_t)(h.e.k - 1) * h.e.sa_k + 1;
+            const size_t e_b = (size_t)(h.m - 1) * h.e.sb_i + (size_t)(h.n - 1) * h.e.sb_j + (size_t)(h.e.k - 1) * h.e.sb_k + 1;
+            if (double *d = have_map ? b2g_map_lookup(ctx, h.e.a, e_a * 8) : nullptr)
+                h.e.a = d, ctx->resident_hit_bytes += (int64_t)e_a * 8;
+            else
+                add(in_rg, h.e.a, e_a);
+            if (double *d = have_map ? b2g_map_lookup(ctx, h.e.b, e_b * 8) : nullptr)
+                h.e.b = d;
+            else
+                add(in_rg, h.e.b, e_b);
         }
     }
     // dense windows (whole rows of their block, or a single row) are addressed as one contiguous vector
@@ -803,12 +812,7 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
     auto t_up = std::chrono::steady_clock::now();
     if (operand_space == B2G_OPERANDS_HOST) {
         size_t in_total = 0, out_total = 0;
-        if ((keep_resident || covered) && dst_zero) // whole output blocks, as announced by b2g_resident_cover
-            for (const auto &c : ctx->cover)
-                out_rg.push_back(B2GRange{c.first, c.second, 0});
-        ctx->cover.clear();
         b2g_merge_ranges(in_rg, in_total), b2g_merge_ranges(out_rg, out_total);
-        out_total_doubles = out_total;
         for (const B2GRange &o : out_rg) // an output block must not also be an input of the same list
             if (!in_rg.empty()) {
                 const B2GRange &r = b2g_locate_range(in_rg, o.lo);
@@ -817,28 +821,45 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
                     return fail("" + std::string(who) + ": an output block aliases an input block of the same list");
             }
         if ((in_total && b2g_dmalloc(ctx, (void **)&d_in, in_total * sizeof(double))) ||
-            b2g_dmalloc(ctx, (void **)&d_out, out_total * sizeof(double)))
+            (out_total && b2g_dmalloc(ctx, (void **)&d_out, out_total * sizeof(double))))
             return fail("");
         if (in_total && b2g_mirror_ranges(ctx, in_rg, d_in))
             return fail("");
-        if (dst_zero) {
-            if (cudaMemsetAsync(d_out, 0, out_total * sizeof(double), ctx->stream) != cudaSuccess)
-                return fail("" + std::string(who) + ": memset failed");
-        } else if (b2g_mirror_ranges(ctx, out_rg, d_out))
-            return fail("");
+        if (out_total) {
+            if (dst_zero) {
+                if (cudaMemsetAsync(d_out, 0, out_total * sizeof(double), ctx->stream) != cudaSuccess)
+                    return fail("" + std::string(who) + ": memset failed");
+            } else if (b2g_mirror_ranges(ctx, out_rg, d_out))
+                return fail("");
+        }
+        // host addresses -> mirror; operands that already are device addresses (resident blocks) stay
+        auto xin = [&](const double *ptr) -> const double * {
+            if (in_rg.empty())
+                return ptr;
+            const B2GRange &r = b2g_locate_range(in_rg, (uintptr_t)ptr);
+            return r.lo <= (uintptr_t)ptr && (uintptr_t)ptr < r.hi ? d_in + r.dev_off + ((uintptr_t)ptr - r.lo) / sizeof(double)
+                                                                  : ptr;
+        };
+        auto xout = [&](double *ptr) -> double * {
+            if (out_rg.empty())
+                return ptr;
+            const B2GRange &r = b2g_locate_range(out_rg, (uintptr_t)ptr);
+            return r.lo <= (uintptr_t)ptr && (uintptr_t)ptr < r.hi ? d_out + r.dev_off + ((uintptr_t)ptr - r.lo) / sizeof(double)
+                                                                  : ptr;
+        };
         for (BlkEntry &e : dev_entries)
             if (e.alpha != 0.0 && e.k > 0)
-                e.a = b2g_translate(in_rg, d_in, e.a), e.b = b2g_translate(in_rg, d_in, e.b);
+                e.a = xin(e.a), e.b = xin(e.b);
         for (BlkUnit &u : units)
-            u.dst = b2g_translate(out_rg, d_out, u.dst);
+            u.dst = xout(u.dst);
         for (BlkUnit &u : gunits)
-            u.dst = b2g_translate(out_rg, d_out, u.dst);
+            u.dst = xout(u.dst);
         for (TileUnit &u : tunits)
-            u.dst = b2g_translate(out_rg, d_out, u.dst);
+            u.dst = xout(u.dst);
         for (BlkSerial &s : serial) {
             if (s.e.alpha != 0.0 && s.e.k > 0)
-                s.e.a = b2g_translate(in_rg, d_in, s.e.a), s.e.b = b2g_translate(in_rg, d_in, s.e.b);
-            s.dst = b2g_translate(out_rg, d_out, s.dst);
+                s.e.a = xin(s.e.a), s.e.b = xin(s.e.b);
+            s.dst = xout(s.dst);
         }
     }
     // single-contribution linear units become self-contained streaming units
@@ -1029,16 +1050,12 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
         cudaEventDestroy(evs);
     }
 
-    // ---- 7. results
-    if (operand_space == B2G_OPERANDS_HOST) {
+    // ---- 7. results (windows of resident output blocks were written in place and stay on the device)
+    if (operand_space == B2G_OPERANDS_HOST && !out_rg.empty()) {
         auto t_dn = std::chrono::steady_clock::now();
-        if (b2g_download_ranges(ctx, out_rg, d_out, dst_zero && !covered))
+        if (b2g_download_ranges(ctx, out_rg, d_out, dst_zero))
             return fail("");
         st.download_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_dn).count();
-        if (keep_resident) { // the host copy now equals the device copy
-            b2g_resident_keep(ctx, d_out, out_rg, out_total_doubles);
-            d_out = nullptr;
-        }
     }
     cleanup();
     if (stats)

@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <thread>
 
@@ -161,6 +162,20 @@ struct MirrorWriter {
     }
 };
 
+// staging slice per host thread: 4 KB aligned, nt * slice >= len
+static inline size_t upload_slice(size_t len, int nt) {
+    return ((len + (size_t)nt - 1) / (size_t)nt + 4095) & ~(size_t)4095;
+}
+// test hook (no device): the [lo, hi) byte ranges the nt staging threads of b2g_upload copy for a chunk of len bytes
+extern "C" int b2g_debug_upload_slices(int64_t len, int nt, int64_t *lo, int64_t *hi) {
+    if (len < 0 || nt < 1 || !lo || !hi)
+        return 1;
+    const size_t slice = upload_slice((size_t)len, nt);
+    for (int t = 0; t < nt; t++)
+        lo[t] = (int64_t)std::min((size_t)len, slice * t), hi[t] = (int64_t)std::min((size_t)len, slice * (t + 1));
+    return 0;
+}
+
 int b2g_upload(b2g_context *ctx, void *dst, const void *src, size_t bytes) {
     constexpr size_t CH = B2G_UP_CHUNK;
     if (ensure_upload_buffers(ctx))
@@ -172,7 +187,7 @@ int b2g_upload(b2g_context *ctx, void *dst, const void *src, size_t bytes) {
         const size_t len = std::min(CH, bytes - off);
         B2G_CUDA(cudaEventSynchronize(ctx->up_done[buf])); // previous DMA out of this buffer finished
         const int nt = ctx->up_threads;
-        const size_t slice = (len / nt + 4095) & ~(size_t)4095;
+        const size_t slice = upload_slice(len, nt);
         std::vector<std::thread> th;
         for (int t = 1; t < nt; t++) {
             const size_t lo = std::min(len, slice * t), hi = std::min(len, slice * (t + 1));
@@ -194,7 +209,6 @@ extern "C" int b2g_context_destroy(b2g_context *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->nccl_comm)
         b2g_comm_destroy(ctx);
-    b2g_resident_drop(ctx);
     if (ctx->h_stage)
         cudaFreeHost(ctx->h_stage);
     for (int i = 0; i < 2; i++) {
@@ -229,14 +243,44 @@ extern "C" int b2g_context_synchronize(b2g_context *ctx) {
     return 0;
 }
 
+// stream-ordered pool allocations (ordered on the context stream like every other piece of work)
 extern "C" int b2g_malloc(b2g_context *ctx, size_t bytes, void **dev) {
+    if (!ctx || !dev) {
+        b2g_set_error("b2g_malloc: null argument");
+        return 1;
+    }
     B2G_CUDA(cudaSetDevice(ctx->device));
-    B2G_CUDA(cudaMalloc(dev, bytes));
-    return 0;
+    return b2g_dmalloc(ctx, dev, bytes);
 }
 extern "C" int b2g_free(b2g_context *ctx, void *dev) {
+    if (!ctx) {
+        b2g_set_error("b2g_free: null context");
+        return 1;
+    }
     B2G_CUDA(cudaSetDevice(ctx->device));
-    B2G_CUDA(cudaFree(dev));
+    b2g_dfree(ctx, dev);
+    return 0;
+}
+extern "C" int b2g_mem_info(b2g_context *ctx, int64_t *free_bytes, int64_t *total_bytes) {
+    if (!ctx) {
+        b2g_set_error("b2g_mem_info: null context");
+        return 1;
+    }
+    B2G_CUDA(cudaSetDevice(ctx->device));
+    size_t f = 0, t = 0;
+    B2G_CUDA(cudaMemGetInfo(&f, &t));
+    // memory parked in the stream-ordered pool is reusable by b2g_malloc
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+        uint64_t reserved = 0, used = 0;
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+        f += (size_t)(reserved - used);
+    }
+    if (free_bytes)
+        *free_bytes = (int64_t)f;
+    if (total_bytes)
+        *total_bytes = (int64_t)t;
     return 0;
 }
 extern "C" int b2g_memcpy_h2d(b2g_context *ctx, void *dev, const void *host, size_t bytes) {
@@ -288,6 +332,8 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
     }
     B2G_CUDA(cudaSetDevice(ctx->device));
     const int64_t n = b0->count;
+    const char *force = getenv("B2G_FORCE_GENERIC");
+    const bool force_generic = force && force[0] == '1';
     b2g_plan *p = new b2g_plan();
     p->ctx = ctx, p->npairs = n, p->csize = csize, p->vsize = vsize, p->max_work = max_work;
     std::vector<B2GPair> &hp = p->h_pairs;
@@ -295,6 +341,7 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
     std::vector<Range> rg;
     rg.reserve((size_t)2 * n);
     int64_t nflop = 0;
+    size_t resident_doubles = 0; // per-pair extents read in place from resident blocks (with repeats)
     for (int64_t i = 0; i < n; i++) {
         if (!valid_trans(b0->ta[i]) || !valid_trans(b0->tb[i]) || !valid_trans(b1->ta[i]) ||
             !valid_trans(b1->tb[i])) {
@@ -311,6 +358,14 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
             b0->ldc[i] != n0 || b1->ldb[i] != n0 || b0->beta[i] != 0.0 || b1->beta[i] != 1.0) {
             b2g_set_error("b2g_plan_create: pair " + std::to_string(i) +
                           " is not a chained W = A0*B0, C1 += A1*W pair");
+            delete p;
+            return 1;
+        }
+        // rotate / three_rotate never record a transposed wavefunction operand (batch_gemm.hpp:893-1022)
+        // and the tile engine has no A-transposed phase 1: refuse instead of computing the wrong product
+        if (ta0 && !force_generic) {
+            b2g_set_error("b2g_plan_create: pair " + std::to_string(i) +
+                          ": transposed wavefunction operand (ta of batch[0]) is not part of the H.C replay list");
             delete p;
             return 1;
         }
@@ -341,11 +396,19 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
         const size_t eb0 = extent(tb0 ? n0 : k0, tb0 ? k0 : n0, q.ldb0);
         const size_t ea1 = extent(ta1 ? k1 : m1, ta1 ? m1 : k1, q.lda1);
         const uintptr_t pb = (uintptr_t)q.b0, pa = (uintptr_t)q.a1;
-        if (eb0)
+        // device-resident blocks (b2g_resident_map) are read in place; the rest is mirrored below
+        if (operand_space == B2G_OPERANDS_HOST && eb0)
+            if (double *d = b2g_map_lookup(ctx, q.b0, eb0 * sizeof(double)))
+                q.b0 = d, q.pad |= 1u, resident_doubles += eb0;
+        if (operand_space == B2G_OPERANDS_HOST && ea1)
+            if (double *d = b2g_map_lookup(ctx, q.a1, ea1 * sizeof(double)))
+                q.a1 = d, q.pad |= 2u, resident_doubles += ea1;
+        if (eb0 && !(q.pad & 1u))
             rg.push_back(Range{pb, pb + eb0 * sizeof(double), 0});
-        if (ea1)
+        if (ea1 && !(q.pad & 2u))
             rg.push_back(Range{pa, pa + ea1 * sizeof(double), 0});
     }
+    ctx->resident_hit_bytes += (int64_t)(resident_doubles * sizeof(double));
     const bool verbose = getenv("B2G_VERBOSE") != nullptr;
     auto tstart = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) {
@@ -383,7 +446,7 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
     if (operand_space == B2G_OPERANDS_HOST && total > 0) {
         if (b2g_dmalloc(ctx, (void **)&p->d_operands, total * sizeof(double)) != 0) {
             b2g_set_error("b2g_plan_create: cudaMalloc of " + std::to_string(total * 8) + " operand bytes failed");
-            delete p;
+            b2g_plan_destroy(p);
             return 1;
         }
         {
@@ -391,8 +454,7 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
             for (size_t i = 0; i < ar.size(); i++)
                 brg[i] = B2GRange{ar[i].lo, ar[i].hi, ar[i].dev_off};
             if (b2g_mirror_ranges(ctx, brg, p->d_operands)) {
-                b2g_dfree(ctx, p->d_operands);
-                delete p;
+                b2g_plan_destroy(p);
                 return 1;
             }
         }
@@ -408,12 +470,18 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
             return ar[lo];
         };
         for (B2GPair &q : hp) {
-            const Range &rb = locate((uintptr_t)q.b0);
-            q.b0 = p->d_operands + rb.dev_off + ((uintptr_t)q.b0 - rb.lo) / sizeof(double);
-            const Range &ra = locate((uintptr_t)q.a1);
-            q.a1 = p->d_operands + ra.dev_off + ((uintptr_t)q.a1 - ra.lo) / sizeof(double);
+            if (!(q.pad & 1u)) {
+                const Range &rb = locate((uintptr_t)q.b0);
+                q.b0 = p->d_operands + rb.dev_off + ((uintptr_t)q.b0 - rb.lo) / sizeof(double);
+            }
+            if (!(q.pad & 2u)) {
+                const Range &ra = locate((uintptr_t)q.a1);
+                q.a1 = p->d_operands + ra.dev_off + ((uintptr_t)q.a1 - ra.lo) / sizeof(double);
+            }
         }
     }
+    for (B2GPair &q : hp)
+        q.pad = 0;
     lap("mirror issue");
     // order: pairs writing the same sigma window become neighbours (locality of the accumulation)
     std::stable_sort(hp.begin(), hp.end(), [](const B2GPair &x, const B2GPair &y) {
@@ -422,13 +490,20 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
         return x.a0_off < y.a0_off;
     });
     if (n > 0) {
-        if (b2g_dmalloc(ctx, (void **)&p->d_pairs, (size_t)n * sizeof(B2GPair)))
+        if (b2g_dmalloc(ctx, (void **)&p->d_pairs, (size_t)n * sizeof(B2GPair)) ||
+            cudaMemcpyAsync(p->d_pairs, hp.data(), (size_t)n * sizeof(B2GPair), cudaMemcpyHostToDevice,
+                            ctx->stream) != cudaSuccess) {
+            b2g_set_error("b2g_plan_create: pair list upload failed");
+            b2g_plan_destroy(p);
             return 1;
-        B2G_CUDA(cudaMemcpyAsync(p->d_pairs, hp.data(), (size_t)n * sizeof(B2GPair), cudaMemcpyHostToDevice,
-                                 ctx->stream));
+        }
     }
     lap("sort pairs");
-    B2G_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        b2g_set_error("b2g_plan_create: operand mirror failed");
+        b2g_plan_destroy(p);
+        return 1;
+    }
     lap("mirror sync");
     p->stats.upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     p->n_generic = n;
@@ -436,8 +511,7 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
     p->stats.launches = n > 0 ? 1 : 0;
     // default route: two-phase DMMA tile engine; B2G_FORCE_GENERIC=1 keeps the one-CTA-per-pair
     // kernel (the correctness anchor the tiled path is tested against)
-    const char *force = getenv("B2G_FORCE_GENERIC");
-    if (!(force && force[0] == '1') && n > 0) {
+    if (!force_generic && n > 0) {
         if (b2g_tiled_build(p)) {
             b2g_plan_destroy(p);
             return 1;
@@ -493,6 +567,22 @@ extern "C" int b2g_plan_profile(b2g_plan *p, const double *c_dev, double *v_dev,
     return b2g_tiled_launch(p, c_dev, v_dev, scale, out, capacity, count);
 }
 
+// fn(lo, hi) over [0, n) cut into at most nt contiguous chunks, one host thread each (the caller runs chunk 0)
+void b2g_parallel_chunks(size_t n, int nt, const std::function<void(size_t, size_t)> &fn) {
+    nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(nt, 1), n / ((size_t)1 << 15)));
+    const size_t slice = (n + (size_t)nt - 1) / (size_t)nt;
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) {
+        const size_t lo = std::min(n, slice * t), hi = std::min(n, slice * (t + 1));
+        if (hi > lo)
+            th.emplace_back(fn, lo, hi);
+    }
+    if (n)
+        fn(0, std::min(n, slice));
+    for (auto &x : th)
+        x.join();
+}
+
 static int ensure_staging(b2g_context *ctx, size_t csize, size_t vsize) {
     const size_t need = std::max(csize, vsize);
     if (ctx->h_stage_doubles < need) {
@@ -526,7 +616,11 @@ extern "C" int b2g_seq_matvec(b2g_plan *p, const double *c_host, double *v_host,
     B2G_CUDA(cudaSetDevice(ctx->device));
     if (ensure_staging(ctx, (size_t)p->csize, (size_t)p->vsize))
         return 1;
-    memcpy(ctx->h_stage, c_host, (size_t)p->csize * sizeof(double));
+    // pageable c -> pinned staging and sigma += staging, both cut over the upload threads (19 MB each at
+    // M = 4000: 8 ms of an 88 ms step on one host thread)
+    b2g_parallel_chunks((size_t)p->csize, ctx->up_threads, [&](size_t lo, size_t hi) {
+        memcpy(ctx->h_stage + lo, c_host + lo, (hi - lo) * sizeof(double));
+    });
     B2G_CUDA(cudaMemcpyAsync(ctx->d_c, ctx->h_stage, (size_t)p->csize * sizeof(double), cudaMemcpyHostToDevice,
                              ctx->stream));
     B2G_CUDA(cudaMemsetAsync(ctx->d_v, 0, (size_t)p->vsize * sizeof(double), ctx->stream));
@@ -537,8 +631,11 @@ extern "C" int b2g_seq_matvec(b2g_plan *p, const double *c_host, double *v_host,
     B2G_CUDA(cudaMemcpyAsync(ctx->h_stage, ctx->d_v, (size_t)p->vsize * sizeof(double), cudaMemcpyDeviceToHost,
                              ctx->stream));
     B2G_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (int64_t i = 0; i < p->vsize; i++)
-        v_host[i] += ctx->h_stage[i];
+    const double *hs = ctx->h_stage;
+    b2g_parallel_chunks((size_t)p->vsize, ctx->up_threads, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++)
+            v_host[i] += hs[i];
+    });
     return 0;
 }
 
@@ -596,10 +693,26 @@ extern "C" int b2g_pairs_execute(b2g_context *ctx, const b2g_batch *b0, const b2
             if (ext)
                 v.push_back(Range{(uintptr_t)ptr, (uintptr_t)ptr + ext * sizeof(double), 0});
         };
-        add(in_rg, b0->a[i], extent(m0, k0, q.lda0));
-        add(in_rg, q.b0, extent(tb0 ? n0 : k0, tb0 ? k0 : n0, q.ldb0));
-        add(in_rg, q.a1, extent(ta1 ? k1 : m1, ta1 ? m1 : k1, q.lda1));
-        add(out_rg, b1->c[i], extent(m1, n1, q.ldc1));
+        // device-resident blocks (b2g_resident_map): inputs are read in place, outputs written in place and
+        // not copied back; q.pad remembers which operands already are device addresses
+        const size_t e_a0 = extent(m0, k0, q.lda0), e_b0 = extent(tb0 ? n0 : k0, tb0 ? k0 : n0, q.ldb0),
+                     e_a1 = extent(ta1 ? k1 : m1, ta1 ? m1 : k1, q.lda1), e_c1 = extent(m1, n1, q.ldc1);
+        if (double *d = e_a0 ? b2g_map_lookup(ctx, b0->a[i], e_a0 * 8) : nullptr)
+            q.a0_off = (int64_t)(uintptr_t)d, q.pad |= 4u, ctx->resident_hit_bytes += (int64_t)e_a0 * 8;
+        else
+            add(in_rg, b0->a[i], e_a0);
+        if (double *d = e_b0 ? b2g_map_lookup(ctx, q.b0, e_b0 * 8) : nullptr)
+            q.b0 = d, q.pad |= 1u;
+        else
+            add(in_rg, q.b0, e_b0);
+        if (double *d = e_a1 ? b2g_map_lookup(ctx, q.a1, e_a1 * 8) : nullptr)
+            q.a1 = d, q.pad |= 2u;
+        else
+            add(in_rg, q.a1, e_a1);
+        if (double *d = e_c1 ? b2g_map_lookup(ctx, b1->c[i], e_c1 * 8) : nullptr)
+            q.c1_off = (int64_t)(uintptr_t)d, q.pad |= 8u;
+        else
+            add(out_rg, b1->c[i], e_c1);
     }
     auto merge = [](std::vector<Range> &rg, size_t &total) {
         std::sort(rg.begin(), rg.end(), [](const Range &x, const Range &y) { return x.lo < y.lo; });
@@ -632,15 +745,17 @@ extern "C" int b2g_pairs_execute(b2g_context *ctx, const b2g_batch *b0, const b2
         return ar[lo];
     };
     // an output block must not also be an input of the same list
-    for (const Range &o : out_rg) {
-        const Range &r = locate(in_rg, o.lo);
-        const Range *nx = (&r + 1 < in_rg.data() + in_rg.size()) ? &r + 1 : nullptr;
-        if ((r.lo <= o.lo && o.lo < r.hi) || (o.lo <= r.lo && r.lo < o.hi) || (nx && nx->lo < o.hi && nx->lo >= o.lo)) {
-            b2g_set_error("b2g_pairs_execute: an output block aliases an input block");
-            delete p;
-            return 1;
+    if (!in_rg.empty())
+        for (const Range &o : out_rg) {
+            const Range &r = locate(in_rg, o.lo);
+            const Range *nx = (&r + 1 < in_rg.data() + in_rg.size()) ? &r + 1 : nullptr;
+            if ((r.lo <= o.lo && o.lo < r.hi) || (o.lo <= r.lo && r.lo < o.hi) ||
+                (nx && nx->lo < o.hi && nx->lo >= o.lo)) {
+                b2g_set_error("b2g_pairs_execute: an output block aliases an input block");
+                delete p;
+                return 1;
+            }
         }
-    }
     double *d_in = nullptr, *d_out = nullptr;
     int rc = 0;
     auto fail = [&](const std::string &msg) {
@@ -655,24 +770,39 @@ extern "C" int b2g_pairs_execute(b2g_context *ctx, const b2g_batch *b0, const b2
         return fail("");
     if (ensure_upload_buffers(ctx))
         return fail("");
-    if (cudaMemsetAsync(d_out, 0, out_total * sizeof(double), ctx->stream) != cudaSuccess)
+    if (out_total && cudaMemsetAsync(d_out, 0, out_total * sizeof(double), ctx->stream) != cudaSuccess)
         return fail("b2g_pairs_execute: memset failed");
-    {
+    if (!in_rg.empty()) {
         std::vector<B2GRange> brg(in_rg.size());
         for (size_t i = 0; i < in_rg.size(); i++)
             brg[i] = B2GRange{in_rg[i].lo, in_rg[i].hi, in_rg[i].dev_off};
         if (b2g_mirror_ranges(ctx, brg, d_in))
             return fail("");
     }
+    // wavefunction-side operands are addressed as offsets from d_in / d_out (negative or beyond the
+    // allocation for resident blocks: plain device address arithmetic)
     for (B2GPair &q : hp) {
-        const Range &ra0 = locate(in_rg, (uintptr_t)q.a0_off);
-        q.a0_off = (int64_t)(ra0.dev_off + ((uintptr_t)q.a0_off - ra0.lo) / sizeof(double));
-        const Range &rb = locate(in_rg, (uintptr_t)q.b0);
-        q.b0 = d_in + rb.dev_off + ((uintptr_t)q.b0 - rb.lo) / sizeof(double);
-        const Range &ra = locate(in_rg, (uintptr_t)q.a1);
-        q.a1 = d_in + ra.dev_off + ((uintptr_t)q.a1 - ra.lo) / sizeof(double);
-        const Range &rc1 = locate(out_rg, (uintptr_t)q.c1_off);
-        q.c1_off = (int64_t)(rc1.dev_off + ((uintptr_t)q.c1_off - rc1.lo) / sizeof(double));
+        if (q.pad & 4u)
+            q.a0_off = (int64_t)((double *)(uintptr_t)q.a0_off - d_in);
+        else {
+            const Range &ra0 = locate(in_rg, (uintptr_t)q.a0_off);
+            q.a0_off = (int64_t)(ra0.dev_off + ((uintptr_t)q.a0_off - ra0.lo) / sizeof(double));
+        }
+        if (!(q.pad & 1u)) {
+            const Range &rb = locate(in_rg, (uintptr_t)q.b0);
+            q.b0 = d_in + rb.dev_off + ((uintptr_t)q.b0 - rb.lo) / sizeof(double);
+        }
+        if (!(q.pad & 2u)) {
+            const Range &ra = locate(in_rg, (uintptr_t)q.a1);
+            q.a1 = d_in + ra.dev_off + ((uintptr_t)q.a1 - ra.lo) / sizeof(double);
+        }
+        if (q.pad & 8u)
+            q.c1_off = (int64_t)((double *)(uintptr_t)q.c1_off - d_out);
+        else {
+            const Range &rc1 = locate(out_rg, (uintptr_t)q.c1_off);
+            q.c1_off = (int64_t)(rc1.dev_off + ((uintptr_t)q.c1_off - rc1.lo) / sizeof(double));
+        }
+        q.pad = 0;
     }
     p->csize = (int64_t)in_total, p->vsize = (int64_t)out_total;
     const double t_up = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -756,28 +886,23 @@ const B2GRange &b2g_locate_range(const std::vector<B2GRange> &ar, uintptr_t ptr)
     return ar[lo];
 }
 
-// resident copy of the host range [lo, hi), if the caller vouched for it
-static const double *resident_lookup(b2g_context *ctx, uintptr_t lo, uintptr_t hi) {
-    if (ctx->vouched.empty() || ctx->resident.empty())
+// ------------------------------------------------------------------ device-resident operands
+
+double *b2g_map_lookup(b2g_context *ctx, const void *ptr, size_t bytes) {
+    const std::vector<B2GMapEntry> &m = ctx->rmap;
+    if (m.empty())
         return nullptr;
-    // vouched: sorted, disjoint
-    size_t a = 0, b = ctx->vouched.size();
+    const uintptr_t lo = (uintptr_t)ptr, hi = lo + bytes;
+    size_t a = 0, b = m.size();
     while (b - a > 1) {
         const size_t mid = (a + b) / 2;
-        if (ctx->vouched[mid].first <= lo)
+        if (m[mid].lo <= lo)
             a = mid;
         else
             b = mid;
     }
-    if (!(ctx->vouched[a].first <= lo && hi <= ctx->vouched[a].second))
-        return nullptr;
-    for (const B2GResident &R : ctx->resident) {
-        if (R.ranges.empty() || lo < R.ranges.front().lo || hi > R.ranges.back().hi)
-            continue;
-        const B2GRange &r = b2g_locate_range(R.ranges, lo);
-        if (r.lo <= lo && hi <= r.hi)
-            return R.dev + r.dev_off + (lo - r.lo) / sizeof(double);
-    }
+    if (m[a].lo <= lo && hi <= m[a].hi)
+        return m[a].dev + (lo - m[a].lo) / sizeof(double);
     return nullptr;
 }
 
@@ -788,121 +913,133 @@ int b2g_mirror_ranges(b2g_context *ctx, const std::vector<B2GRange> &rg, double 
     B2G_CUDA(cudaEventSynchronize(ctx->up_done[0]));
     B2G_CUDA(cudaEventSynchronize(ctx->up_done[1]));
     for (const B2GRange &r : rg) {
-        if (const double *res = resident_lookup(ctx, r.lo, r.hi)) {
-            // a staging slice is shipped as ONE contiguous device span: close it so that it cannot
-            // cover (and overwrite) the span this range is copied into device to device
-            if (mw.flush())
-                return 1;
-            static const bool check = getenv("B2G_RESIDENT_CHECK") != nullptr;
-            if (check) { // debugging aid: the vouched host block must equal its resident copy
-                std::vector<double> tmp((r.hi - r.lo) / sizeof(double));
-                B2G_CUDA(cudaMemcpyAsync(tmp.data(), res, r.hi - r.lo, cudaMemcpyDeviceToHost, ctx->stream));
-                B2G_CUDA(cudaStreamSynchronize(ctx->stream));
-                const double *h = (const double *)r.lo;
-                size_t bad = 0, first = 0;
-                for (size_t i = 0; i < tmp.size(); i++)
-                    if (tmp[i] != h[i] && !(tmp[i] != tmp[i] && h[i] != h[i])) {
-                        if (!bad)
-                            first = i;
-                        bad++;
-                    }
-                if (bad)
-                    fprintf(stderr, "[b2g] resident mismatch: host %p + %zu doubles, %zu differ, first at %zu (dev %.17g host %.17g)\n",
-                            (const void *)r.lo, tmp.size(), bad, first, tmp[first], h[first]);
-            }
-            B2G_CUDA(cudaMemcpyAsync(dev_base + r.dev_off, res, r.hi - r.lo, cudaMemcpyDeviceToDevice, ctx->stream));
-            ctx->resident_hits++, ctx->resident_hit_bytes += (int64_t)(r.hi - r.lo);
-            continue;
-        }
         if (mw.add(r.dev_off * sizeof(double), (const void *)r.lo, r.hi - r.lo))
             return 1;
+        ctx->mirrored_bytes += (int64_t)(r.hi - r.lo);
     }
-    const int rc = mw.flush();
-    ctx->vouched.clear(); // one shot
-    return rc;
+    return mw.flush();
 }
 
-void b2g_resident_keep(b2g_context *ctx, double *dev, const std::vector<B2GRange> &rg, size_t doubles) {
-    // a new mirror of a host range supersedes older ones that overlap it
-    for (size_t i = 0; i < ctx->resident.size();) {
-        B2GResident &R = ctx->resident[i];
-        bool overlap = false;
-        if (!R.ranges.empty() && !rg.empty() && R.ranges.front().lo < rg.back().hi && rg.front().lo < R.ranges.back().hi)
-            for (const B2GRange &r : rg) {
-                const B2GRange &q = b2g_locate_range(R.ranges, r.lo);
-                const B2GRange *nx = (&q + 1 < R.ranges.data() + R.ranges.size()) ? &q + 1 : nullptr;
-                if ((q.lo < r.hi && r.lo < q.hi) || (nx && nx->lo < r.hi && r.lo < nx->hi)) {
-                    overlap = true;
-                    break;
-                }
-            }
-        if (overlap) {
-            b2g_dfree(ctx, R.dev);
-            ctx->resident.erase(ctx->resident.begin() + (long)i);
-        } else
-            i++;
-    }
-    B2GResident R;
-    R.dev = dev, R.ranges = rg, R.doubles = doubles;
-    ctx->resident.push_back(std::move(R));
-}
-
-extern "C" int b2g_resident_vouch(b2g_context *ctx, int64_t count, const double *const *host, const int64_t *doubles) {
-    if (!ctx || (count > 0 && (!host || !doubles))) {
-        b2g_set_error("b2g_resident_vouch: null argument");
+extern "C" int b2g_resident_map(b2g_context *ctx, int64_t count, const double *const *host, const int64_t *doubles,
+                                double *const *dev) {
+    if (!ctx || (count > 0 && (!host || !doubles || !dev))) {
+        b2g_set_error("b2g_resident_map: null argument");
         return 1;
     }
+    std::vector<B2GMapEntry> m;
+    m.reserve((size_t)std::max<int64_t>(count, 0));
     for (int64_t i = 0; i < count; i++)
-        if (host[i] && doubles[i] > 0)
-            ctx->vouched.emplace_back((uintptr_t)host[i], (uintptr_t)host[i] + (uintptr_t)doubles[i] * sizeof(double));
-    std::sort(ctx->vouched.begin(), ctx->vouched.end());
-    std::vector<std::pair<uintptr_t, uintptr_t>> m;
-    for (auto &v : ctx->vouched) {
-        if (!m.empty() && v.first <= m.back().second)
-            m.back().second = std::max(m.back().second, v.second);
-        else
-            m.push_back(v);
-    }
-    ctx->vouched.swap(m);
+        if (host[i] && dev[i] && doubles[i] > 0)
+            m.push_back(B2GMapEntry{(uintptr_t)host[i], (uintptr_t)host[i] + (uintptr_t)doubles[i] * sizeof(double),
+                                    dev[i]});
+    std::sort(m.begin(), m.end(), [](const B2GMapEntry &x, const B2GMapEntry &y) { return x.lo < y.lo; });
+    for (size_t i = 1; i < m.size(); i++)
+        if (m[i].lo < m[i - 1].hi) {
+            b2g_set_error("b2g_resident_map: host ranges overlap (two live blocks cannot share host addresses)");
+            return 1;
+        }
+    ctx->rmap.swap(m);
     return 0;
 }
 
-extern "C" int b2g_resident_cover(b2g_context *ctx, int64_t count, const double *const *host, const int64_t *doubles) {
-    if (!ctx || (count > 0 && (!host || !doubles))) {
-        b2g_set_error("b2g_resident_cover: null argument");
-        return 1;
-    }
-    ctx->cover.clear();
-    for (int64_t i = 0; i < count; i++)
-        if (host[i] && doubles[i] > 0)
-            ctx->cover.emplace_back((uintptr_t)host[i], (uintptr_t)host[i] + (uintptr_t)doubles[i] * sizeof(double));
-    return 0;
-}
-
-extern "C" int b2g_resident_drop(b2g_context *ctx) {
-    if (!ctx)
-        return 0;
-    B2G_CUDA(cudaSetDevice(ctx->device));
-    for (B2GResident &R : ctx->resident)
-        b2g_dfree(ctx, R.dev);
-    ctx->resident.clear();
-    ctx->vouched.clear();
-    ctx->cover.clear();
-    return 0;
-}
-
-extern "C" int b2g_resident_stats(const b2g_context *ctx, int64_t *bytes_held, int64_t *bytes_hit) {
+extern "C" int b2g_resident_stats(const b2g_context *ctx, int64_t *bytes_hit, int64_t *bytes_mirrored) {
     if (!ctx) {
         b2g_set_error("b2g_resident_stats: null context");
         return 1;
     }
-    int64_t held = 0;
-    for (const B2GResident &R : ctx->resident)
-        held += (int64_t)(R.doubles * sizeof(double));
-    if (bytes_held)
-        *bytes_held = held;
     if (bytes_hit)
         *bytes_hit = ctx->resident_hit_bytes;
+    if (bytes_mirrored)
+        *bytes_mirrored = ctx->mirrored_bytes;
+    return 0;
+}
+
+// Batched block transfers between host blocks and their device shadows, ordered on the context stream.
+// Registered (pinned) host memory is copied directly; pageable memory goes through the pinned staging ring.
+static bool host_is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+extern "C" int b2g_download(b2g_context *ctx, int64_t count, double *const *host, const double *const *dev,
+                            const int64_t *doubles) {
+    if (!ctx || (count > 0 && (!host || !dev || !doubles))) {
+        b2g_set_error("b2g_download: null argument");
+        return 1;
+    }
+    B2G_CUDA(cudaSetDevice(ctx->device));
+    std::vector<B2GRange> staged; // pageable destinations: packed through the staging ring
+    std::vector<const double *> staged_dev;
+    for (int64_t i = 0; i < count; i++) {
+        if (doubles[i] <= 0)
+            continue;
+        if (host_is_pinned(host[i]))
+            B2G_CUDA(cudaMemcpyAsync(host[i], dev[i], (size_t)doubles[i] * sizeof(double), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+        else {
+            staged.push_back(B2GRange{(uintptr_t)host[i], (uintptr_t)host[i] + (size_t)doubles[i] * sizeof(double), 0});
+            staged_dev.push_back(dev[i]);
+        }
+    }
+    // pageable blocks one by one (each a contiguous device stretch): base = the block itself
+    for (size_t i = 0; i < staged.size(); i++) {
+        std::vector<B2GRange> one(1, staged[i]);
+        if (b2g_download_ranges(ctx, one, staged_dev[i], false))
+            return 1;
+    }
+    B2G_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int b2g_upload_blocks(b2g_context *ctx, int64_t count, double *const *dev, const double *const *host,
+                                 const int64_t *doubles) {
+    if (!ctx || (count > 0 && (!host || !dev || !doubles))) {
+        b2g_set_error("b2g_upload_blocks: null argument");
+        return 1;
+    }
+    B2G_CUDA(cudaSetDevice(ctx->device));
+    if (ensure_upload_buffers(ctx))
+        return 1;
+    for (int64_t i = 0; i < count; i++) {
+        if (doubles[i] <= 0)
+            continue;
+        const size_t bytes = (size_t)doubles[i] * sizeof(double);
+        if (host_is_pinned(host[i]))
+            B2G_CUDA(cudaMemcpyAsync(dev[i], host[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
+        else if (bytes >= B2G_UP_CHUNK / 4) {
+            if (b2g_upload(ctx, dev[i], host[i], bytes))
+                return 1;
+        } else { // small pageable block: one staged slice
+            MirrorWriter mw{ctx, (char *)dev[i]};
+            if (mw.add(0, host[i], bytes) || mw.flush())
+                return 1;
+        }
+        ctx->mirrored_bytes += (int64_t)bytes;
+    }
+    B2G_CUDA(cudaStreamSynchronize(ctx->stream)); // the staging buffers and the host blocks are free again
+    return 0;
+}
+
+extern "C" int b2g_host_register(b2g_context *ctx, void *ptr, size_t bytes) {
+    if (!ctx || !ptr) {
+        b2g_set_error("b2g_host_register: null argument");
+        return 1;
+    }
+    B2G_CUDA(cudaSetDevice(ctx->device));
+    B2G_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return 0;
+}
+extern "C" int b2g_host_unregister(b2g_context *ctx, void *ptr) {
+    if (!ctx || !ptr) {
+        b2g_set_error("b2g_host_unregister: null argument");
+        return 1;
+    }
+    B2G_CUDA(cudaSetDevice(ctx->device));
+    B2G_CUDA(cudaHostUnregister(ptr));
     return 0;
 }
 

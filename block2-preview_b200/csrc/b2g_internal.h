@@ -3,6 +3,7 @@
 #include "../../include/b2g.h"
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <functional>
 #include <string>
 #include <utility>
 #include <vector>
@@ -32,12 +33,10 @@ struct B2GRange {
     uintptr_t lo, hi; // host bytes [lo, hi)
     size_t dev_off;   // doubles from the device base
 };
-// Output blocks of a blocking call kept in HBM after their download (B2G_KEEP_RESIDENT): the next
-// calls that mirror host ranges the caller vouches for (b2g_resident_vouch) copy them device to device.
-struct B2GResident {
-    double *dev = nullptr;                // one allocation (cudaMalloc'ed through the stream pool)
-    std::vector<B2GRange> ranges;       // host ranges it mirrors, with their offsets
-    size_t doubles = 0;
+// Device-resident operands (b2g_resident_map): host byte range [lo, hi) currently lives at dev.
+struct B2GMapEntry {
+    uintptr_t lo, hi;
+    double *dev;
 };
 
 struct b2g_context {
@@ -59,11 +58,9 @@ struct b2g_context {
     cudaStream_t side[N_SIDE] = {};
     cudaEvent_t side_done[N_SIDE] = {};
     cudaEvent_t fork_ev = nullptr;
-    std::vector<B2GResident> resident;
-    std::vector<std::pair<uintptr_t, uintptr_t>> vouched; // host byte ranges valid for the NEXT mirror (one shot)
-    int64_t resident_hits = 0, resident_hit_bytes = 0;
+    std::vector<B2GMapEntry> rmap; // sorted by lo, disjoint (b2g_resident_map)
+    int64_t resident_hits = 0, resident_hit_bytes = 0, mirrored_bytes = 0;
     bool blocking_attr_set = false; // dynamic shared memory limits of the blocking kernels raised on this device
-    std::vector<std::pair<uintptr_t, uintptr_t>> cover; // full extents of the blocks the next KEEP_RESIDENT call writes
     void *h_up[2] = {nullptr, nullptr};
     cudaEvent_t up_done[2] = {nullptr, nullptr};
     size_t up_bytes = 0;
@@ -89,6 +86,8 @@ int b2g_dmalloc(b2g_context *ctx, void **ptr, size_t bytes);
 void b2g_dfree(b2g_context *ctx, void *ptr);
 // pageable host -> device copy through pinned staging filled by several host threads
 int b2g_upload(b2g_context *ctx, void *dst, const void *src, size_t bytes);
+// fn(lo, hi) over [0, n) in at most nt contiguous chunks on host threads
+void b2g_parallel_chunks(size_t n, int nt, const std::function<void(size_t, size_t)> &fn);
 #define B2G_CUDA(expr)                                                                   \
     do {                                                                                 \
         cudaError_t e__ = (expr);                                                        \
@@ -108,8 +107,8 @@ inline double *b2g_translate(const std::vector<B2GRange> &rg, double *dev_base, 
 }
 // host ranges -> device (pinned staging, small neighbours packed into one DMA); asynchronous
 int b2g_mirror_ranges(b2g_context *ctx, const std::vector<B2GRange> &rg, double *dev_base);
-// keep `dev` (ownership passes to the context) as the resident mirror of the host ranges rg
-void b2g_resident_keep(b2g_context *ctx, double *dev, const std::vector<B2GRange> &rg, size_t doubles);
+// device address of the host range [ptr, ptr + bytes) if it lies inside one mapped range, else nullptr
+double *b2g_map_lookup(b2g_context *ctx, const void *ptr, size_t bytes);
 // device -> host ranges through pinned staging; add = true: host += device, else host = device. Synchronous.
 int b2g_download_ranges(b2g_context *ctx, const std::vector<B2GRange> &rg, const double *dev_base, bool add);
 

@@ -1,6 +1,7 @@
 // b2g_tiled.cu — the two-phase DMMA replay of the H.C pair list (see b2g_tiled.cuh).
 #include "b2g_tiled.cuh"
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <map>
 #include <numeric>
@@ -365,10 +366,12 @@ struct TiledPlan {
 template <class Cfg, bool L> static int launch_p1(const LaunchGroup &g, const TiledPlan &tp, b2g_context *ctx,
                                                   cudaStream_t stream, unsigned int *counter, const double *c) {
     auto kern = phase1_kernel<Cfg, L>;
-    static bool attr = false;
-    if (!attr) {
+    // the dynamic shared memory limit is a per-device function attribute: one bit per device ordinal
+    static std::atomic<uint64_t> attr_mask{0};
+    const uint64_t bit = (uint64_t)1 << (ctx->device & 63);
+    if (!(attr_mask.load(std::memory_order_acquire) & bit)) {
         B2G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr = true;
+        attr_mask.fetch_or(bit, std::memory_order_release);
     }
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::THREADS, Cfg::SMEM_BYTES);
@@ -380,10 +383,12 @@ template <class Cfg, bool L> static int launch_p2(const LaunchGroup &g, const Ti
                                                   cudaStream_t stream, unsigned int *counter, double *v,
                                                   double scale) {
     auto kern = phase2_kernel<Cfg, L>;
-    static bool attr = false;
-    if (!attr) {
+    // the dynamic shared memory limit is a per-device function attribute: one bit per device ordinal
+    static std::atomic<uint64_t> attr_mask{0};
+    const uint64_t bit = (uint64_t)1 << (ctx->device & 63);
+    if (!(attr_mask.load(std::memory_order_acquire) & bit)) {
         B2G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr = true;
+        attr_mask.fetch_or(bit, std::memory_order_release);
     }
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::THREADS, Cfg::SMEM_BYTES);

@@ -15,7 +15,35 @@ using namespace block2;
 struct TermCollector {
     bool active = false;
     vector<vector<b2g_tp_term>> per_thread;
+    // H_eff diagonal: one recorder per walking thread, filled through the reference's own
+    // BatchGEMMSeq::tensor_product_diagonal / three_tensor_product_diagonal (core/batch_gemm.hpp:1110-1135)
+    bool diag_active = false;
+    vector<shared_ptr<BatchGEMMSeq<double>>> diag_seqs;
     TermCollector() : per_thread(max(1, threading->n_threads_global)) {}
+    void begin_diag() {
+        diag_seqs.assign((size_t)max(1, threading->n_threads_global), nullptr);
+        for (auto &q : diag_seqs)
+            q = make_shared<BatchGEMMSeq<double>>(0, SeqTypes::Auto);
+        diag_active = true;
+    }
+    void end_diag() {
+        diag_active = false;
+        diag_seqs.clear();
+    }
+    // intermediates / numerical_transform: the iadd calls of the stock walk (core/tensor_functions.hpp:2404-2517),
+    // recorded per walking thread the same way
+    bool iadd_active = false;
+    vector<shared_ptr<BatchGEMMSeq<double>>> iadd_seqs;
+    void begin_iadd() {
+        iadd_seqs.assign((size_t)max(1, threading->n_threads_global), nullptr);
+        for (auto &q : iadd_seqs)
+            q = make_shared<BatchGEMMSeq<double>>(0, SeqTypes::Auto);
+        iadd_active = true;
+    }
+    void end_iadd() {
+        iadd_active = false;
+        iadd_seqs.clear();
+    }
     void clear() {
         for (auto &v : per_thread)
             v.clear();
@@ -46,6 +74,41 @@ template <typename S> struct GPUOperatorFunctions : OperatorFunctions<S, double>
         shared_ptr<GPUOperatorFunctions<S>> r = make_shared<GPUOperatorFunctions<S>>(cg, collector);
         r->seq = seq->copy();
         return r;
+    }
+    // While the H_eff diagonal is recorded, the enumeration of the stock methods (operator_functions.hpp:
+    // 211-328) runs unchanged but against this thread's own recorder, so that nothing lands in the shared
+    // sequence TensorFunctions::tensor_product_diagonal executes on the host when the walk is over.
+    struct SeqSwap {
+        shared_ptr<BatchGEMMSeq<FL>> &slot, saved;
+        SeqSwap(shared_ptr<BatchGEMMSeq<FL>> &slot, const shared_ptr<BatchGEMMSeq<FL>> &tmp) : slot(slot), saved(slot) {
+            slot = tmp;
+        }
+        ~SeqSwap() { slot = saved; }
+    };
+    void tensor_product_diagonal(uint8_t conj, const shared_ptr<SparseMatrix<S, FL>> &a,
+                                 const shared_ptr<SparseMatrix<S, FL>> &b, const shared_ptr<SparseMatrix<S, FL>> &c, S opdq,
+                                 FL scale = 1.0) const override {
+        if (!collector->diag_active)
+            return Base::tensor_product_diagonal(conj, a, b, c, opdq, scale);
+        SeqSwap sw(const_cast<GPUOperatorFunctions *>(this)->seq, collector->diag_seqs.at(threading->get_thread_id()));
+        Base::tensor_product_diagonal(conj, a, b, c, opdq, scale);
+    }
+    void three_tensor_product_diagonal(uint8_t conj, const shared_ptr<SparseMatrix<S, FL>> &a,
+                                       const shared_ptr<SparseMatrix<S, FL>> &b, const shared_ptr<SparseMatrix<S, FL>> &c,
+                                       uint8_t dconj, const shared_ptr<SparseMatrix<S, FL>> &da,
+                                       const shared_ptr<SparseMatrix<S, FL>> &db, bool dleft, S opdq,
+                                       FL scale = 1.0) const override {
+        if (!collector->diag_active)
+            return Base::three_tensor_product_diagonal(conj, a, b, c, dconj, da, db, dleft, opdq, scale);
+        SeqSwap sw(const_cast<GPUOperatorFunctions *>(this)->seq, collector->diag_seqs.at(threading->get_thread_id()));
+        Base::three_tensor_product_diagonal(conj, a, b, c, dconj, da, db, dleft, opdq, scale);
+    }
+    void iadd(const shared_ptr<SparseMatrix<S, FL>> &a, const shared_ptr<SparseMatrix<S, FL>> &b, FL scale = 1.0,
+              bool conj = false) const override {
+        if (!collector->iadd_active)
+            return Base::iadd(a, b, scale, conj);
+        SeqSwap sw(const_cast<GPUOperatorFunctions *>(this)->seq, collector->iadd_seqs.at(threading->get_thread_id()));
+        Base::iadd(a, b, scale, conj);
     }
     void tensor_product(uint8_t conj, const shared_ptr<SparseMatrix<S, FL>> &a, const shared_ptr<SparseMatrix<S, FL>> &b,
                         const shared_ptr<SparseMatrix<S, FL>> &c, FL scale = 1.0) const override {
@@ -127,14 +190,14 @@ inline void record_blocking_expr(const shared_ptr<OperatorFunctions<S, double>> 
     else {
         sum = make_shared<SparseMatrix<S, FL>>(make_shared<VectorAllocator<FL>>());
         const shared_ptr<SparseMatrixInfo<S>> &sinfo = side.at(abs_value((shared_ptr<OpExpr<S>>)op->ops[0]))->info;
-        if (alloc_tmp != nullptr) // structure-only recording: storage from the caller, pre-sums not recorded
+        if (alloc_tmp != nullptr) // storage from the caller (reserved addresses, structure-only arenas)
             (*alloc_tmp)(sum, sinfo);
-        else {
+        else
             sum->allocate(sinfo);
+        if (pre != nullptr) // structure-only recording passes no pre-sum recorder
             for (size_t i = 0; i < op->ops.size(); i++)
                 pre->iadd(sum, side.at(abs_value((shared_ptr<OpExpr<S>>)op->ops[i])), op->ops[i]->factor,
                           op->conjs[i]);
-        }
         temps.push_back(sum);
     }
     if (sum_right)

@@ -19,9 +19,15 @@ using namespace std;
 
 struct Args {
     string fcidump, pg = "d2h", occ = "", scratch = "/tmp/b2g_scratch", davidson = "device";
-    int bond = 250, n_sweeps = 6, threads = 8, seed = 0, device = 0, ranks = 1, rank = 0;
+    int bond = 250, n_sweeps = 6, threads = 8, device = 0, ranks = 1, rank = 0;
+    // never 0: Random::rand_seed(0) seeds from the clock (core/utils.hpp:231-236) and the two arms of
+    // --compare would start from different MPS
+    int seed = 1234;
     string shm = "b2g";
-    bool compare = false, verify = false, gpu_rotate = false, gpu_contract = false;
+    bool compare = false, verify = false, gpu_rotate = true, gpu_contract = true, gpu_diag = true, gpu_iadd = true,
+         host_mirror = false, pin = true, cpu_only = false, classic = false;
+    int noise_sweeps = 2;   // sweeps per noise level: {noise x k, 0.1 noise x k, 0 ...}
+    double dav_thrd = 0;    // > 0: Davidson threshold of every sweep (default: the reference's noise-derived schedule)
     double conv = 1e-7, noise = 1e-5;
     size_t dsize_gb = 8;
 };
@@ -66,7 +72,10 @@ static RunResult run_dmrg(const Args &args, const shared_ptr<MPO<S, double>> &mp
     me->delayed_contraction = OpNamesSet::normal_ops();
     me->cached_contraction = true;
     vector<ubond_t> bdims = {bond_dim};
-    vector<double> noises = {args.noise, args.noise, args.noise * 0.1, args.noise * 0.1, 0.0};
+    vector<double> noises;
+    for (int z = 0; z < 2 * args.noise_sweeps; z++)
+        noises.push_back(z < args.noise_sweeps ? args.noise : args.noise * 0.1);
+    noises.push_back(0.0);
     if (args.noise == 0)
         noises = {0.0};
     shared_ptr<DMRG<S, double, double>> dmrg;
@@ -80,6 +89,8 @@ static RunResult run_dmrg(const Args &args, const shared_ptr<MPO<S, double>> &mp
     dmrg->noise_type = NoiseTypes::DensityMatrix;
     dmrg->decomp_type = DecompositionTypes::DensityMatrix;
     dmrg->davidson_soft_max_iter = 4000;
+    if (args.dav_thrd > 0)
+        dmrg->davidson_conv_thrds = vector<double>(noises.size(), args.dav_thrd);
     Timer t;
     t.get_time();
     dmrg->solve(args.n_sweeps, true, args.conv * 0.1);
@@ -112,8 +123,18 @@ int main(int argc, char **argv) {
         else if (k == "--dsize") a.dsize_gb = (size_t)atol(nxt().c_str());
         else if (k == "--compare") a.compare = true;
         else if (k == "--verify") a.verify = true;
-        else if (k == "--gpu-rotate") a.gpu_rotate = true;
+        else if (k == "--gpu-rotate") a.gpu_rotate = true;   // default since round 2; kept for old command lines
         else if (k == "--gpu-contract") a.gpu_contract = true;
+        else if (k == "--no-gpu-rotate") a.gpu_rotate = false;
+        else if (k == "--no-gpu-contract") a.gpu_contract = false;
+        else if (k == "--no-gpu-diag") a.gpu_diag = false;
+        else if (k == "--no-gpu-iadd") a.gpu_iadd = false;
+        else if (k == "--noise-sweeps") a.noise_sweeps = atoi(nxt().c_str());
+        else if (k == "--dav-thrd") a.dav_thrd = atof(nxt().c_str());
+        else if (k == "--classic") a.classic = true; // ClassicParallelMPO instead of ParallelMPO (NewScheme)
+        else if (k == "--cpu-only") a.cpu_only = true; // the stock CPU path alone (sweep-time baseline)
+        else if (k == "--host-mirror") a.host_mirror = true;
+        else if (k == "--no-pin") a.pin = false;
         else if (k == "--ranks") a.ranks = atoi(nxt().c_str());
         else if (k == "--rank") a.rank = atoi(nxt().c_str());
         else if (k == "--shm") a.shm = nxt();
@@ -153,7 +174,13 @@ int main(int argc, char **argv) {
         shared_ptr<ParallelCommunicator<S>> comm =
             make_shared<b2g_host::ShmCommunicator<S>>(a.ranks, a.rank, a.shm);
         shared_ptr<ParallelRule<S, double>> rule = make_shared<ParallelRuleQC<S, double>>(comm);
-        mpo = make_shared<ParallelMPO<S, double>>(mpo, rule);
+        // NewScheme (default, parallel_mpo.hpp:150): no blocking collectives, Partial operators repeated on every
+        // rank.  --classic (parallel_mpo.hpp:32): every term on exactly one rank, Partial operators reduced to
+        // their owner after blocking (ParallelRule::distributed_apply, parallel_rule.hpp:418-494).
+        if (a.classic)
+            mpo = make_shared<ClassicParallelMPO<S, double>>(mpo, rule);
+        else
+            mpo = make_shared<ParallelMPO<S, double>>(mpo, rule);
         // all ranks share the scratch directory: ParallelRule's constructor gives every rank its own
         // prefix for distributed files and lets only the root write the common ones (parallel_rule.hpp:340)
         if (a.rank != 0)
@@ -164,6 +191,17 @@ int main(int argc, char **argv) {
         printf("=== reference CPU path (stock TensorFunctions, %d threads) ===\n", a.threads);
         ref = run_dmrg<S>(a, mpo, hamil, target, false);
     }
+    if (a.cpu_only) {
+        if (!a.compare)
+            ref = run_dmrg<S>(a, mpo, hamil, target, false);
+        for (size_t i = 0; i < ref.energies.size(); i++)
+            printf("SWEEP %zu E_ref=%.12f\n", i, ref.energies[i]);
+        printf("{\"mode\": \"b2g_dmrg\", \"cpu_only\": 1, \"bond\": %d, \"seed\": %d, \"sweeps\": %zu, \"t_ref\": %.3f, "
+               "\"threads\": %d, \"e_ref\": %.12f}\n",
+               a.bond, a.seed, ref.energies.size(), ref.total, a.threads, ref.energies.empty() ? 0.0 : ref.energies.back());
+        fflush(stdout);
+        _exit(0);
+    }
     printf("=== GPU path (b2g_host::install, davidson = %s) ===\n", a.davidson.c_str());
     shared_ptr<TensorFunctions<S, double>> stock_tf = mpo->tf;
     shared_ptr<b2g_host::Session> session =
@@ -171,6 +209,11 @@ int main(int argc, char **argv) {
     session->verify = a.verify;
     session->gpu_rotate = a.gpu_rotate;
     session->gpu_contract = a.gpu_contract;
+    session->gpu_diag = a.gpu_diag;
+    session->gpu_iadd = a.gpu_iadd;
+    session->host_mirror = a.host_mirror;
+    if (a.pin)
+        session->pin_stacks();
     RunResult gpu = run_dmrg<S>(a, mpo, hamil, target, true);
     for (size_t i = 0; i < gpu.energies.size(); i++) {
         if (a.compare && i < ref.energies.size())
@@ -187,25 +230,38 @@ int main(int argc, char **argv) {
         fflush(stdout);
         _exit(0);
     }
-    printf("{\"mode\": \"b2g_dmrg\", \"ranks\": %d, \"davidson\": \"%s\", \"bond\": %d, \"sweeps\": %zu, \"t_gpu\": %.3f, "
-           "\"t_ref\": %.3f, \"threads\": %d, \"e_gpu\": %.12f, \"e_ref\": %.12f, \"max_sweep_diff\": %.3e, "
+    int64_t res_hit = 0, res_mirrored = 0;
+    b2g_resident_stats(session->ctx, &res_hit, &res_mirrored);
+    printf("{\"mode\": \"b2g_dmrg\", \"ranks\": %d, \"davidson\": \"%s\", \"bond\": %d, \"seed\": %d, \"sweeps\": %zu, "
+           "\"t_gpu\": %.3f, \"t_ref\": %.3f, \"threads\": %d, \"e_gpu\": %.12f, \"e_ref\": %.12f, "
+           "\"max_sweep_diff\": %.3e, \"final_diff\": %.3e, "
            "\"plans\": %zu, \"host_matvecs\": %zu, \"t_plan\": %.3f, \"t_host_matvec\": %.3f, \"launches\": %lld, "
            "\"matvec_sites_verified\": %zu, \"max_matvec_rel_err\": %.3e, \"gpu_rotate\": %d, \"rotations\": %zu, "
-           "\"t_rotate\": %.3f, \"rotate_gflop\": %.3f, \"max_rotate_rel_err\": %.3e, \"gpu_contract\": %d, "
-           "\"contractions\": %zu, \"t_contract\": %.3f, \"contract_entries\": %zu, \"contract_kernel_ms\": %.3f, "
-           "\"contract_gbytes\": %.4f, \"max_contract_rel_err\": %.3e, "
+           "\"t_rotate\": %.3f, \"t_rotate_download\": %.3f, \"rotate_gflop\": %.3f, \"max_rotate_rel_err\": %.3e, "
+           "\"gpu_contract\": %d, \"contractions\": %zu, \"t_contract\": %.3f, \"contract_entries\": %zu, "
+           "\"contract_kernel_ms\": %.3f, \"contract_gbytes\": %.4f, \"max_contract_rel_err\": %.3e, "
            "\"t_contract_record\": %.3f, \"t_contract_plan\": %.3f, \"t_contract_upload\": %.3f, "
-           "\"t_contract_download\": %.3f, \"resident_hit_gbytes\": %.3f, \"resident_peak_gbytes\": %.3f}\n",
-           a.ranks, a.davidson.c_str(), a.bond, gpu.energies.size(), gpu.total, ref.total, a.threads,
+           "\"t_contract_download\": %.3f, \"gpu_diag\": %d, \"diagonals\": %zu, \"t_diag\": %.3f, "
+           "\"diag_entries\": %zu, \"max_diag_rel_err\": %.3e, \"gpu_iadd\": %d, \"iadd_walks\": %zu, \"t_iadd\": %.3f, "
+           "\"iadd_entries\": %zu, \"max_iadd_rel_err\": %.3e, \"host_mirror\": %d, \"pinned_stacks\": %d, "
+           "\"resident_read_gbytes\": %.3f, \"mirrored_gbytes\": %.3f, \"resident_peak_gbytes\": %.3f, "
+           "\"resident_uploaded_gbytes\": %.3f, \"resident_downloaded_gbytes\": %.3f, \"resident_evicted_gbytes\": %.3f}\n",
+           a.ranks, a.davidson.c_str(), a.bond, a.seed, gpu.energies.size(), gpu.total, ref.total, a.threads,
            gpu.energies.empty() ? 0.0 : gpu.energies.back(), ref.energies.empty() ? 0.0 : ref.energies.back(),
-           maxdiff, session->n_plan, session->n_matvec, session->t_plan, session->t_matvec,
+           maxdiff,
+           (a.compare && !gpu.energies.empty() && !ref.energies.empty()) ? gpu.energies.back() - ref.energies.back() : 0.0,
+           session->n_plan, session->n_matvec, session->t_plan, session->t_matvec,
            (long long)b2g_context_launches(session->ctx), session->n_verified, session->max_matvec_err,
-           (int)a.gpu_rotate, session->n_rotate, session->t_rotate, session->rotate_flops * 1e-9,
-           session->max_rotate_err, (int)a.gpu_contract, session->n_contract, session->t_contract,
-           session->contract_entries, session->contract_kernel_ms, session->contract_bytes * 1e-9,
+           (int)a.gpu_rotate, session->n_rotate, session->t_rotate, session->t_rotate_download,
+           session->rotate_flops * 1e-9, session->max_rotate_err, (int)a.gpu_contract, session->n_contract,
+           session->t_contract, session->contract_entries, session->contract_kernel_ms, session->contract_bytes * 1e-9,
            session->max_contract_err, session->t_contract_record, session->t_contract_plan,
-           session->t_contract_upload, session->t_contract_download, session->resident_hit_bytes * 1e-9,
-           session->resident_peak_bytes * 1e-9);
+           session->t_contract_upload, session->t_contract_download, (int)a.gpu_diag, session->n_diag,
+           session->t_diag, session->diag_entries, session->max_diag_err, (int)a.gpu_iadd, session->n_iadd,
+           session->t_iadd, session->iadd_entries, session->max_iadd_err, (int)session->host_mirror,
+           (int)(session->pinned != nullptr), res_hit * 1e-9, res_mirrored * 1e-9, session->store->peak * 1e-9,
+           session->store->uploaded_bytes * 1e-9, session->store->downloaded_bytes * 1e-9,
+           session->store->evicted_bytes * 1e-9);
     fflush(stdout);
     _exit(0);
 }

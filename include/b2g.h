@@ -25,6 +25,10 @@
  *                        <- the same blocking step one level up: the GMatrixFunctions::tensor_product calls
  *                           (core/matrix_functions.hpp:1269-1397) OperatorFunctions::tensor_product makes per
  *                           connection-info entry (core/operator_functions.hpp:672-711)
+ *   b2g_resident_map / b2g_download / b2g_upload_blocks / b2g_host_register
+ *                        <- the partition traffic of MovingEnvironment::left_contract_rotate / move_to
+ *                           (dmrg/moving_environment.hpp:226-430, 1542-1575) through DataFrame stack 1
+ *                           (core/allocator.hpp:617-660): environments stay in HBM
  *   b2g_davidson         <- IterativeMatrixFunctions<double>::davidson (k = 1, Normal type,
  *                           Olsen preconditioner)  core/iterative_matrix_functions.hpp:864-1173, 93-108
  *   b2g_comm_* / b2g_allreduce_sum
@@ -144,11 +148,6 @@ typedef struct b2g_blocking_stats {
     double upload_seconds, download_seconds, plan_seconds;
 } b2g_blocking_stats;
 
-#define B2G_KEEP_RESIDENT 2 /* host operand space: after the download the output blocks also stay in HBM (owned by
-                               the context) until b2g_resident_drop; see b2g_resident_vouch */
-#define B2G_DST_COVERED 4 /* with B2G_DST_ZERO, host operand space: the output blocks are exactly the extents
-                              announced by b2g_resident_cover and need NOT be initialised on the host - the
-                              device result (zero where no entry writes) overwrites them */
 #define B2G_PLAN_ONLY 8 /* regroup the list (clusters, units, serial components, algorithmic bytes) and return the
                            stats without touching a device; ctx may be NULL */
 #define B2G_DST_ZERO 1 /* caller guarantees every output block is zero on entry (freshly allocate()d operators):
@@ -189,20 +188,31 @@ typedef struct b2g_tp_term {
 int b2g_tensor_product_execute(b2g_context *ctx, int64_t count, const b2g_tp_term *terms, int operand_space,
                                int flags, b2g_blocking_stats *stats);
 
-/* Resident blocks.  A blocking call with B2G_KEEP_RESIDENT leaves its output blocks in HBM.  The host copy
- * stays authoritative: a later call (b2g_pairs_execute, b2g_plan_create, b2g_batch_execute,
- * b2g_tensor_product_execute) takes an input from the resident copy instead of the host ONLY if the caller
- * vouched for that host range since the previous mirroring call - i.e. states that the host block has not
- * been written since the blocking call produced it.  Vouching is one-shot (cleared by the next call that
- * mirrors operands).  b2g_resident_drop frees all resident blocks. */
-int b2g_resident_vouch(b2g_context *ctx, int64_t count, const double *const *host, const int64_t *doubles);
-/* Full extents of the (zero-initialised) output blocks of the NEXT B2G_KEEP_RESIDENT | B2G_DST_ZERO call: the
- * resident mirror then covers whole blocks, including sectors no term writes, so that a later reader of a
- * whole block finds it in one piece.  One shot. */
-int b2g_resident_cover(b2g_context *ctx, int64_t count, const double *const *host, const int64_t *doubles);
-int b2g_resident_drop(b2g_context *ctx);
-/* resident bytes currently held / host->device bytes avoided so far */
-int b2g_resident_stats(const b2g_context *ctx, int64_t *bytes_held, int64_t *bytes_hit);
+/* Device-resident operands (environments stay in HBM between left/right_contract, left/right_rotate and
+ * the H.C plan of the next site).  The host binding owns device buffers (b2g_malloc) that shadow operator blocks
+ * and tells the library where they are: a table of host ranges whose content currently lives at the given
+ * device addresses.  Every entry point that takes HOST operand pointers (b2g_plan_create, b2g_pairs_execute,
+ * b2g_batch_execute, b2g_tensor_product_execute) consults the table:
+ *   - an input operand that lies inside a mapped range is read in place from HBM (no upload, no copy);
+ *   - an output window that lies inside a mapped range is written in place in HBM and NOT copied back to the
+ *     host (with B2G_DST_ZERO the caller has zeroed the device buffer; the host range is never touched, it may
+ *     be address space without memory behind it).
+ * Ranges must not overlap.  The table stays in force until the next b2g_resident_map call (count = 0 clears it).
+ * It replaces the per-partition host<->device traffic of MovingEnvironment::left_contract_rotate / move_to
+ * (dmrg/moving_environment.hpp:226-430, 1542-1575), whose data live in DataFrame stack 1 (core/allocator.hpp:617-660). */
+int b2g_resident_map(b2g_context *ctx, int64_t count, const double *const *host, const int64_t *doubles,
+                     double *const *dev);
+/* host->device bytes avoided by resident inputs so far / bytes mirrored from the host so far */
+int b2g_resident_stats(const b2g_context *ctx, int64_t *bytes_hit, int64_t *bytes_mirrored);
+/* Block transfers between host blocks and their device shadows, ordered on the context stream; synchronous.
+ * Registered (b2g_host_register) host memory is copied by DMA directly, pageable memory through pinned staging. */
+int b2g_download(b2g_context *ctx, int64_t count, double *const *host, const double *const *dev,
+                 const int64_t *doubles);
+int b2g_upload_blocks(b2g_context *ctx, int64_t count, double *const *dev, const double *const *host,
+                      const int64_t *doubles);
+/* page-lock an existing host allocation (e.g. the DataFrame stacks, core/allocator.hpp:536) */
+int b2g_host_register(b2g_context *ctx, void *ptr, size_t bytes);
+int b2g_host_unregister(b2g_context *ctx, void *ptr);
 
 /* Davidson ground state with device-resident vectors; H applied through the plan.
  * ket_host: in = initial guess, out = eigenvector.  diag_host: H_eff diagonal.
@@ -218,12 +228,18 @@ int b2g_comm_init(b2g_context *ctx, int nranks, int rank, const void *id128);
 int b2g_comm_destroy(b2g_context *ctx);
 int b2g_allreduce_sum(b2g_context *ctx, double *dev, int64_t count); /* in place, async */
 
-/* device memory helpers for hosts without a CUDA runtime binding of their own */
+/* device memory helpers for hosts without a CUDA runtime binding of their own; b2g_malloc / b2g_free are
+ * stream-ordered pool allocations on the context stream (cheap enough for one buffer per operator tensor) */
 int b2g_malloc(b2g_context *ctx, size_t bytes, void **dev);
 int b2g_free(b2g_context *ctx, void *dev);
+/* free (including memory parked in the allocation pool) and total device memory */
+int b2g_mem_info(b2g_context *ctx, int64_t *free_bytes, int64_t *total_bytes);
 int b2g_memcpy_h2d(b2g_context *ctx, void *dev, const void *host, size_t bytes);
 int b2g_memcpy_d2h(b2g_context *ctx, void *host, const void *dev, size_t bytes);
 int b2g_memset_zero(b2g_context *ctx, void *dev, size_t bytes);
+
+/* test hook, no device: byte ranges [lo[t], hi[t]) the nt staging threads copy for an upload chunk of len bytes */
+int b2g_debug_upload_slices(int64_t len, int nt, int64_t *lo, int64_t *hi);
 
 #ifdef __cplusplus
 }

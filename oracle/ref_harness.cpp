@@ -46,8 +46,8 @@ struct Args {
     string mode = "dmrg", fcidump = "", sym = "su2", pg = "d2h", out = "",
            occ = "", scratch = "/tmp/b2ref_scratch";
     int bond = 250, site = -1, sweeps = 0, n_sweeps = 8, threads = 8, reps = 3,
-        dav_max = 4000, seed = 0;
-    bool with_data = true, structure_only = false, run_eigs = true;
+        dav_max = 4000, seed = 1234; // never 0: Random::rand_seed(0) seeds from the clock (core/utils.hpp:231-236)
+    bool with_data = true, structure_only = false, run_eigs = true, classic = false;
     double conv = 1e-7, noise = 1e-5, max_gflop = 0;
     int warmup = 1, ranks = 1, rank = 0, blk_call = 0;
     string shm = "";
@@ -96,6 +96,7 @@ static Args parse(int argc, char **argv) {
         else if (k == "--rank") a.rank = atoi(nxt().c_str());
         else if (k == "--shm") a.shm = nxt();
         else if (k == "--blk-call") a.blk_call = atoi(nxt().c_str());
+        else if (k == "--classic") a.classic = true;
         else if (k == "--nodata") a.with_data = false;
         else if (k == "--noeigs") a.run_eigs = false;
         else if (k == "--struct") a.structure_only = true, a.with_data = false, a.run_eigs = false;
@@ -103,6 +104,11 @@ static Args parse(int argc, char **argv) {
             fprintf(stderr, "unknown option %s\n", k.c_str());
             exit(2);
         }
+    }
+    if (a.seed == 0) {
+        fprintf(stderr, "--seed 0 means 'seed from the clock' in the reference (core/utils.hpp:231-236): "
+                        "runs would not be reproducible; pass a non-zero seed\n");
+        exit(2);
     }
     return a;
 }
@@ -1062,9 +1068,15 @@ template <typename S> static int run(const Args &args) {
         else
             comm = make_shared<LoneRankCommunicator<S>>(args.ranks, args.rank);
         shared_ptr<ParallelRule<S, FL>> rule = make_shared<ParallelRuleQC<S, FL>>(comm);
-        mpo = make_shared<ParallelMPO<S, FL>>(mpo, rule);
-        printf("MPO parallelised: rank %d of %d (ParallelRuleQC, NewScheme) T=%.3f\n", args.rank, args.ranks,
-               t.get_time());
+        // --classic: ClassicParallelMPO (parallel_mpo.hpp:32-148): expressions localised to the owner of every
+        // operator, Partial operators reduced to their owner after blocking (distributed_apply,
+        // parallel_rule.hpp:467-489) - no term is repeated on several ranks.  Default: ParallelMPO, NewScheme.
+        if (args.classic)
+            mpo = make_shared<ClassicParallelMPO<S, FL>>(mpo, rule);
+        else
+            mpo = make_shared<ParallelMPO<S, FL>>(mpo, rule);
+        printf("MPO parallelised: rank %d of %d (ParallelRuleQC, %s) T=%.3f\n", args.rank, args.ranks,
+               args.classic ? "classic scheme" : "NewScheme", t.get_time());
     }
     if (args.mode == "tpdump")
         g_tp_args = &args;
@@ -1072,7 +1084,8 @@ template <typename S> static int run(const Args &args) {
         g_varena.init((size_t)1 << 44);
         if (args.ranks > 1)
             mpo->tf = make_shared<StructTensorFunctions<S, FL, ParallelTensorFunctions<S, FL>>>(
-                mpo->tf->opf, dynamic_pointer_cast<ParallelMPO<S, FL>>(mpo)->rule);
+                mpo->tf->opf, args.classic ? dynamic_pointer_cast<ClassicParallelMPO<S, FL>>(mpo)->rule
+                                           : dynamic_pointer_cast<ParallelMPO<S, FL>>(mpo)->rule);
         else
             mpo->tf = make_shared<StructTensorFunctions<S, FL>>(mpo->tf->opf);
     }

@@ -292,60 +292,49 @@ def test_gpu_tensor_product_terms_match_oracle(b2g, ctx, seed, kron, zero):
 
 
 @pytest.mark.gpu
-def test_gpu_resident_blocks_are_used_only_when_vouched(b2g, ctx):
-    """KEEP_RESIDENT leaves the blocked operators in HBM; a later call reads them from there only for host
-    ranges the caller vouched for since the previous mirroring call (one shot).  The host copy is made to
-    differ on purpose to see which copy was read."""
+def test_gpu_resident_map_reads_and_writes_in_place(b2g, ctx):
+    """b2g_resident_map: an input inside a mapped host range is read from its device shadow (the host copy is
+    made to differ on purpose, to see which copy was read), an output inside a mapped range is written on
+    the device only - the host range is never touched - and unmapped operands keep the mirrored route."""
     rng = np.random.default_rng(11)
     n = 5000
     src, one = rng.standard_normal(n), np.ones(1)
-    mid, out = np.zeros(n), np.zeros(n)
+    mid, out = np.full(n, -1.0), np.zeros(n)
     p = lambda arr: np.array([arr.ctypes.data], dtype=np.uint64)
     axpy = lambda a, c, flags: ctx.batch_execute([111], [111], [n], [1], [1], [2.0], p(a), [1], p(one), [1], [1.0],
                                                  p(c), [1], [1], b2g.OPERANDS_HOST, flags)
-    ctx.resident_drop()
-    axpy(src, mid, b2g.DST_ZERO | b2g.KEEP_RESIDENT)
-    assert np.array_equal(mid, 2.0 * src)
-    held, hit0 = ctx.resident_stats()
-    assert held >= 8 * n
-    mid[:] = -1.0  # host copy now differs from the resident copy
-    ctx.resident_vouch(p(mid), [n])
-    axpy(mid, out, b2g.DST_ZERO)
-    assert np.array_equal(out, 4.0 * src)  # read from HBM
-    assert ctx.resident_stats()[1] - hit0 == 8 * n
-    out[:] = 0.0
-    axpy(mid, out, b2g.DST_ZERO)  # not vouched again: the host copy is read
-    assert np.array_equal(out, np.full(n, -2.0))
-    ctx.resident_vouch(p(mid), [n])
-    ctx.resident_drop()  # dropping also forgets the vouching
+    d_mid = ctx.malloc(8 * n)
+    ctx.memset_zero(d_mid, 8 * n)
+    hit0 = ctx.resident_stats()[0]
+    ctx.resident_map(p(mid), [n], [d_mid])
+    axpy(src, mid, b2g.DST_ZERO)            # output mapped: written in HBM, host copy untouched
+    assert np.array_equal(mid, np.full(n, -1.0))
+    axpy(mid, out, b2g.DST_ZERO)            # input mapped: read from HBM
+    assert np.array_equal(out, 4.0 * src)
+    assert ctx.resident_stats()[0] - hit0 == 8 * n
+    back = np.zeros(n)
+    ctx.download(p(back), [d_mid], [n])
+    assert np.array_equal(back, 2.0 * src)
+    ctx.resident_map([], [], [])            # cleared: the host copy is read again
     out[:] = 0.0
     axpy(mid, out, b2g.DST_ZERO)
     assert np.array_equal(out, np.full(n, -2.0))
-    assert ctx.resident_stats()[0] == 0
+    ctx.upload_blocks([d_mid], p(src), [n])
+    ctx.download(p(back), [d_mid], [n])
+    assert np.array_equal(back, src)
+    with pytest.raises(b2g.B2GError, match="overlap"):
+        ctx.resident_map([mid.ctypes.data, mid.ctypes.data + 8], [n, 4], [d_mid, d_mid])
+    ctx.free(d_mid)
 
 
-@pytest.mark.gpu
-def test_gpu_covered_outputs_need_no_initialisation(b2g, ctx):
-    """DST_COVERED: the announced output blocks are overwritten by the device result, zero where no entry
-    writes, so the host block may hold garbage on entry."""
-    rng = np.random.default_rng(12)
-    rows, cols = 40, 30
-    src, one = rng.standard_normal(rows * 10), np.ones(1)
-    out = np.full(rows * cols, 7.0)  # garbage
-    p = lambda arr, off=0: arr.ctypes.data + 8 * off
-    # rows-as-AXPY into the column window [5, 15) of every row
-    a = np.array([p(src, r * 10) for r in range(rows)], dtype=np.uint64)
-    c = np.array([p(out, r * cols + 5) for r in range(rows)], dtype=np.uint64)
-    b = np.full(rows, p(one), dtype=np.uint64)
-    with pytest.raises(b2g.B2GError, match="B2G_DST_COVERED"):
-        ctx.batch_execute([111], [111], [10], [1], [1], [3.0], a, [1], b, [1], [1.0], c, [1], [rows],
-                          b2g.OPERANDS_HOST, b2g.DST_ZERO | b2g.DST_COVERED)
-    ctx.resident_cover([p(out)], [rows * cols])
-    ctx.batch_execute([111], [111], [10], [1], [1], [3.0], a, [1], b, [1], [1.0], c, [1], [rows], b2g.OPERANDS_HOST,
-                      b2g.DST_ZERO | b2g.DST_COVERED)
-    ref = np.zeros((rows, cols))
-    ref[:, 5:15] = 3.0 * src.reshape(rows, 10)
-    assert np.array_equal(out.reshape(rows, cols), ref)
+def test_upload_staging_slices_cover_every_byte(b2g):
+    """the per-thread staging slices of the pageable upload path must cover the whole chunk
+    for every length / thread count (floor division lost the tail when len / nt was a multiple of 4096)."""
+    for nt in (1, 2, 3, 7, 8, 12, 16):
+        for length in (0, 1, 4095, 4096, 4097, 9371656, 16 * 4096 * 143 + 8, (32 << 20) - 8, 32 << 20):
+            lo, hi = b2g.upload_slices(length, nt)
+            assert lo[0] == 0 and (hi >= lo).all()
+            assert (lo[1:] == hi[:-1]).all() and hi[-1] == length, (nt, length, lo, hi)
 
 
 def test_recorded_blocking_workloads_are_consistent(b2g):

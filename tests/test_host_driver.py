@@ -4,8 +4,9 @@ binary block2-preview_b200/host/_build/b2g_dmrg_* (built by __graft_entry__.buil
 reference tree exists; the binary and its FCIDUMP inputs travel to the GPU box).
 
 Bars (BASELINE.json north_star): H.C <= 1e-11 relative against the reference's CPU executor
-on the live H_eff of every site; converged energy within 1e-8 Ha of the reference's stored values
-(unit_test/test_dmrg_n2_sto3g.cpp:191, unit_test/test_rotation_h10_sto6g.cpp:43)."""
+on the live H_eff of every site; energy per sweep within 1e-8 Ha of the reference's CPU path run in the
+same process from the same seed; converged energy within the reference's own tolerance of its stored values
+(unit_test/test_dmrg_n2_sto3g.cpp:73,131-138,191; unit_test/test_rotation_h10_sto6g.cpp:43)."""
 import json
 import os
 import subprocess
@@ -20,73 +21,84 @@ E_N2_1AG = -107.654122447525      # reference golden, SU2 singlet Ag
 E_H10 = -5.424385375684663        # reference golden, H10 STO-6G R=1.8
 
 
-def run_driver(exe, *args):
+def run_driver(exe, *args, timeout=900):
     path = os.path.join(BUILD, exe)
     if not os.path.exists(path):
         pytest.skip(f"{path} not built (needs the reference tree at build time)")
     env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
     out = subprocess.run([path, *args, "--scratch", "/tmp/b2g_test_scratch"], env=env, capture_output=True,
-                         text=True, timeout=900)
-    assert out.returncode == 0, out.stderr[-2000:]
+                         text=True, timeout=timeout)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-2000:])
     line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1]
-    return json.loads(line)
+    return json.loads(line), out.stdout
+
+
+N2 = ("--fcidump", os.path.join(BUILD, "data", "N2.STO3G.FCIDUMP"), "--bond", "250", "--threads", "4", "--noise", "1e-6")
+H10 = ("--fcidump", os.path.join(BUILD, "data", "H10.STO6G.R1.8.FCIDUMP"), "--threads", "8", "--noise", "1e-6")
+C2 = ("--fcidump", os.path.join(BUILD, "data", "C2.CAS.PVDZ.FCIDUMP"), "--threads", "16", "--noise", "1e-5")
 
 
 @pytest.mark.parametrize("davidson", ["device", "host"])
-def test_n2_sto3g_su2_energy_and_matvec_parity(davidson):
-    r = run_driver("b2g_dmrg_su2", "--fcidump", os.path.join(BUILD, "data", "N2.STO3G.FCIDUMP"), "--bond", "250",
-                   "--nsweeps", "8", "--threads", "4", "--noise", "1e-6", "--davidson", davidson, "--verify")
+def test_n2_sto3g_su2_every_list_against_the_reference_executor(davidson):
+    """--verify: every H.C list, every blocking call, every rotation list and every H_eff diagonal of the sweep is
+    re-executed by the reference's own executor on the same recorded list and compared (device-resident
+    environments with host mirrors, so that the reference executor can read the operands)."""
+    r, _ = run_driver("b2g_dmrg_su2", *N2, "--nsweeps", "8", "--davidson", davidson, "--verify")
     assert abs(r["e_gpu"] - E_N2_1AG) < 1e-8, r
     assert r["matvec_sites_verified"] > 0 or davidson == "host"
     assert r["max_matvec_rel_err"] < 1e-11, r
-    assert r["launches"] > 0
-
-
-def test_h10_sto6g_sz_energy_matches_reference_run():
-    r = run_driver("b2g_dmrg_sz", "--fcidump", os.path.join(BUILD, "data", "H10.STO6G.R1.8.FCIDUMP"), "--bond",
-                   "500", "--nsweeps", "8", "--threads", "8", "--noise", "1e-6", "--compare", "--verify")
-    assert abs(r["e_gpu"] - r["e_ref"]) < 1e-8, r          # same run, CPU path first
-    assert abs(r["e_gpu"] - E_H10) < 1e-7, r               # the reference's own tolerance for this value
-    assert r["max_matvec_rel_err"] < 1e-11, r
-
-
-def test_renormalisation_on_device_matches_reference_executor():
-    """--gpu-rotate: left_rotate / right_rotate lists (OperatorFunctions::tensor_rotate ->
-    BatchGEMMSeq::rotate) run through b2g_pairs_execute; --verify replays every list with the
-    reference's own auto_perform() and compares all rotated operator blocks."""
-    r = run_driver("b2g_dmrg_su2", "--fcidump", os.path.join(BUILD, "data", "N2.STO3G.FCIDUMP"), "--bond", "250",
-                   "--nsweeps", "8", "--threads", "4", "--noise", "1e-6", "--gpu-rotate", "--verify")
-    assert r["rotations"] > 0 and r["max_rotate_rel_err"] < 1e-11, r
-    assert abs(r["e_gpu"] - E_N2_1AG) < 1e-8, r
-    r = run_driver("b2g_dmrg_sz", "--fcidump", os.path.join(BUILD, "data", "H10.STO6G.R1.8.FCIDUMP"), "--bond",
-                   "300", "--nsweeps", "6", "--threads", "8", "--noise", "1e-6", "--gpu-rotate")
-    assert r["rotations"] > 0 and abs(r["e_gpu"] - E_H10) < 1e-6, r
-
-
-def test_blocking_on_device_matches_reference_executor():
-    """--gpu-contract: left_contract / right_contract recorded by the reference's own walker / OperatorFunctions
-    and executed by b2g_tensor_product_execute (resident blocks feeding the rotation list and the H.C plan);
-    --verify re-records every call with the reference's recorder, runs its auto_perform() and compares all
-    blocked operators, and does the same for every rotation list and H.C list."""
-    r = run_driver("b2g_dmrg_su2", "--fcidump", os.path.join(BUILD, "data", "N2.STO3G.FCIDUMP"), "--bond", "250",
-                   "--nsweeps", "8", "--threads", "4", "--noise", "1e-6", "--gpu-contract", "--gpu-rotate", "--verify")
     assert r["contractions"] > 0 and r["max_contract_rel_err"] < 1e-11, r
     assert r["rotations"] > 0 and r["max_rotate_rel_err"] < 1e-11, r
-    assert r["max_matvec_rel_err"] < 1e-11 and r["resident_hit_gbytes"] > 0, r
+    assert r["diagonals"] > 0 and r["max_diag_rel_err"] < 1e-11, r
+    assert r["iadd_walks"] > 0 and r["max_iadd_rel_err"] < 1e-11, r
+    assert r["launches"] > 0 and r["resident_read_gbytes"] > 0, r
+
+
+# Per-sweep energies are compared with the Davidson threshold pinned at 1e-10 in both arms: with the reference's
+# default schedule (threshold = noise / 10 on the SQUARED residual) an eigenvalue is only defined to ~1e-7 inside
+# a noisy sweep, and one more or one fewer Davidson iteration at a site moves the sweep energy by that much
+# (H10: 6e-8 between the arms in sweeps 1-2, 3e-12 at convergence; profiles/r02_energy_parity.md).
+TIGHT = ("--dav-thrd", "1e-10")
+
+
+def test_n2_device_resident_environments_energy_per_sweep():
+    """Default mode: environments and blocked operators stay in HBM (blocked operators have no host copy at all).
+    Same seed as the CPU arm run first in the same process: energy of every sweep within 1e-8 Ha."""
+    r, out = run_driver("b2g_dmrg_su2", *N2, *TIGHT, "--nsweeps", "10", "--compare")
+    assert r["host_mirror"] == 0 and r["resident_read_gbytes"] > 0, r
+    assert r["max_sweep_diff"] < 1e-8, (r, [ln for ln in out.splitlines() if ln.startswith("SWEEP")])
     assert abs(r["e_gpu"] - E_N2_1AG) < 1e-8, r
-    r = run_driver("b2g_dmrg_sz", "--fcidump", os.path.join(BUILD, "data", "H10.STO6G.R1.8.FCIDUMP"), "--bond",
-                   "300", "--nsweeps", "6", "--threads", "8", "--noise", "1e-6", "--gpu-contract", "--gpu-rotate",
-                   "--verify")
-    assert r["contractions"] > 0 and r["max_contract_rel_err"] < 1e-11 and r["max_rotate_rel_err"] < 1e-11, r
+
+
+def test_h10_sto6g_sz_energy_per_sweep_and_lists():
+    r, out = run_driver("b2g_dmrg_sz", *H10, *TIGHT, "--bond", "500", "--nsweeps", "8", "--compare")
+    assert r["max_sweep_diff"] < 1e-8, (r, [ln for ln in out.splitlines() if ln.startswith("SWEEP")])
+    assert abs(r["e_gpu"] - E_H10) < 1e-7, r               # the reference's own tolerance for this value
+    r, _ = run_driver("b2g_dmrg_sz", *H10, "--bond", "300", "--nsweeps", "6", "--verify")
+    assert r["max_matvec_rel_err"] < 1e-11 and r["max_contract_rel_err"] < 1e-11, r
+    assert r["max_rotate_rel_err"] < 1e-11 and r["max_diag_rel_err"] < 1e-11 and r["max_iadd_rel_err"] < 1e-11, r
     assert abs(r["e_gpu"] - E_H10) < 1e-6, r
 
 
-def test_blocking_on_device_zero_fill_route(monkeypatch):
-    """B2G_ZERO_OUTPUTS=1: zero-initialised outputs + add (B2G_DST_ZERO without B2G_DST_COVERED)."""
-    monkeypatch.setenv("B2G_ZERO_OUTPUTS", "1")
-    r = run_driver("b2g_dmrg_su2", "--fcidump", os.path.join(BUILD, "data", "N2.STO3G.FCIDUMP"), "--bond", "120",
-                   "--nsweeps", "4", "--threads", "4", "--noise", "1e-6", "--gpu-contract", "--gpu-rotate", "--verify")
-    assert r["contractions"] > 0 and r["max_contract_rel_err"] < 1e-11 and r["max_rotate_rel_err"] < 1e-11, r
+def test_c2_cas_pvdz_m500_energy_matches_the_cpu_arm():
+    """C2 CAS cc-pVDZ (26 orbitals) has no stored energy in the reference tree: parity is against the
+    reference's CPU path in the same process, same seed and schedule, run to convergence (noise -> 0, then
+    zero-noise sweeps until the energy change is below 1e-9).  From a random MPS the first sweeps of this system
+    are chaotic - the reference itself lands 2e-3 Ha apart after half a sweep when only its thread count changes
+    (profiles/r02_energy_parity.md) - so only the converged energies are comparable."""
+    r, out = run_driver("b2g_dmrg_su2", *C2, *TIGHT, "--bond", "500", "--nsweeps", "16", "--noise-sweeps", "3",
+                        "--conv", "1e-9", "--compare", timeout=1500)
+    assert abs(r["final_diff"]) < 1e-8, (r, [ln for ln in out.splitlines() if ln.startswith("SWEEP")])
+
+
+def test_host_paths_still_available():
+    """--no-gpu-contract / --no-gpu-rotate / --no-gpu-diag: the reference's CPU blocking with only H.C on the
+    device (round-1 default); --host-mirror: device path with every blocked operator copied back."""
+    r, _ = run_driver("b2g_dmrg_su2", *N2, "--nsweeps", "4", "--no-gpu-contract", "--no-gpu-rotate", "--no-gpu-diag",
+                      "--no-gpu-iadd", "--verify")
+    assert r["contractions"] == 0 and r["rotations"] == 0 and r["max_matvec_rel_err"] < 1e-11, r
+    r, _ = run_driver("b2g_dmrg_su2", *N2, "--nsweeps", "4", "--host-mirror")
+    assert r["host_mirror"] == 1 and r["contractions"] > 0, r
 
 
 def test_two_rank_dmrg_over_parallel_rule_qc_and_nccl(b2g):
