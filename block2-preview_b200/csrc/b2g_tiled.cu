@@ -6,23 +6,29 @@
 #include <map>
 #include <numeric>
 #include <tuple>
+#include <unordered_map>
 
 namespace b2g {
 
 // ----------------------------------------------------------------------------
 // Shared pipelined main loop.  Src provides:
-//   int  steps() const          number of BK-deep stages of this unit
-//   void issue(double*, double*) cp.async the next stage into (As, Bs) and advance
+//   int    steps() const            number of BK-deep stages of this unit
+//   double issue(double*, double*)  cp.async the next stage into (As, Bs), advance, and return the factor
+//                                   of the K-segment the stage belongs to (phase 1; phase 2 returns 1)
 // ----------------------------------------------------------------------------
-template <class Cfg, bool A_KC, bool B_KC, bool FULL, class Src>
-__device__ __forceinline__ void mainloop_impl(Src &src, double *smem, double (&acc)[Cfg::MI][Cfg::NI][2], int wm0,
-                                              int wn0, int mi_n, int ni_n) {
+template <class Cfg, bool A_KC, bool B_KC, bool FULL, bool SCALE, class Src>
+__device__ __forceinline__ void mainloop_impl(Src &src, double *smem, double *s_alpha,
+                                              double (&acc)[Cfg::MI][Cfg::NI][2], int wm0, int wn0, int mi_n,
+                                              int ni_n) {
     double *As = smem, *Bs = smem + Cfg::STAGES * Cfg::A_STAGE;
     const int total = src.steps();
 #pragma unroll
     for (int s = 0; s < Cfg::STAGES - 1; s++) {
-        if (s < total)
-            src.issue(As + s * Cfg::A_STAGE, Bs + s * Cfg::B_STAGE);
+        if (s < total) {
+            const double al = src.issue(As + s * Cfg::A_STAGE, Bs + s * Cfg::B_STAGE);
+            if (SCALE && threadIdx.x == 0)
+                s_alpha[s] = al;
+        }
         cp_async_commit();
     }
     for (int step = 0; step < total; step++) {
@@ -31,25 +37,27 @@ __device__ __forceinline__ void mainloop_impl(Src &src, double *smem, double (&a
         const int nxt = step + Cfg::STAGES - 1;
         if (nxt < total) {
             const int st = nxt % Cfg::STAGES;
-            src.issue(As + st * Cfg::A_STAGE, Bs + st * Cfg::B_STAGE);
+            const double al = src.issue(As + st * Cfg::A_STAGE, Bs + st * Cfg::B_STAGE);
+            if (SCALE && threadIdx.x == 0)
+                s_alpha[st] = al; // slot st was last read before the barrier above
         }
         cp_async_commit();
         const int cur = step % Cfg::STAGES;
-        compute_stage<Cfg, A_KC, B_KC, FULL>(As + cur * Cfg::A_STAGE, Bs + cur * Cfg::B_STAGE, acc, wm0, wn0, mi_n,
-                                             ni_n);
+        compute_stage<Cfg, A_KC, B_KC, FULL, SCALE>(As + cur * Cfg::A_STAGE, Bs + cur * Cfg::B_STAGE, acc, wm0, wn0,
+                                                    mi_n, ni_n, SCALE ? s_alpha[cur] : 1.0);
     }
     cp_async_wait<0>();
     __syncthreads();
 }
 
 // The guard-free body is chosen per CTA (block-uniform: every warp of an interior tile is full).
-template <class Cfg, bool A_KC, bool B_KC, class Src>
-__device__ __forceinline__ void mainloop(Src &src, double *smem, double (&acc)[Cfg::MI][Cfg::NI][2], int wm0, int wn0,
-                                         int mi_n, int ni_n, bool cta_full) {
+template <class Cfg, bool A_KC, bool B_KC, bool SCALE, class Src>
+__device__ __forceinline__ void mainloop(Src &src, double *smem, double *s_alpha, double (&acc)[Cfg::MI][Cfg::NI][2],
+                                         int wm0, int wn0, int mi_n, int ni_n, bool cta_full) {
     if (cta_full)
-        mainloop_impl<Cfg, A_KC, B_KC, true>(src, smem, acc, wm0, wn0, mi_n, ni_n);
+        mainloop_impl<Cfg, A_KC, B_KC, true, SCALE>(src, smem, s_alpha, acc, wm0, wn0, mi_n, ni_n);
     else
-        mainloop_impl<Cfg, A_KC, B_KC, false>(src, smem, acc, wm0, wn0, mi_n, ni_n);
+        mainloop_impl<Cfg, A_KC, B_KC, false, SCALE>(src, smem, s_alpha, acc, wm0, wn0, mi_n, ni_n);
 }
 
 template <class Cfg> __device__ __forceinline__ void warp_origin(int &wm0, int &wn0) {
@@ -62,24 +70,44 @@ __device__ __forceinline__ int clampi(int x, int lo, int hi) { return x < lo ? l
 
 // ------------------------------ phase 1 -------------------------------------
 template <class Cfg, bool B_KC> struct P1Src {
+    const P1Seg *seg, *seg_end;
+    const double *c;
     const double *a, *b;
-    int lda, ldb, m_valid, n_valid, k_left, nsteps;
+    P1Seg nxt; // descriptor of the following segment, fetched one segment ahead
+    double alpha;
+    int lda, ldb, row0, col0, m_valid, n_valid, k_left, nsteps;
     __device__ int steps() const { return nsteps; }
-    __device__ void issue(double *As, double *Bs) {
+    __device__ void use(const P1Seg &s) {
+        lda = s.lda, ldb = s.ldb, alpha = s.alpha;
+        a = c + s.a_off + (size_t)row0 * lda;
+        b = B_KC ? s.b0 + (size_t)col0 * ldb : s.b0 + col0;
+        k_left = s.k0;
+        if (seg + 1 < seg_end)
+            nxt = seg[1];
+    }
+    __device__ void open() { use(*seg); }
+    __device__ double issue(double *As, double *Bs) {
+        const double al = alpha;
         load_tile<Cfg::BM, Cfg::THREADS, true, Cfg::BK>(As, a, lda, m_valid, k_left);
         load_tile<Cfg::BN, Cfg::THREADS, B_KC, Cfg::BK>(Bs, b, ldb, n_valid, k_left);
-        a += Cfg::BK;
-        b += B_KC ? Cfg::BK : (size_t)Cfg::BK * ldb;
         k_left -= Cfg::BK;
+        if (k_left > 0) {
+            a += Cfg::BK;
+            b += B_KC ? Cfg::BK : (size_t)Cfg::BK * ldb;
+        } else if (++seg < seg_end)
+            use(nxt);
+        return al;
     }
 };
 
 template <class Cfg, bool B_KC>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
-phase1_kernel(const P1Pair *__restrict__ pairs, const Unit *__restrict__ units, int n_units,
-              unsigned int *__restrict__ counter, const double *__restrict__ c, double *__restrict__ wbuf) {
+phase1_kernel(const P1Group *__restrict__ groups, const P1Seg *__restrict__ segs, const Unit *__restrict__ units,
+              int n_units, unsigned int *__restrict__ counter, const double *__restrict__ c,
+              double *__restrict__ wbuf) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_unit;
+    __shared__ double s_alpha[Cfg::STAGES];
     int wm0, wn0;
     warp_origin<Cfg>(wm0, wn0);
     const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
@@ -89,14 +117,17 @@ phase1_kernel(const P1Pair *__restrict__ pairs, const Unit *__restrict__ units, 
         if (threadIdx.x == 0)
             s_unit = (int)(atomicAdd(counter, 1u) + gridDim.x);
         const Unit un = units[u];
-        const P1Pair p = pairs[un.idx];
+        const P1Group g = groups[un.idx];
         const int row0 = un.row0, col0 = un.col0;
         P1Src<Cfg, B_KC> src;
-        src.a = c + p.a_off + (size_t)row0 * p.lda;
-        src.b = B_KC ? p.b0 + (size_t)col0 * p.ldb : p.b0 + col0;
-        src.lda = p.lda, src.ldb = p.ldb;
-        src.m_valid = p.m0 - row0, src.n_valid = p.n0 - col0;
-        src.k_left = p.k0, src.nsteps = (p.k0 + Cfg::BK - 1) / Cfg::BK;
+        src.seg = segs + g.seg_begin, src.seg_end = segs + g.seg_end, src.c = c;
+        src.row0 = row0, src.col0 = col0;
+        src.m_valid = g.m0 - row0, src.n_valid = g.n0 - col0;
+        int ns = 0;
+        for (const P1Seg *s = src.seg; s < src.seg_end; s++)
+            ns += (s->k0 + Cfg::BK - 1) / Cfg::BK;
+        src.nsteps = ns;
+        src.open();
         const int mi_n = clampi((src.m_valid - wm0 + 7) / 8, 0, Cfg::MI);
         const int ni_n = clampi((src.n_valid - wn0 + 7) / 8, 0, Cfg::NI);
         double acc[Cfg::MI][Cfg::NI][2];
@@ -105,18 +136,19 @@ phase1_kernel(const P1Pair *__restrict__ pairs, const Unit *__restrict__ units, 
 #pragma unroll
             for (int ni = 0; ni < Cfg::NI; ni++)
                 acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-        mainloop<Cfg, true, B_KC>(src, smem, acc, wm0, wn0, mi_n, ni_n, src.m_valid >= Cfg::BM && src.n_valid >= Cfg::BN);
-        double *w = wbuf + p.w_off;
+        mainloop<Cfg, true, B_KC, true>(src, smem, s_alpha, acc, wm0, wn0, mi_n, ni_n,
+                                        src.m_valid >= Cfg::BM && src.n_valid >= Cfg::BN);
+        double *w = wbuf + g.w_off;
 #pragma unroll
         for (int mi = 0; mi < Cfg::MI; mi++)
 #pragma unroll
             for (int ni = 0; ni < Cfg::NI; ni++) {
                 const int r = row0 + wm0 + mi * 8 + lr, cc = col0 + wn0 + ni * 8 + lc * 2;
-                if (mi < mi_n && ni < ni_n && r < p.m0) {
-                    if (cc < p.n0)
-                        w[(size_t)r * p.n0 + cc] = p.alpha * acc[mi][ni][0];
-                    if (cc + 1 < p.n0)
-                        w[(size_t)r * p.n0 + cc + 1] = p.alpha * acc[mi][ni][1];
+                if (mi < mi_n && ni < ni_n && r < g.m0) {
+                    if (cc < g.n0)
+                        w[(size_t)r * g.wld + cc] = acc[mi][ni][0];
+                    if (cc + 1 < g.n0)
+                        w[(size_t)r * g.wld + cc + 1] = acc[mi][ni][1];
                 }
             }
         u = s_unit; // written before the barriers of the main loop
@@ -130,26 +162,29 @@ template <class Cfg, bool A_KC> struct P2Src {
     const double *wbuf;
     const double *a, *b;
     P2Seg nxt; // descriptor of the following segment, fetched one segment ahead
-    int lda, n0, row0, col0, m_valid, n_valid, k_left, nsteps;
+    int lda, wld, row0, col0, m_valid, n_valid, n_lo, n_hi, k_left, nsteps;
     __device__ int steps() const { return nsteps; }
     __device__ void use(const P2Seg &s) {
-        lda = s.lda;
+        lda = s.lda, wld = s.wld;
         a = A_KC ? s.a1 + (size_t)row0 * lda : s.a1 + row0;
-        b = wbuf + s.w_off + col0;
+        // tile column j is panel column col0 + j; the W panel of this segment holds [col_lo, col_hi) only
+        b = wbuf + s.w_off + (col0 - s.col_lo);
+        n_lo = max(0, s.col_lo - col0), n_hi = min(n_valid, s.col_hi - col0);
         k_left = s.klen;
         if (seg + 1 < seg_end)
             nxt = seg[1];
     }
     __device__ void open() { use(*seg); }
-    __device__ void issue(double *As, double *Bs) {
+    __device__ double issue(double *As, double *Bs) {
         load_tile<Cfg::BM, Cfg::THREADS, A_KC, Cfg::BK>(As, a, lda, m_valid, k_left);
-        load_tile<Cfg::BN, Cfg::THREADS, false, Cfg::BK>(Bs, b, n0, n_valid, k_left);
+        load_tile<Cfg::BN, Cfg::THREADS, false, Cfg::BK>(Bs, b, wld, n_hi, k_left, n_lo);
         k_left -= Cfg::BK;
         if (k_left > 0) {
             a += A_KC ? Cfg::BK : (size_t)Cfg::BK * lda;
-            b += (size_t)Cfg::BK * n0;
+            b += (size_t)Cfg::BK * wld;
         } else if (++seg < seg_end)
             use(nxt);
+        return 1.0;
     }
 };
 
@@ -172,7 +207,7 @@ phase2_kernel(const P2Window *__restrict__ wins, const P2Seg *__restrict__ segs,
         const P2Window win = wins[un.idx];
         P2Src<Cfg, A_KC> src;
         src.seg = segs + un.seg_begin, src.seg_end = segs + un.seg_end, src.wbuf = wbuf;
-        src.n0 = win.n0, src.row0 = un.row0, src.col0 = un.col0;
+        src.row0 = un.row0, src.col0 = un.col0;
         src.m_valid = win.m1 - src.row0, src.n_valid = win.n0 - src.col0;
         int ns = 0;
         for (const P2Seg *s = src.seg; s < src.seg_end; s++)
@@ -187,7 +222,8 @@ phase2_kernel(const P2Window *__restrict__ wins, const P2Seg *__restrict__ segs,
 #pragma unroll
             for (int ni = 0; ni < Cfg::NI; ni++)
                 acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-        mainloop<Cfg, A_KC, false>(src, smem, acc, wm0, wn0, mi_n, ni_n, src.m_valid >= Cfg::BM && src.n_valid >= Cfg::BN);
+        mainloop<Cfg, A_KC, false, false>(src, smem, nullptr, acc, wm0, wn0, mi_n, ni_n,
+                                          src.m_valid >= Cfg::BM && src.n_valid >= Cfg::BN);
         if (un.poff >= 0) {
             // deterministic mode: the K-chunk partial goes to its own tile slot; reduce_kernel sums
             // the slots of a sigma tile in chunk order
@@ -219,24 +255,6 @@ phase2_kernel(const P2Window *__restrict__ wins, const P2Seg *__restrict__ segs,
         }
         u = s_unit; // written before the barriers of the main loop
         __syncthreads();
-    }
-}
-
-// ------------------------------ W pre-sum -----------------------------------
-// sum_p A1 * W_p = A1 * (sum_p W_p) for pairs that share the sigma window and the operator
-// block A1: their W are added (memory-bound, in place into the first one) so phase 2 multiplies
-// by A1 once.
-__global__ void __launch_bounds__(256) wsum_kernel(const SumTask *__restrict__ tasks, int n_tasks,
-                                                   double *__restrict__ wbuf) {
-    for (int t = blockIdx.x; t < n_tasks; t += gridDim.x) {
-        const SumTask k = tasks[t];
-        double *d = wbuf + k.dst + k.start;
-        for (int64_t e = threadIdx.x; e < k.count; e += 256) {
-            double s = d[e];
-            for (int j = 0; j < k.nsrc; j++)
-                s += wbuf[k.src[j] + k.start + e];
-            d[e] = s;
-        }
     }
 }
 
@@ -278,15 +296,18 @@ reduce_kernel(const OutTile *__restrict__ tiles, int n_tiles, const int64_t *__r
 // Host side: tile configurations, unit lists, launches
 // ----------------------------------------------------------------------------
 // Tile configurations.  An output matrix is cut into 128-row tiles plus one 64-row strip for the
-// remainder, and into 64-column tiles plus 16- or 8-column strips for the remainder, so padding
-// waste stays at the 8-element granularity of the DMMA blocks.
+// remainder, and into 64-column tiles plus 16- or 8-column strips for the remainder; a remainder of
+// 1..8 columns widens the last 64-column tile to 72 instead of opening an 8-column strip that would
+// stream the whole A operand again for a ninth of the work.
 using Cfg0 = TileCfg<128, 64, 4, 2, 3, 2>; // 8 warps, 32x32 warp tiles (bulk of large sectors)
 using Cfg1 = TileCfg<64, 64, 2, 2, 3, 3>; // 4 warps, 32x32
 using Cfg2 = TileCfg<128, 16, 8, 1, 4>; // 8 warps, 16x16 (column remainders)
 using Cfg3 = TileCfg<64, 16, 4, 1, 4>;  // 4 warps, 16x16
-using Cfg4 = TileCfg<128, 8, 8, 1, 4>;  // 8 warps, 16x8  (skinny sigma windows, n0 <= 8)
+using Cfg4 = TileCfg<128, 8, 8, 1, 4>;  // 8 warps, 16x8  (narrow panels, width <= 8)
 using Cfg5 = TileCfg<64, 8, 4, 1, 4>;   // 4 warps, 16x8
-constexpr int NCFG = 6;
+using Cfg6 = TileCfg<128, 72, 8, 1, 3, 2>; // 8 warps, 16x72 (64 + a remainder of 1..8 columns)
+using Cfg7 = TileCfg<64, 72, 4, 1, 3, 3>;  // 4 warps, 16x72
+constexpr int NCFG = 8;
 
 struct CfgInfo {
     int bm, bn, threads, smem;
@@ -296,9 +317,13 @@ static const CfgInfo kCfg[NCFG] = {{Cfg0::BM, Cfg0::BN, Cfg0::THREADS, Cfg0::SME
                                    {Cfg2::BM, Cfg2::BN, Cfg2::THREADS, Cfg2::SMEM_BYTES},
                                    {Cfg3::BM, Cfg3::BN, Cfg3::THREADS, Cfg3::SMEM_BYTES},
                                    {Cfg4::BM, Cfg4::BN, Cfg4::THREADS, Cfg4::SMEM_BYTES},
-                                   {Cfg5::BM, Cfg5::BN, Cfg5::THREADS, Cfg5::SMEM_BYTES}};
+                                   {Cfg5::BM, Cfg5::BN, Cfg5::THREADS, Cfg5::SMEM_BYTES},
+                                   {Cfg6::BM, Cfg6::BN, Cfg6::THREADS, Cfg6::SMEM_BYTES},
+                                   {Cfg7::BM, Cfg7::BN, Cfg7::THREADS, Cfg7::SMEM_BYTES}};
 
-static inline int cfg_of(int bm, int bn) { return (bn == 64 ? 0 : bn == 16 ? 2 : 4) + (bm == 128 ? 0 : 1); }
+static inline int cfg_of(int bm, int bn) {
+    return (bn == 64 ? 0 : bn == 16 ? 2 : bn == 8 ? 4 : 6) + (bm == 128 ? 0 : 1);
+}
 
 struct Strip {
     int origin, tile; // first element, tile extent class
@@ -315,13 +340,22 @@ static std::vector<Strip> split_rows(int m) {
         out.push_back(Strip{r, 64});
     return out;
 }
-// columns: 64-column tiles, then 16- / 8-column strips for the remainder
+// columns: 64-column tiles (the last one 72 wide when 1..8 columns would be left over), then 16- / 8-column
+// strips for what remains
 static std::vector<Strip> split_cols(int n) {
+    static const bool wide = getenv("B2G_NO_TILE72") == nullptr;
     std::vector<Strip> out;
     int c = 0;
     while (n - c > 32) {
-        out.push_back(Strip{c, 64});
-        c += 64;
+        const int left = n - c - 64; // columns after a 64-wide tile here
+        const bool last64 = left <= 32; // no further 64-wide tile follows
+        if (wide && last64 && ((left >= 1 && left <= 8) || (left >= 17 && left <= 24))) {
+            out.push_back(Strip{c, 72});
+            c += 72;
+        } else {
+            out.push_back(Strip{c, 64});
+            c += 64;
+        }
     }
     while (n - c > 8) {
         out.push_back(Strip{c, 16});
@@ -341,19 +375,17 @@ struct LaunchGroup { // one kernel launch: units of one (phase, cfg, layout)
 
 struct TiledPlan {
     b2g_context *ctx = nullptr;
-    SumTask *d_sum = nullptr;
-    int n_sum = 0;
-    double sum_bytes = 0;
     // deterministic sigma accumulation
     OutTile *d_tiles = nullptr;
     int64_t *d_part_off = nullptr;
     double *d_pbuf = nullptr;
     int n_tiles = 0;
-    // sigma windows may overlap (a block and its sub-windows): tiles are ordered by the colour of
-    // their window in the interval-overlap graph and each colour is reduced by its own launch
+    // row panels may overlap in sigma (a block and its row sub-windows): tiles are ordered by the colour of
+    // their panel in the interval-overlap graph and each colour is reduced by its own launch
     std::vector<std::pair<int, int>> tile_ranges;
     size_t pbuf_doubles = 0;
-    P1Pair *d_p1 = nullptr;
+    P1Group *d_p1g = nullptr;
+    P1Seg *d_p1s = nullptr;
     P2Window *d_win = nullptr;
     P2Seg *d_seg = nullptr;
     double *d_wbuf = nullptr;
@@ -363,33 +395,36 @@ struct TiledPlan {
     std::vector<void *> to_free;
 };
 
+// the dynamic shared memory limit is a per-device function attribute: one bit per device ordinal
+template <class K> static int raise_smem_limit(K kern, int bytes, int device, std::atomic<uint64_t> &mask) {
+    const uint64_t bit = (uint64_t)1 << (device & 63);
+    if (!(mask.load(std::memory_order_acquire) & bit)) {
+        B2G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        mask.fetch_or(bit, std::memory_order_release);
+    }
+    return 0;
+}
+
 template <class Cfg, bool L> static int launch_p1(const LaunchGroup &g, const TiledPlan &tp, b2g_context *ctx,
                                                   cudaStream_t stream, unsigned int *counter, const double *c) {
     auto kern = phase1_kernel<Cfg, L>;
-    // the dynamic shared memory limit is a per-device function attribute: one bit per device ordinal
     static std::atomic<uint64_t> attr_mask{0};
-    const uint64_t bit = (uint64_t)1 << (ctx->device & 63);
-    if (!(attr_mask.load(std::memory_order_acquire) & bit)) {
-        B2G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_mask.fetch_or(bit, std::memory_order_release);
-    }
+    if (raise_smem_limit(kern, Cfg::SMEM_BYTES, ctx->device, attr_mask))
+        return 1;
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::THREADS, Cfg::SMEM_BYTES);
     const int grid = std::min(g.n_units, ctx->sm_count * std::max(per_sm, 1));
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tp.d_p1, g.d_units, g.n_units, counter, c, tp.d_wbuf);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tp.d_p1g, tp.d_p1s, g.d_units, g.n_units, counter, c,
+                                                                tp.d_wbuf);
     return 0;
 }
 template <class Cfg, bool L> static int launch_p2(const LaunchGroup &g, const TiledPlan &tp, b2g_context *ctx,
                                                   cudaStream_t stream, unsigned int *counter, double *v,
                                                   double scale) {
     auto kern = phase2_kernel<Cfg, L>;
-    // the dynamic shared memory limit is a per-device function attribute: one bit per device ordinal
     static std::atomic<uint64_t> attr_mask{0};
-    const uint64_t bit = (uint64_t)1 << (ctx->device & 63);
-    if (!(attr_mask.load(std::memory_order_acquire) & bit)) {
-        B2G_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_mask.fetch_or(bit, std::memory_order_release);
-    }
+    if (raise_smem_limit(kern, Cfg::SMEM_BYTES, ctx->device, attr_mask))
+        return 1;
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::THREADS, Cfg::SMEM_BYTES);
     const int grid = std::min(g.n_units, ctx->sm_count * std::max(per_sm, 1));
@@ -401,6 +436,22 @@ template <class Cfg, bool L> static int launch_p2(const LaunchGroup &g, const Ti
 } // namespace b2g
 
 using namespace b2g;
+
+namespace {
+struct Key4 {
+    uint64_t a, b, c, d;
+    bool operator==(const Key4 &o) const { return a == o.a && b == o.b && c == o.c && d == o.d; }
+};
+struct Key4Hash {
+    size_t operator()(const Key4 &k) const {
+        uint64_t h = k.a * 0x9E3779B97F4A7C15ull;
+        h = (h ^ (h >> 29)) + k.b * 0xBF58476D1CE4E5B9ull;
+        h = (h ^ (h >> 31)) + k.c * 0x94D049BB133111EBull;
+        h = (h ^ (h >> 27)) + k.d * 0xD6E8FEB86659FD93ull;
+        return (size_t)(h ^ (h >> 32));
+    }
+};
+} // namespace
 
 void b2g_tiled_destroy(void *h) {
     TiledPlan *tp = (TiledPlan *)h;
@@ -423,67 +474,250 @@ int b2g_tiled_build(b2g_plan *p) {
         return 0;
     const char *env_kc = getenv("B2G_KCHUNK");
     const int64_t kchunk = env_kc ? atoll(env_kc) : 2048;
+    static const bool merge_cols = getenv("B2G_NO_PANELS") == nullptr; // A/B switch: one panel per window
 
-    // ---- phase 1 descriptors + W workspace layout
-    std::vector<P1Pair> p1(n);
-    size_t woff = 0;
+    // ---- 1. sigma blocks: connected sets of overlapping windows; a window is (row, column) placed in its block
+    struct Win {
+        int64_t c_off;
+        int32_t m1, n0, ldc;
+        int64_t lo, hi;
+        int block, row, col, panel, layer;
+    };
+    std::unordered_map<Key4, int, Key4Hash> wid;
+    std::vector<Win> wv;
+    std::vector<int> pair_win(n, -1);
     for (size_t i = 0; i < n; i++) {
         const B2GPair &q = hp[i];
-        P1Pair &d = p1[i];
-        d.b0 = q.b0, d.w_off = (int64_t)woff, d.alpha = q.alpha0 * q.alpha1;
-        d.a_off = q.a0_off, d.lda = q.lda0, d.ldb = q.ldb0;
-        d.m0 = q.m0, d.n0 = q.n0, d.k0 = q.k0, d.tb0 = (q.flags & B2G_F_TB0) ? 1 : 0;
-        woff += (size_t)q.m0 * q.n0;
+        if (q.m0 == 0 || q.n0 == 0 || q.m1 == 0)
+            continue;
+        const Key4 key{(uint64_t)q.c1_off, (uint64_t)(uint32_t)q.m1, (uint64_t)(uint32_t)q.n0, (uint64_t)(uint32_t)q.ldc1};
+        auto it = wid.find(key);
+        if (it == wid.end()) {
+            it = wid.emplace(key, (int)wv.size()).first;
+            wv.push_back(Win{q.c1_off, q.m1, q.n0, q.ldc1, q.c1_off,
+                             q.c1_off + (int64_t)(q.m1 - 1) * q.ldc1 + q.n0, -1, 0, 0, -1, 0});
+        }
+        pair_win[i] = it->second;
+    }
+    {
+        std::vector<int> order(wv.size());
+        std::iota(order.begin(), order.end(), 0);
+        std::sort(order.begin(), order.end(), [&wv](int x, int y) { return wv[x].lo < wv[y].lo; });
+        int nb = 0;
+        int64_t cur_hi = 0, cur_lo = 0;
+        int cur_ld = 0;
+        bool uniform = true;
+        std::vector<int> members;
+        auto close = [&]() {
+            // a block whose windows share one pitch is a matrix: (row, col) of every window inside it
+            for (int w : members) {
+                wv[w].block = nb;
+                if (uniform && merge_cols) {
+                    wv[w].row = (int)((wv[w].lo - cur_lo) / cur_ld), wv[w].col = (int)((wv[w].lo - cur_lo) % cur_ld);
+                    if (wv[w].col + wv[w].n0 > cur_ld) // wraps around the pitch: not a sub-matrix
+                        wv[w].row = -1;
+                } else
+                    wv[w].row = -1;
+            }
+            members.clear();
+            nb++;
+        };
+        for (int w : order) {
+            if (!members.empty() && wv[w].lo >= cur_hi)
+                close();
+            if (members.empty())
+                cur_lo = wv[w].lo, cur_hi = wv[w].hi, cur_ld = wv[w].ldc, uniform = true;
+            else
+                cur_hi = std::max(cur_hi, wv[w].hi), uniform = uniform && wv[w].ldc == cur_ld;
+            members.push_back(w);
+        }
+        if (!members.empty())
+            close();
+    }
+    // ---- 2. row panels: windows of one block with the same row range (merged along the columns);
+    //         windows that overlap in columns inside a panel go to different layers (their W never share a slot)
+    struct Panel {
+        int64_t c_off; // sigma offset of (row 0, column col_lo)
+        int32_t m1, ldc, col_lo, col_hi;
+        std::vector<int> wins;
+    };
+    std::vector<Panel> panels;
+    {
+        std::map<std::tuple<int, int, int>, int> pid; // (block, row, m1)
+        for (size_t w = 0; w < wv.size(); w++) {
+            Win &x = wv[w];
+            if (x.row < 0) { // irregular: a panel of its own
+                x.panel = (int)panels.size(), x.col = 0;
+                panels.push_back(Panel{x.c_off, x.m1, x.ldc, 0, x.n0, {(int)w}});
+                continue;
+            }
+            auto key = std::make_tuple(x.block, x.row, x.m1);
+            auto it = pid.find(key);
+            if (it == pid.end()) {
+                it = pid.emplace(key, (int)panels.size()).first;
+                panels.push_back(Panel{x.c_off - x.col, x.m1, x.ldc, x.col, x.col + x.n0, {}});
+            }
+            Panel &pn = panels[it->second];
+            pn.col_lo = std::min(pn.col_lo, x.col), pn.col_hi = std::max(pn.col_hi, x.col + x.n0);
+            pn.wins.push_back((int)w);
+            x.panel = it->second;
+        }
+        for (Panel &pn : panels) {
+            if (pn.wins.size() > 1 || (pn.wins.size() == 1 && wv[pn.wins[0]].row >= 0)) {
+                // columns relative to the panel origin; layers by interval colouring over the column ranges
+                std::sort(pn.wins.begin(), pn.wins.end(), [&wv](int x, int y) { return wv[x].col < wv[y].col; });
+                std::vector<int> layer_end; // last column used per layer
+                for (int w : pn.wins) {
+                    int l = 0;
+                    while (l < (int)layer_end.size() && layer_end[l] > wv[w].col)
+                        l++;
+                    if (l == (int)layer_end.size())
+                        layer_end.push_back(0);
+                    layer_end[l] = wv[w].col + wv[w].n0;
+                    wv[w].layer = l;
+                }
+                pn.c_off += pn.col_lo;
+                for (int w : pn.wins)
+                    wv[w].col -= pn.col_lo;
+                pn.col_hi -= pn.col_lo, pn.col_lo = 0;
+            }
+        }
+    }
+    // ---- 3. phase-2 segments = (panel, layer, A1 block, layout); phase-1 groups = (segment, window, tb0)
+    struct HostSeg {
+        int panel, layer, ta1, lda1, m0;
+        const double *a1;
+        int64_t w_off;
+        int wld, col_lo, col_hi;
+    };
+    std::unordered_map<Key4, int, Key4Hash> sid;
+    std::vector<HostSeg> hsegs;
+    // (segment, window) -> group; a (segment, window) fed through both operand layouts of B0 needs two W slots:
+    // the second layout gets a twin segment (same A1, K longer by m0) so that no W element is written twice
+    struct HostGroup {
+        int seg, win, tb0;
+        std::vector<size_t> pairs;
+    };
+    std::unordered_map<Key4, int, Key4Hash> gid;
+    std::vector<HostGroup> hgroups;
+    std::unordered_map<int, int> twin;
+    auto seg_of = [&](int panel, int layer, const B2GPair &q, int variant) -> int {
+        const int ta1 = (q.flags & B2G_F_TA1) ? 1 : 0;
+        const Key4 sk{(uint64_t)(uintptr_t)q.a1, ((uint64_t)(uint32_t)panel << 32) | (uint32_t)q.lda1,
+                      ((uint64_t)(uint32_t)q.m0 << 32) | (uint32_t)layer, (uint64_t)(ta1 | (variant << 1))};
+        auto it = sid.find(sk);
+        if (it == sid.end()) {
+            it = sid.emplace(sk, (int)hsegs.size()).first;
+            hsegs.push_back(HostSeg{panel, layer, ta1, q.lda1, q.m0, q.a1, 0, 0, INT32_MAX, 0});
+        }
+        return it->second;
+    };
+    for (size_t i = 0; i < n; i++) {
+        if (pair_win[i] < 0)
+            continue;
+        const B2GPair &q = hp[i];
+        const Win &x = wv[pair_win[i]];
+        const int tb0 = (q.flags & B2G_F_TB0) ? 1 : 0;
+        int seg = seg_of(x.panel, x.layer, q, 0);
+        const Key4 gk{(uint64_t)(uint32_t)seg, (uint64_t)(uint32_t)pair_win[i], 0, 0};
+        auto it = gid.find(gk);
+        int g;
+        if (it == gid.end()) {
+            g = (int)hgroups.size();
+            gid.emplace(gk, g);
+            hgroups.push_back(HostGroup{seg, pair_win[i], tb0, {}});
+        } else {
+            g = it->second;
+            if (hgroups[g].tb0 != tb0) { // the other layout: same window, twin segment
+                seg = seg_of(x.panel, x.layer, q, 1);
+                const Key4 gk2{(uint64_t)(uint32_t)seg, (uint64_t)(uint32_t)pair_win[i], 0, 0};
+                auto it2 = gid.find(gk2);
+                if (it2 == gid.end()) {
+                    g = (int)hgroups.size();
+                    gid.emplace(gk2, g);
+                    hgroups.push_back(HostGroup{seg, pair_win[i], tb0, {}});
+                } else
+                    g = it2->second;
+            }
+        }
+        HostSeg &hs = hsegs[hgroups[g].seg];
+        hs.col_lo = std::min(hs.col_lo, x.col), hs.col_hi = std::max(hs.col_hi, x.col + x.n0);
+        hgroups[g].pairs.push_back(i);
+    }
+    // W panels: m0 x wld per segment, wld = the column span its groups cover (even, so that rows stay 16-byte
+    // aligned); columns of the span no group writes stay zero from the one memset below
+    size_t woff = 0;
+    for (HostSeg &hs : hsegs) {
+        hs.col_lo &= ~1;
+        hs.wld = ((hs.col_hi - hs.col_lo) + 1) & ~1;
+        hs.w_off = (int64_t)woff;
+        woff += (size_t)hs.m0 * hs.wld;
     }
     tp->wbuf_doubles = woff;
-
-    // ---- windows: pairs that accumulate into the same sigma window
-    std::map<std::tuple<int64_t, int, int, int>, int> wid;
-    std::vector<P2Window> wins;
-    std::vector<std::vector<size_t>> wpairs[2]; // [layout][window] -> pair indices
-    for (size_t i = 0; i < n; i++) {
-        const B2GPair &q = hp[i];
-        auto key = std::make_tuple(q.c1_off, q.m1, q.n0, q.ldc1);
-        auto it = wid.find(key);
-        int w;
-        if (it == wid.end()) {
-            w = (int)wins.size();
-            wid[key] = w;
-            wins.push_back(P2Window{q.c1_off, q.ldc1, q.m1, q.n0, 0});
-            wpairs[0].emplace_back(), wpairs[1].emplace_back();
-        } else
-            w = it->second;
-        wpairs[(q.flags & B2G_F_TA1) ? 1 : 0][w].push_back(i);
+    std::vector<P1Group> p1g;
+    std::vector<P1Seg> p1s;
+    p1g.reserve(hgroups.size()), p1s.reserve(n);
+    for (HostGroup &hg : hgroups) {
+        const HostSeg &hs = hsegs[hg.seg];
+        const Win &x = wv[hg.win];
+        P1Group g;
+        g.w_off = hs.w_off + (x.col - hs.col_lo), g.wld = hs.wld, g.m0 = hs.m0, g.n0 = x.n0;
+        g.seg_begin = (int)p1s.size();
+        // neighbours read the same wavefunction window (L2 reuse of c inside the group)
+        if (hg.pairs.size() > 1)
+            std::stable_sort(hg.pairs.begin(), hg.pairs.end(),
+                             [&hp](size_t a, size_t b) { return hp[a].a0_off < hp[b].a0_off; });
+        for (size_t i : hg.pairs) {
+            const B2GPair &q = hp[i];
+            p1s.push_back(P1Seg{q.b0, q.a0_off, q.alpha0 * q.alpha1, q.lda0, q.ldb0, q.k0, 0});
+        }
+        g.seg_end = (int)p1s.size(), g.pad = 0;
+        p1g.push_back(g);
     }
 
-    // ---- units
+    // ---- 4. units
     struct HostUnit {
         Unit u;
         double cost, flops;
     };
     std::map<std::tuple<int, int, int>, std::vector<HostUnit>> groups; // (phase, cfg, layout)
-    for (size_t i = 0; i < n; i++) {
-        const B2GPair &q = hp[i];
-        if (q.m0 == 0 || q.n0 == 0)
-            continue;
-        for (const Strip &rs : split_rows(q.m0))
-            for (const Strip &cs : split_cols(q.n0)) {
+    for (size_t gi = 0; gi < hgroups.size(); gi++) {
+        const HostGroup &hg = hgroups[gi];
+        const P1Group &g = p1g[gi];
+        int64_t ksum = 0;
+        for (size_t i : hg.pairs)
+            ksum += hp[i].k0;
+        for (const Strip &rs : split_rows(g.m0))
+            for (const Strip &cs : split_cols(g.n0)) {
                 const int c = cfg_of(rs.tile, cs.tile);
-                groups[std::make_tuple(1, c, p1[i].tb0)].push_back(
-                    HostUnit{Unit{(int)i, rs.origin, cs.origin, 0, 0, 0, -1}, (double)rs.tile * cs.tile * (q.k0 + 32),
-                             2.0 * std::min(rs.tile, q.m0 - rs.origin) * std::min(cs.tile, q.n0 - cs.origin) * q.k0});
+                groups[std::make_tuple(1, c, hg.tb0)].push_back(HostUnit{
+                    Unit{(int)gi, rs.origin, cs.origin, 0, 0, 0, -1},
+                    (double)rs.tile * cs.tile * (double)(ksum + 32 * (int64_t)hg.pairs.size()),
+                    2.0 * std::min(rs.tile, g.m0 - rs.origin) * std::min(cs.tile, g.n0 - cs.origin) * (double)ksum});
             }
     }
+    std::vector<P2Window> wins(panels.size());
+    for (size_t k = 0; k < panels.size(); k++)
+        wins[k] = P2Window{panels[k].c_off, panels[k].ldc, panels[k].m1, panels[k].col_hi - panels[k].col_lo, 0};
+    // segments of a panel, per layout, neighbours share the operator block (L2 reuse across K-chunks)
+    std::vector<std::vector<int>> pseg[2];
+    pseg[0].resize(panels.size()), pseg[1].resize(panels.size());
+    for (size_t k = 0; k < hsegs.size(); k++)
+        if (hsegs[k].col_hi > hsegs[k].col_lo)
+            pseg[hsegs[k].ta1][hsegs[k].panel].push_back((int)k);
+    for (int lay = 0; lay < 2; lay++)
+        for (auto &lst : pseg[lay])
+            std::sort(lst.begin(), lst.end(), [&hsegs](int x, int y) { return hsegs[x].a1 < hsegs[y].a1; });
     // K-chunk: 2048 for the big lists; shorter when the list is small so that phase 2 still
-    // spreads over the whole chip (few sigma windows, each with a long chain of short segments)
+    // spreads over the whole chip (few panels, each with a long chain of short segments)
     int64_t kchunk_eff = kchunk;
     if (!env_kc) {
         double tile_k = 0;
         for (int lay = 0; lay < 2; lay++)
-            for (size_t w = 0; w < wins.size(); w++) {
+            for (size_t w = 0; w < panels.size(); w++) {
                 double ks = 0;
-                for (size_t idx : wpairs[lay][w])
-                    ks += hp[idx].m0;
+                for (int k : pseg[lay][w])
+                    ks += hsegs[k].m0;
                 tile_k += ks * (double)split_rows(wins[w].m1).size() * (double)split_cols(wins[w].n0).size();
             }
         const double want_units = 24.0 * ctx->sm_count;
@@ -491,70 +725,42 @@ int b2g_tiled_build(b2g_plan *p) {
         kchunk_eff = (kchunk_eff + 15) / 16 * 16;
     }
     std::vector<P2Seg> segs;
-    std::vector<SumTask> sums;
-    const char *env_merge = getenv("B2G_NO_WSUM");
-    const bool merge_w = !(env_merge && env_merge[0] == '1');
-    const int64_t sum_chunk = 32768;
     for (int lay = 0; lay < 2; lay++)
-        for (size_t w = 0; w < wins.size(); w++) {
-            auto &lst = wpairs[lay][w];
+        for (size_t w = 0; w < panels.size(); w++) {
+            const std::vector<int> &lst = pseg[lay][w];
             if (lst.empty() || wins[w].m1 == 0 || wins[w].n0 == 0)
                 continue;
-            // neighbours share the operator block (pre-summed below; L2 reuse across K-chunks)
-            std::stable_sort(lst.begin(), lst.end(), [&hp](size_t x, size_t y) {
-                if (hp[x].a1 != hp[y].a1)
-                    return hp[x].a1 < hp[y].a1;
-                if (hp[x].lda1 != hp[y].lda1)
-                    return hp[x].lda1 < hp[y].lda1;
-                return hp[x].m0 < hp[y].m0;
-            });
             const std::vector<Strip> rsv = split_rows(wins[w].m1), csv = split_cols(wins[w].n0);
-            size_t s0 = segs.size();
-            int64_t ksum = 0;
-            auto flush = [&](size_t s1) {
-                if (s1 == s0)
-                    return;
-                for (const Strip &rs : rsv)
-                    for (const Strip &cs : csv)
+            // one filtered segment list per column tile: a tile skips the operator blocks whose W panel has
+            // nothing in its columns (block-sparse B)
+            for (const Strip &cs : csv) {
+                const int t_lo = cs.origin, t_hi = std::min(cs.origin + cs.tile, wins[w].n0);
+                size_t s0 = segs.size();
+                int64_t ksum = 0;
+                auto flush = [&](size_t s1) {
+                    if (s1 == s0)
+                        return;
+                    for (const Strip &rs : rsv)
                         groups[std::make_tuple(2, cfg_of(rs.tile, cs.tile), lay)].push_back(
                             HostUnit{Unit{(int)w, rs.origin, cs.origin, (int)s0, (int)s1, 0, -1},
                                      (double)rs.tile * cs.tile * (double)(ksum + 32),
-                                     2.0 * std::min(rs.tile, wins[w].m1 - rs.origin) *
-                                         std::min(cs.tile, wins[w].n0 - cs.origin) * (double)ksum});
-                s0 = s1, ksum = 0;
-            };
-            for (size_t z = 0; z < lst.size();) {
-                const B2GPair &q = hp[lst[z]];
-                // run of pairs with the same operator block: one segment, W summed beforehand
-                size_t z1 = z + 1;
-                while (merge_w && z1 < lst.size() && z1 - z < 4 && hp[lst[z1]].a1 == q.a1 && hp[lst[z1]].lda1 == q.lda1 &&
-                       hp[lst[z1]].m0 == q.m0)
-                    z1++;
-                if (q.m0 != 0) {
-                    const int64_t total = (int64_t)q.m0 * q.n0;
-                    for (size_t y = z + 1; y < z1; y += 3) { // up to 3 sources per task
-                        SumTask st{};
-                        st.dst = p1[lst[z]].w_off;
-                        st.nsrc = (int)std::min<size_t>(3, z1 - y);
-                        for (int j = 0; j < st.nsrc; j++)
-                            st.src[j] = p1[lst[y + j]].w_off;
-                        for (int64_t s = 0; s < total; s += sum_chunk) {
-                            st.start = s, st.count = std::min<int64_t>(sum_chunk, total - s);
-                            sums.push_back(st);
-                            tp->sum_bytes += 8.0 * st.count * (st.nsrc + 2);
-                        }
-                    }
-                    segs.push_back(P2Seg{q.a1, p1[lst[z]].w_off, q.lda1, q.m0});
-                    ksum += q.m0;
+                                     2.0 * std::min(rs.tile, wins[w].m1 - rs.origin) * (t_hi - t_lo) * (double)ksum});
+                    s0 = s1, ksum = 0;
+                };
+                for (int k : lst) {
+                    const HostSeg &hs = hsegs[k];
+                    if (hs.col_hi <= t_lo || hs.col_lo >= t_hi || hs.m0 == 0)
+                        continue;
+                    segs.push_back(P2Seg{hs.a1, hs.w_off, hs.lda1, hs.m0, hs.wld, hs.col_lo, hs.col_hi, 0});
+                    ksum += hs.m0;
                     if (ksum >= kchunk_eff)
                         flush(segs.size());
                 }
-                z = z1;
+                flush(segs.size());
             }
-            flush(segs.size());
         }
 
-    // ---- upload
+    // ---- 5. upload
     auto upload = [&](const void *src, size_t bytes, void **dst) -> int {
         if (b2g_dmalloc(ctx, dst, bytes))
             return 1;
@@ -563,32 +769,32 @@ int b2g_tiled_build(b2g_plan *p) {
             B2G_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
         return 0;
     };
-    if (upload(p1.data(), p1.size() * sizeof(P1Pair), (void **)&tp->d_p1))
+    if (upload(p1g.data(), p1g.size() * sizeof(P1Group), (void **)&tp->d_p1g))
+        return 1;
+    if (upload(p1s.data(), p1s.size() * sizeof(P1Seg), (void **)&tp->d_p1s))
         return 1;
     if (upload(wins.data(), wins.size() * sizeof(P2Window), (void **)&tp->d_win))
         return 1;
     if (upload(segs.data(), segs.size() * sizeof(P2Seg), (void **)&tp->d_seg))
         return 1;
-    // at most 4 pairs are merged per run, so every destination range belongs to exactly one task
-    tp->n_sum = (int)sums.size();
-    if (upload(sums.data(), sums.size() * sizeof(SumTask), (void **)&tp->d_sum))
-        return 1;
     if (b2g_dmalloc(ctx, (void **)&tp->d_wbuf, std::max<size_t>(tp->wbuf_doubles, 2) * sizeof(double)))
         return 1;
     tp->to_free.push_back(tp->d_wbuf);
+    // phase 1 overwrites the column range of every group on every matvec; what no group covers must read as zero
+    B2G_CUDA(cudaMemsetAsync(tp->d_wbuf, 0, std::max<size_t>(tp->wbuf_doubles, 2) * sizeof(double), ctx->stream));
     // deterministic sigma accumulation: one partial slot per phase-2 unit, grouped by sigma tile
     // (a tile collects partials from both operand layouts), slots in K-chunk order
     const char *env_atomic = getenv("B2G_ATOMIC_SIGMA");
     std::vector<OutTile> tiles;
     std::vector<int64_t> part_off;
     if (!(env_atomic && env_atomic[0] == '1')) {
-        std::map<std::tuple<int, int, int>, std::vector<std::pair<int, HostUnit *>>> by_tile; // (win,row0,col0)
+        std::map<std::tuple<int, int, int>, std::vector<std::pair<int, HostUnit *>>> by_tile; // (panel,row0,col0)
         for (auto &kv : groups)
             if (std::get<0>(kv.first) == 2)
                 for (HostUnit &hu : kv.second)
                     by_tile[std::make_tuple(hu.u.idx, hu.u.row0, hu.u.col0)].push_back(
                         std::make_pair(std::get<1>(kv.first), &hu));
-        // colour the windows so that windows sharing sigma elements never share a launch
+        // colour the panels so that panels sharing sigma elements never share a launch
         std::vector<int> colour(wins.size(), 0);
         {
             std::vector<int> order(wins.size());
@@ -626,10 +832,8 @@ int b2g_tiled_build(b2g_plan *p) {
         for (auto &to : tile_order) {
             auto kvit = by_tile.find(to.second);
             auto &kv = *kvit;
-            if (tp->tile_ranges.empty() || to.first != (int)tp->tile_ranges.size() - 1) {
-                while ((int)tp->tile_ranges.size() <= to.first)
-                    tp->tile_ranges.push_back(std::make_pair((int)tiles.size(), (int)tiles.size()));
-            }
+            while ((int)tp->tile_ranges.size() <= to.first)
+                tp->tile_ranges.push_back(std::make_pair((int)tiles.size(), (int)tiles.size()));
             auto &lst = kv.second;
             std::stable_sort(lst.begin(), lst.end(),
                              [](const std::pair<int, HostUnit *> &x, const std::pair<int, HostUnit *> &y) {
@@ -681,7 +885,7 @@ int b2g_tiled_build(b2g_plan *p) {
         return 1;
     tp->to_free.push_back(tp->d_counters);
     B2G_CUDA(cudaStreamSynchronize(ctx->stream));
-    p->stats.launches = (int64_t)tp->groups.size() + 1;
+    p->stats.launches = (int64_t)tp->groups.size() + (int64_t)tp->tile_ranges.size();
     p->stats.n_large = (int64_t)n, p->stats.n_small = 0;
     return 0;
 }
@@ -739,25 +943,15 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
     if (fork)
         B2G_CUDA(cudaEventRecord(ctx->fork_ev, ctx->stream));
     int gi = 0;
-    bool summed = false;
+    bool phase2_open = false;
     for (const LaunchGroup &g : tp->groups) {
-        if (g.phase == 2 && !summed) {
-            summed = true;
+        if (g.phase == 2 && !phase2_open) { // every W panel is complete before the first phase-2 launch
+            phase2_open = true;
             if (fork) {
                 if (join())
                     return 1;
-            }
-            if (tp->n_sum > 0) {
-                if (begin("wsum", 0.0, tp->n_sum))
-                    return 1;
-                wsum_kernel<<<std::min(tp->n_sum, ctx->sm_count * 8), 256, 0, ctx->stream>>>(tp->d_sum, tp->n_sum,
-                                                                                             tp->d_wbuf);
-                ctx->launches++;
-                if (end())
-                    return 1;
-            }
-            if (fork)
                 B2G_CUDA(cudaEventRecord(ctx->fork_ev, ctx->stream));
+            }
         }
         cudaStream_t gs = ctx->stream;
         const bool side = fork_all || (fork_small && g.flops < fork_small_below);
@@ -788,6 +982,10 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
         B2G_DISPATCH(1, 4, 1, (launch_p1<Cfg4, true>(g, *tp, ctx, gs, counter, c_dev)))
         B2G_DISPATCH(1, 5, 0, (launch_p1<Cfg5, false>(g, *tp, ctx, gs, counter, c_dev)))
         B2G_DISPATCH(1, 5, 1, (launch_p1<Cfg5, true>(g, *tp, ctx, gs, counter, c_dev)))
+        B2G_DISPATCH(1, 6, 0, (launch_p1<Cfg6, false>(g, *tp, ctx, gs, counter, c_dev)))
+        B2G_DISPATCH(1, 6, 1, (launch_p1<Cfg6, true>(g, *tp, ctx, gs, counter, c_dev)))
+        B2G_DISPATCH(1, 7, 0, (launch_p1<Cfg7, false>(g, *tp, ctx, gs, counter, c_dev)))
+        B2G_DISPATCH(1, 7, 1, (launch_p1<Cfg7, true>(g, *tp, ctx, gs, counter, c_dev)))
         B2G_DISPATCH(2, 0, 0, (launch_p2<Cfg0, true>(g, *tp, ctx, gs, counter, v_dev, scale)))
         B2G_DISPATCH(2, 0, 1, (launch_p2<Cfg0, false>(g, *tp, ctx, gs, counter, v_dev, scale)))
         B2G_DISPATCH(2, 1, 0, (launch_p2<Cfg1, true>(g, *tp, ctx, gs, counter, v_dev, scale)))
@@ -800,6 +998,10 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
         B2G_DISPATCH(2, 4, 1, (launch_p2<Cfg4, false>(g, *tp, ctx, gs, counter, v_dev, scale)))
         B2G_DISPATCH(2, 5, 0, (launch_p2<Cfg5, true>(g, *tp, ctx, gs, counter, v_dev, scale)))
         B2G_DISPATCH(2, 5, 1, (launch_p2<Cfg5, false>(g, *tp, ctx, gs, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 6, 0, (launch_p2<Cfg6, true>(g, *tp, ctx, gs, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 6, 1, (launch_p2<Cfg6, false>(g, *tp, ctx, gs, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 7, 0, (launch_p2<Cfg7, true>(g, *tp, ctx, gs, counter, v_dev, scale)))
+        B2G_DISPATCH(2, 7, 1, (launch_p2<Cfg7, false>(g, *tp, ctx, gs, counter, v_dev, scale)))
 #undef B2G_DISPATCH
         if (rc)
             return rc;

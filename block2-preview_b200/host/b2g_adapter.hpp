@@ -596,6 +596,11 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
                 throw std::runtime_error("b2g: iadd list has chained pairs");
             } else
                 outp.insert(outp.end(), q->batch[1]->c.begin(), q->batch[1]->c.end());
+        vector<b2g_tp_term> terms;
+        for (auto &tv : gopf->collector->iadd_terms)
+            terms.insert(terms.end(), tv.begin(), tv.end());
+        for (auto &tm : terms)
+            outp.push_back(tm.c);
         std::sort(outp.begin(), outp.end());
         vector<shared_ptr<SparseMatrix<S, FL>>> outs;
         std::unordered_map<const void *, char> seen;
@@ -631,6 +636,12 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
                 session->iadd_entries += (size_t)st.entries;
                 opf->seq->cumulative_nflop += (size_t)st.nflop_mnk;
             }
+        if (rc == 0 && !terms.empty()) {
+            rc = b2g_tensor_product_execute(session->ctx, (int64_t)terms.size(), terms.data(), B2G_OPERANDS_HOST,
+                                            B2G_DST_ZERO, &st);
+            session->iadd_entries += (size_t)st.entries;
+            opf->seq->cumulative_nflop += (size_t)st.nflop_mnk;
+        }
         store().clear_map();
         if (rc != 0) {
             gopf->collector->end_iadd();
@@ -658,6 +669,9 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
             for (auto &q : gopf->collector->iadd_seqs)
                 if (q->batch[1]->gp.size() != 0)
                     q->auto_perform();
+            for (auto &tm : terms) // the eager reference routine on every block descriptor
+                GMatrixFunctions<FL>::iadd(GMatrix<FL>(tm.c, tm.conja ? tm.an : tm.am, tm.conja ? tm.am : tm.an),
+                                           GMatrix<FL>((FL *)tm.a, tm.am, tm.an), tm.scale, tm.conja != 0);
             session->max_iadd_err = max(session->max_iadd_err, rel_diff(gpu, outs));
             for (size_t z = 0; z < outs.size(); z++)
                 memcpy(outs[z]->data, gpu[z].data(), sizeof(double) * outs[z]->total_memory);

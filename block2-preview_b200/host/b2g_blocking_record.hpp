@@ -33,16 +33,19 @@ struct TermCollector {
     // intermediates / numerical_transform: the iadd calls of the stock walk (core/tensor_functions.hpp:2404-2517),
     // recorded per walking thread the same way
     bool iadd_active = false;
-    vector<shared_ptr<BatchGEMMSeq<double>>> iadd_seqs;
+    vector<shared_ptr<BatchGEMMSeq<double>>> iadd_seqs; // additions with a block factor != 1 (GEMM form)
+    vector<vector<b2g_tp_term>> iadd_terms;             // c_block += f * op(b_block), one descriptor per block
     void begin_iadd() {
-        iadd_seqs.assign((size_t)max(1, threading->n_threads_global), nullptr);
+        const size_t nt = (size_t)max(1, threading->n_threads_global);
+        iadd_seqs.assign(nt, nullptr);
         for (auto &q : iadd_seqs)
             q = make_shared<BatchGEMMSeq<double>>(0, SeqTypes::Auto);
+        iadd_terms.assign(nt, vector<b2g_tp_term>());
         iadd_active = true;
     }
     void end_iadd() {
         iadd_active = false;
-        iadd_seqs.clear();
+        iadd_seqs.clear(), iadd_terms.clear();
     }
     void clear() {
         for (auto &v : per_thread)
@@ -107,8 +110,39 @@ template <typename S> struct GPUOperatorFunctions : OperatorFunctions<S, double>
               bool conj = false) const override {
         if (!collector->iadd_active)
             return Base::iadd(a, b, scale, conj);
-        SeqSwap sw(const_cast<GPUOperatorFunctions *>(this)->seq, collector->iadd_seqs.at(threading->get_thread_id()));
-        Base::iadd(a, b, scale, conj);
+        const int tid = threading->get_thread_id();
+        if (a->factor != (FL)1.0 || a->total_memory >= (size_t)INT32_MAX) { // rare: keep the recorded GEMM form
+            SeqSwap sw(const_cast<GPUOperatorFunctions *>(this)->seq, collector->iadd_seqs.at(tid));
+            return Base::iadd(a, b, scale, conj);
+        }
+        // One descriptor per sector block instead of the per-row GEMM groups of the recorder: the block walk of
+        // the stock method (core/operator_functions.hpp:135-174), emitting c_block += f * op(b_block) as a
+        // tensor-product term with the 1 x 1 unit block as second factor.
+        if (abs(b->factor * scale) < TINY)
+            return;
+        static const double one = 1.0;
+        vector<b2g_tp_term> &out = collector->iadd_terms.at(tid);
+        b2g_tp_term t;
+        t.b = &one, t.bm = t.bn = 1, t.conjb = 0, t.reserved = 0;
+        if (a->info == b->info && !conj) {
+            t.a = b->data, t.c = a->data, t.am = 1, t.an = (int32_t)a->total_memory, t.cn = (int32_t)a->total_memory;
+            t.conja = 0, t.scale = scale * b->factor;
+            out.push_back(t);
+            return;
+        }
+        const S bdq = b->info->delta_quantum;
+        for (int ia = 0, ib; ia < a->info->n; ia++) {
+            const S bra = a->info->quanta[ia].get_bra(a->info->delta_quantum), ket = a->info->quanta[ia].get_ket();
+            const S bq = conj ? bdq.combine(ket, bra) : bdq.combine(bra, ket);
+            if (bq == S(S::invalid) || (ib = b->info->find_state(bq)) == -1)
+                continue;
+            FL factor = scale * b->factor;
+            if (conj)
+                factor *= cg->transpose_cg(bdq, bra, ket);
+            const GMatrix<FL> ma = (*a)[ia], mb = (*b)[ib];
+            t.a = mb.data, t.c = ma.data, t.am = mb.m, t.an = mb.n, t.cn = ma.n, t.conja = conj ? 1 : 0, t.scale = factor;
+            out.push_back(t);
+        }
     }
     void tensor_product(uint8_t conj, const shared_ptr<SparseMatrix<S, FL>> &a, const shared_ptr<SparseMatrix<S, FL>> &b,
                         const shared_ptr<SparseMatrix<S, FL>> &c, FL scale = 1.0) const override {

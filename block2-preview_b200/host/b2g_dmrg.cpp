@@ -26,6 +26,7 @@ struct Args {
     string shm = "b2g";
     bool compare = false, verify = false, gpu_rotate = true, gpu_contract = true, gpu_diag = true, gpu_iadd = true,
          host_mirror = false, pin = true, cpu_only = false, classic = false;
+    int restart_sweeps = 0; // --compare: zero-noise sweeps both arms run from the CPU arm's final MPS (same state)
     int noise_sweeps = 2;   // sweeps per noise level: {noise x k, 0.1 noise x k, 0 ...}
     double dav_thrd = 0;    // > 0: Davidson threshold of every sweep (default: the reference's noise-derived schedule)
     double conv = 1e-7, noise = 1e-5;
@@ -98,9 +99,57 @@ static RunResult run_dmrg(const Args &args, const shared_ptr<MPO<S, double>> &mp
     r.total = t.get_time();
     for (auto &e : dmrg->energies)
         r.energies.push_back((double)e[0]);
+    if (!gpu && args.restart_sweeps > 0) {
+        // keep the converged state of the CPU arm on disk under its own tag: both arms continue from it
+        shared_ptr<MPS<S, double>> cp = mps->deep_copy("B2GEND");
+        cp->info->save_data(frame_<double>()->mps_dir + "/B2GEND-mps_info.bin");
+        cp->info->deallocate();
+    }
     mps_info->deallocate();
     me->remove_partition_files();
     return r;
+}
+
+// Zero-noise sweeps from the state the CPU arm ended in (tag B2GEND), on a private copy: the two arms start from
+// the SAME MPS, so the energy of every sweep is comparable to rounding (no random initial state, no noise draws).
+template <typename S>
+static vector<double> continue_dmrg(const Args &args, const shared_ptr<MPO<S, double>> &mpo, bool gpu) {
+    shared_ptr<MPSInfo<S>> info = make_shared<MPSInfo<S>>(0);
+    info->load_data(frame_<double>()->mps_dir + "/B2GEND-mps_info.bin");
+    info->load_mutable();
+    shared_ptr<MPS<S, double>> mps = make_shared<MPS<S, double>>(info);
+    mps->load_data();
+    mps->load_mutable();
+    info->tag = gpu ? "B2GCG" : "B2GCR";
+    info->save_mutable();
+    mps->save_mutable();
+    mps->save_data();
+    mps->deallocate();
+    info->deallocate_mutable();
+    shared_ptr<MovingEnvironment<S, double, double>> me =
+        make_shared<MovingEnvironment<S, double, double>>(mpo, mps, mps, "DMRG");
+    me->init_environments(false);
+    me->delayed_contraction = OpNamesSet::normal_ops();
+    me->cached_contraction = true;
+    vector<ubond_t> bdims = {(ubond_t)args.bond};
+    vector<double> noises = {0.0};
+    shared_ptr<DMRG<S, double, double>> dmrg;
+    if (gpu)
+        dmrg = make_shared<b2g_host::GPUDMRG<S>>(me, bdims, noises);
+    else
+        dmrg = make_shared<DMRG<S, double, double>>(me, bdims, noises);
+    dmrg->iprint = 2;
+    dmrg->noise_type = NoiseTypes::DensityMatrix;
+    dmrg->decomp_type = DecompositionTypes::DensityMatrix;
+    dmrg->davidson_soft_max_iter = 4000;
+    dmrg->davidson_conv_thrds = vector<double>(1, args.dav_thrd > 0 ? args.dav_thrd : 1e-10);
+    dmrg->solve(args.restart_sweeps, mps->center == 0, 0.0);
+    vector<double> e;
+    for (auto &x : dmrg->energies)
+        e.push_back((double)x[0]);
+    info->deallocate();
+    me->remove_partition_files();
+    return e;
 }
 
 int main(int argc, char **argv) {
@@ -131,6 +180,7 @@ int main(int argc, char **argv) {
         else if (k == "--no-gpu-iadd") a.gpu_iadd = false;
         else if (k == "--noise-sweeps") a.noise_sweeps = atoi(nxt().c_str());
         else if (k == "--dav-thrd") a.dav_thrd = atof(nxt().c_str());
+        else if (k == "--restart-sweeps") a.restart_sweeps = atoi(nxt().c_str());
         else if (k == "--classic") a.classic = true; // ClassicParallelMPO instead of ParallelMPO (NewScheme)
         else if (k == "--cpu-only") a.cpu_only = true; // the stock CPU path alone (sweep-time baseline)
         else if (k == "--host-mirror") a.host_mirror = true;
@@ -187,9 +237,14 @@ int main(int argc, char **argv) {
             cout.setstate(ios::failbit); // like MPICommunicator (parallel_mpi.hpp:60-61)
     }
     RunResult ref;
+    vector<double> cont_ref, cont_gpu;
     if (a.compare) {
         printf("=== reference CPU path (stock TensorFunctions, %d threads) ===\n", a.threads);
         ref = run_dmrg<S>(a, mpo, hamil, target, false);
+        if (a.restart_sweeps > 0) {
+            printf("=== reference CPU path, %d zero-noise sweeps from its own final state ===\n", a.restart_sweeps);
+            cont_ref = continue_dmrg<S>(a, mpo, false);
+        }
     }
     if (a.cpu_only) {
         if (!a.compare)
@@ -215,6 +270,16 @@ int main(int argc, char **argv) {
     if (a.pin)
         session->pin_stacks();
     RunResult gpu = run_dmrg<S>(a, mpo, hamil, target, true);
+    double restart_diff = 0;
+    if (a.compare && a.restart_sweeps > 0) {
+        printf("=== GPU path, %d zero-noise sweeps from the CPU arm's final state ===\n", a.restart_sweeps);
+        cont_gpu = continue_dmrg<S>(a, mpo, true);
+        for (size_t i = 0; i < min(cont_gpu.size(), cont_ref.size()); i++) {
+            printf("RESTART SWEEP %zu E_gpu=%.12f E_ref=%.12f diff=%.3e\n", i, cont_gpu[i], cont_ref[i],
+                   cont_gpu[i] - cont_ref[i]);
+            restart_diff = max(restart_diff, fabs(cont_gpu[i] - cont_ref[i]));
+        }
+    }
     for (size_t i = 0; i < gpu.energies.size(); i++) {
         if (a.compare && i < ref.energies.size())
             printf("SWEEP %zu E_gpu=%.12f E_ref=%.12f diff=%.3e\n", i, gpu.energies[i], ref.energies[i],
@@ -234,7 +299,7 @@ int main(int argc, char **argv) {
     b2g_resident_stats(session->ctx, &res_hit, &res_mirrored);
     printf("{\"mode\": \"b2g_dmrg\", \"ranks\": %d, \"davidson\": \"%s\", \"bond\": %d, \"seed\": %d, \"sweeps\": %zu, "
            "\"t_gpu\": %.3f, \"t_ref\": %.3f, \"threads\": %d, \"e_gpu\": %.12f, \"e_ref\": %.12f, "
-           "\"max_sweep_diff\": %.3e, \"final_diff\": %.3e, "
+           "\"max_sweep_diff\": %.3e, \"final_diff\": %.3e, \"restart_sweeps\": %zu, \"max_restart_sweep_diff\": %.3e, "
            "\"plans\": %zu, \"host_matvecs\": %zu, \"t_plan\": %.3f, \"t_host_matvec\": %.3f, \"launches\": %lld, "
            "\"matvec_sites_verified\": %zu, \"max_matvec_rel_err\": %.3e, \"gpu_rotate\": %d, \"rotations\": %zu, "
            "\"t_rotate\": %.3f, \"t_rotate_download\": %.3f, \"rotate_gflop\": %.3f, \"max_rotate_rel_err\": %.3e, "
@@ -250,6 +315,7 @@ int main(int argc, char **argv) {
            gpu.energies.empty() ? 0.0 : gpu.energies.back(), ref.energies.empty() ? 0.0 : ref.energies.back(),
            maxdiff,
            (a.compare && !gpu.energies.empty() && !ref.energies.empty()) ? gpu.energies.back() - ref.energies.back() : 0.0,
+           min(cont_gpu.size(), cont_ref.size()), restart_diff,
            session->n_plan, session->n_matvec, session->t_plan, session->t_matvec,
            (long long)b2g_context_launches(session->ctx), session->n_verified, session->max_matvec_err,
            (int)a.gpu_rotate, session->n_rotate, session->t_rotate, session->t_rotate_download,

@@ -137,9 +137,11 @@ def shared_operator_list(rng, reps=(1, 2, 4, 5, 9), dims=((70, 33), (9, 140), (1
     return d
 
 
-@pytest.mark.parametrize("no_wsum", ["0", "1"])
-def test_shared_operator_blocks_are_merged_correctly(b2g, ctx, monkeypatch, no_wsum):
-    monkeypatch.setenv("B2G_NO_WSUM", no_wsum)
+@pytest.mark.parametrize("no_panels", ["0", "1"])
+def test_shared_operator_blocks_are_merged_correctly(b2g, ctx, monkeypatch, no_panels):
+    """Pairs that feed one sigma window through the same operator block A1 are summed inside phase 1 (K-segments
+    of one GEMM with per-segment factors); B2G_NO_PANELS=1 keeps one panel per window."""
+    monkeypatch.setenv("B2G_NO_PANELS", no_panels)
     d = shared_operator_list(np.random.default_rng(33))
     want = sd.replay(d, nthreads=4)
     plan = b2g.SeqPlan.from_seqfile(ctx, as_seqfile(b2g, d), d.arenas)
@@ -150,8 +152,88 @@ def test_shared_operator_blocks_are_merged_correctly(b2g, ctx, monkeypatch, no_w
     plan.close()
 
 
+def sigma_block_list(rng, blocks=((150, 71), (40, 200), (9, 9), (130, 81), (64, 1047 // 8), (300, 2))):
+    """Sigma blocks cut into column sub-windows, row sub-windows and a full-block window, as the two-site
+    wavefunction blocks of the reference are (batch_gemm.hpp:952-1022: &c(cst, 0) / &c(0, cst) with ld = block
+    width); the windows of one row range share a pool of operator blocks A1, every (window, A1) has 1..5 pairs
+    with different factors, operand layouts and K lengths.  Exercises the row-panel merge of phase 2 (W panels
+    with column spans, layers for overlapping column ranges, block-sparse K lists) and the 72-wide tiles."""
+    rows, coff, voff, aoff = [], 0, 0, 0
+
+    def new_block(nelem):
+        nonlocal aoff
+        o = aoff
+        aoff += nelem
+        return o
+    for (R, C) in blocks:
+        cuts = sorted(set([0, C] + [int(x) for x in rng.integers(1, C, size=min(3, C - 1))])) if C > 1 else [0, C]
+        col_wins = [(0, R, cuts[i], cuts[i + 1] - cuts[i]) for i in range(len(cuts) - 1)]
+        wins = col_wins + [(0, R, 0, C)]
+        if C > 3:
+            wins.append((0, R, cuts[1] // 2, max(1, (C - cuts[1] // 2) // 2)))  # overlaps its neighbours
+        if R > 8:
+            wins += [(0, R // 2, 0, C), (R // 2, R - R // 2, 0, C)]           # row sub-windows
+        pools = {}
+        for (r0, m1, c0, n0) in wins:
+            key = (r0, m1)
+            if key not in pools:
+                pools[key] = []
+                for _ in range(5):
+                    ta1, m0 = int(rng.integers(2)), int(rng.integers(1, 70))
+                    lda1 = (m1 if ta1 else m0) + int(rng.integers(0, 2))
+                    pools[key].append((new_block(((m0 if ta1 else m1) - 1) * lda1 + (m1 if ta1 else m0)), ta1, m0, lda1))
+            for z in rng.choice(5, size=int(rng.integers(2, 6)), replace=False):
+                a1_off, ta1, m0, lda1 = pools[key][z]
+                for _ in range(int(rng.integers(1, 6))):
+                    k0, tb0 = int(rng.integers(1, 60)), int(rng.integers(2))
+                    ldb0 = (k0 if tb0 else n0) + int(rng.integers(0, 2))
+                    lda0 = k0 + int(rng.integers(0, 3))
+                    b0_off = new_block(((n0 if tb0 else k0) - 1) * ldb0 + (k0 if tb0 else n0))
+                    rows.append(dict(ta0=0, tb0=tb0, m0=m0, n0=n0, k0=k0, lda0=lda0, ldb0=ldb0, ldc0=n0, ta1=ta1, tb1=0,
+                                     m1=m1, n1=n0, k1=m0, lda1=lda1, ldb1=n0, ldc1=C,
+                                     alpha0=float(rng.choice([1.0, -1.0, 0.5])), beta0=0.0,
+                                     alpha1=float(rng.standard_normal()), beta1=1.0, a0_off=coff, b0_arena=0,
+                                     b0_off=b0_off, a1_arena=0, a1_off=a1_off, c1_off=voff + r0 * C + c0, w_off=0))
+                    coff += (m0 - 1) * lda0 + k0
+        voff += R * C
+    order = rng.permutation(len(rows))
+    rows = [rows[i] for i in order]
+    p = {k: np.array([r[k] for r in rows]) for k in rows[0]}
+    for k in sd.I32_NAMES:
+        p[k] = p[k].astype(np.int32)
+    for k in sd.I64_NAMES:
+        p[k] = p[k].astype(np.int64)
+    mw = int((p["m0"].astype(np.int64) * p["n0"]).max())
+    nf = int((p["m0"].astype(np.int64) * p["n0"] * p["k0"] + p["m1"].astype(np.int64) * p["n1"] * p["k1"]).sum())
+    d = sd.SeqDump(npairs=len(rows), csize=coff, vsize=voff, max_work=mw, nflop_mnk=nf, site=0, bond_dim=0,
+                   n_sites=0, ndav_ref=0, has_eigs=False, e_ref=0.0, const_e=0.0, t_ref_matvec=0.0, conv_thrd=0.0,
+                   arena_sizes=np.array([aoff], dtype=np.int64), p=p)
+    d.arenas = rng.standard_normal(aoff)
+    d.c = rng.standard_normal(coff)
+    return d
+
+
+@pytest.mark.parametrize("env", [{}, {"B2G_NO_PANELS": "1"}, {"B2G_NO_TILE72": "1"}, {"B2G_KCHUNK": "64"},
+                                 {"B2G_ATOMIC_SIGMA": "1"}])
+def test_sigma_blocks_with_sub_windows_merge_into_row_panels(b2g, ctx, monkeypatch, env):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for seed in (51, 52):
+        d = sigma_block_list(np.random.default_rng(seed))
+        want = sd.replay(d, nthreads=4)
+        plan = b2g.SeqPlan.from_seqfile(ctx, as_seqfile(b2g, d), d.arenas)
+        got = np.zeros(d.vsize)
+        plan(d.c, got, 1.0)
+        assert rel(got, want) < TOL, (seed, env)
+        again = np.zeros(d.vsize)
+        plan(d.c, again, 1.0)
+        if "B2G_ATOMIC_SIGMA" not in env:
+            assert np.array_equal(got, again)  # W panels are rebuilt, not re-added; fixed summation order
+        plan.close()
+
+
 def test_matvec_is_repeatable_on_one_plan(b2g, ctx):
-    """W is pre-summed in place: a second replay on the same plan must rebuild it, not re-add it."""
+    """A second replay on the same plan must rebuild the W panels, not add to them."""
     d = shared_operator_list(np.random.default_rng(34))
     plan = b2g.SeqPlan.from_seqfile(ctx, as_seqfile(b2g, d), d.arenas)
     a, b_ = np.zeros(d.vsize), np.zeros(d.vsize)
