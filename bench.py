@@ -95,6 +95,35 @@ def workload_config(full) -> dict:
             "operator_bytes": 8 * full.operand_doubles, "flop_per_step": full.flops}
 
 
+def small_sector(b2g, torch, ctx, dev, stream, peaks, reps=20):
+    path = os.path.join(ROOT, "workloads", "other_configs", "c2_m500_s12.b2seq.gz")
+    sf = b2g.load_seqfile(path)
+    gen = torch.Generator(device=dev).manual_seed(77)
+    ops = torch.empty(max(sf.operand_doubles, 1), dtype=torch.float64, device=dev).normal_(0.0, 1.0, generator=gen)
+    plan = b2g.SeqPlan.from_seqfile(ctx, sf, ops.data_ptr(), b2g.OPERANDS_DEVICE)
+    c = torch.randn(sf.csize, dtype=torch.float64, device=dev, generator=gen)
+    v = torch.zeros(sf.vsize, dtype=torch.float64, device=dev)
+    for _ in range(3):
+        plan.matvec_dev(c.data_ptr(), v.data_ptr(), 1.0)
+    ctx.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        plan.matvec_dev(c.data_ptr(), v.data_ptr(), 1.0)
+    e1.record(stream)
+    ctx.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    alg = 8.0 * (sf.operand_doubles + sf.csize + sf.vsize)
+    hbm = float(peaks.get("hbm_gbs", 6550.0))
+    out = {"workload": "C2 CAS cc-pVDZ SU2 M=500, site 12 H_eff pair list", "pairs": sf.npairs, "gflop": sf.flops * 1e-9,
+           "ms_per_matvec": ms, "tflops": sf.flops / (ms * 1e-3) * 1e-12, "launches_per_matvec": int(plan.stats.launches),
+           "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) * 1e-9, "peak": hbm, "unit": "GB/s",
+                        "frac": alg / (ms * 1e-3) * 1e-9 / hbm, "algorithmic_bytes": alg,
+                        "flop_per_byte": sf.flops / alg}}
+    plan.close()
+    return out
+
+
 def sigma_parity(np, torch, sf, full, ops, c_host, v_dev, world, dist, k=8, budget_flop=3.0e11, seed=7):
     """Checker, outside every timed region: sigma of K sampled blocks recomputed in plain numpy fp64 from the
     operands as they sit in HBM - for every pair that writes into the block,
@@ -240,6 +269,10 @@ def fp64_gemm_peak(torch, dev) -> float:
 
 
 def run_b200(args) -> None:
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if world_env > 1:  # the numpy parity checker of every rank shares the host cores
+        os.environ.setdefault("OPENBLAS_NUM_THREADS", str(max(1, host_threads() // world_env)))
+        os.environ.setdefault("OMP_NUM_THREADS", str(max(1, host_threads() // world_env)))
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -442,6 +475,18 @@ def run_b200(args) -> None:
             except Exception as exc:  # the baseline is reported, never needed by the GPU path
                 line["cpu_baseline"] = {"value": None, "unit": "TFLOP/s", "cores": host_threads(), "kind": "reference",
                                         "sample": f"unavailable: {exc}"}
+        if world == 1:
+            # the small-sector regime (north_star: "achieved HBM GB/s for small ones"): the C2 CAS cc-pVDZ M=500
+            # mid-chain list (149 004 pairs, dims <= 94, 9 GFLOP) is far below the ridge; its bound is HBM / launch
+            # latency, reported as algorithmic bytes (distinct operator doubles + |c| + |sigma|) over kernel time
+            try:
+                line["small_sector"] = small_sector(b2g, torch, ctx, dev, stream, peaks)
+            except Exception as exc:
+                line["small_sector"] = {"unavailable": str(exc)}
+            try:  # complete sweeps through block2's own driver: recorded runs of this round, not timed here
+                line["sweep"] = json.load(open(os.path.join(ROOT, "profiles", "r02_sweeps.json")))
+            except Exception:
+                pass
         if world == 1:
             # the blocking step that feeds this H_eff (left_contract at the same site, same recording run):
             # HBM-bound kernels, reported beside the matvec with their own roofline

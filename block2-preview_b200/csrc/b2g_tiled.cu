@@ -2,6 +2,7 @@
 #include "b2g_tiled.cuh"
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdlib>
 #include <map>
 #include <numeric>
@@ -123,10 +124,7 @@ phase1_kernel(const P1Group *__restrict__ groups, const P1Seg *__restrict__ segs
         src.seg = segs + g.seg_begin, src.seg_end = segs + g.seg_end, src.c = c;
         src.row0 = row0, src.col0 = col0;
         src.m_valid = g.m0 - row0, src.n_valid = g.n0 - col0;
-        int ns = 0;
-        for (const P1Seg *s = src.seg; s < src.seg_end; s++)
-            ns += (s->k0 + Cfg::BK - 1) / Cfg::BK;
-        src.nsteps = ns;
+        src.nsteps = un.pad; // BK-deep stages of the unit (counted by the host: no dependent loads here)
         src.open();
         const int mi_n = clampi((src.m_valid - wm0 + 7) / 8, 0, Cfg::MI);
         const int ni_n = clampi((src.n_valid - wn0 + 7) / 8, 0, Cfg::NI);
@@ -209,10 +207,7 @@ phase2_kernel(const P2Window *__restrict__ wins, const P2Seg *__restrict__ segs,
         src.seg = segs + un.seg_begin, src.seg_end = segs + un.seg_end, src.wbuf = wbuf;
         src.row0 = un.row0, src.col0 = un.col0;
         src.m_valid = win.m1 - src.row0, src.n_valid = win.n0 - src.col0;
-        int ns = 0;
-        for (const P2Seg *s = src.seg; s < src.seg_end; s++)
-            ns += (s->klen + Cfg::BK - 1) / Cfg::BK;
-        src.nsteps = ns;
+        src.nsteps = un.pad; // BK-deep stages of the unit (counted by the host: no dependent loads here)
         src.open();
         const int mi_n = clampi((src.m_valid - wm0 + 7) / 8, 0, Cfg::MI);
         const int ni_n = clampi((src.n_valid - wn0 + 7) / 8, 0, Cfg::NI);
@@ -475,6 +470,16 @@ int b2g_tiled_build(b2g_plan *p) {
     const char *env_kc = getenv("B2G_KCHUNK");
     const int64_t kchunk = env_kc ? atoll(env_kc) : 2048;
     static const bool merge_cols = getenv("B2G_NO_PANELS") == nullptr; // A/B switch: one panel per window
+    static const bool verbose = getenv("B2G_VERBOSE") != nullptr;
+    auto tstart = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (verbose) {
+            auto now = std::chrono::steady_clock::now();
+            fprintf(stderr, "[b2g] tiled_build %-14s %8.3f ms\n", what,
+                    std::chrono::duration<double, std::milli>(now - tstart).count());
+            tstart = now;
+        }
+    };
 
     // ---- 1. sigma blocks: connected sets of overlapping windows; a window is (row, column) placed in its block
     struct Win {
@@ -534,6 +539,7 @@ int b2g_tiled_build(b2g_plan *p) {
         if (!members.empty())
             close();
     }
+    lap("windows");
     // ---- 2. row panels: windows of one block with the same row range (merged along the columns);
     //         windows that overlap in columns inside a panel go to different layers (their W never share a slot)
     struct Panel {
@@ -583,6 +589,7 @@ int b2g_tiled_build(b2g_plan *p) {
             }
         }
     }
+    lap("panels");
     // ---- 3. phase-2 segments = (panel, layer, A1 block, layout); phase-1 groups = (segment, window, tb0)
     struct HostSeg {
         int panel, layer, ta1, lda1, m0;
@@ -675,6 +682,7 @@ int b2g_tiled_build(b2g_plan *p) {
         p1g.push_back(g);
     }
 
+    lap("groups");
     // ---- 4. units
     struct HostUnit {
         Unit u;
@@ -685,13 +693,14 @@ int b2g_tiled_build(b2g_plan *p) {
         const HostGroup &hg = hgroups[gi];
         const P1Group &g = p1g[gi];
         int64_t ksum = 0;
+        int nsteps = 0; // every tile configuration has BK = 16
         for (size_t i : hg.pairs)
-            ksum += hp[i].k0;
+            ksum += hp[i].k0, nsteps += (hp[i].k0 + 15) / 16;
         for (const Strip &rs : split_rows(g.m0))
             for (const Strip &cs : split_cols(g.n0)) {
                 const int c = cfg_of(rs.tile, cs.tile);
                 groups[std::make_tuple(1, c, hg.tb0)].push_back(HostUnit{
-                    Unit{(int)gi, rs.origin, cs.origin, 0, 0, 0, -1},
+                    Unit{(int)gi, rs.origin, cs.origin, 0, 0, nsteps, -1},
                     (double)rs.tile * cs.tile * (double)(ksum + 32 * (int64_t)hg.pairs.size()),
                     2.0 * std::min(rs.tile, g.m0 - rs.origin) * std::min(cs.tile, g.n0 - cs.origin) * (double)ksum});
             }
@@ -737,22 +746,23 @@ int b2g_tiled_build(b2g_plan *p) {
                 const int t_lo = cs.origin, t_hi = std::min(cs.origin + cs.tile, wins[w].n0);
                 size_t s0 = segs.size();
                 int64_t ksum = 0;
+                int nsteps = 0;
                 auto flush = [&](size_t s1) {
                     if (s1 == s0)
                         return;
                     for (const Strip &rs : rsv)
                         groups[std::make_tuple(2, cfg_of(rs.tile, cs.tile), lay)].push_back(
-                            HostUnit{Unit{(int)w, rs.origin, cs.origin, (int)s0, (int)s1, 0, -1},
+                            HostUnit{Unit{(int)w, rs.origin, cs.origin, (int)s0, (int)s1, nsteps, -1},
                                      (double)rs.tile * cs.tile * (double)(ksum + 32),
                                      2.0 * std::min(rs.tile, wins[w].m1 - rs.origin) * (t_hi - t_lo) * (double)ksum});
-                    s0 = s1, ksum = 0;
+                    s0 = s1, ksum = 0, nsteps = 0;
                 };
                 for (int k : lst) {
                     const HostSeg &hs = hsegs[k];
                     if (hs.col_hi <= t_lo || hs.col_lo >= t_hi || hs.m0 == 0)
                         continue;
                     segs.push_back(P2Seg{hs.a1, hs.w_off, hs.lda1, hs.m0, hs.wld, hs.col_lo, hs.col_hi, 0});
-                    ksum += hs.m0;
+                    ksum += hs.m0, nsteps += (hs.m0 + 15) / 16;
                     if (ksum >= kchunk_eff)
                         flush(segs.size());
                 }
@@ -760,6 +770,7 @@ int b2g_tiled_build(b2g_plan *p) {
             }
         }
 
+    lap("units");
     // ---- 5. upload
     auto upload = [&](const void *src, size_t bytes, void **dst) -> int {
         if (b2g_dmalloc(ctx, dst, bytes))
@@ -884,7 +895,9 @@ int b2g_tiled_build(b2g_plan *p) {
     if (b2g_dmalloc(ctx, (void **)&tp->d_counters, sizeof(unsigned int) * 64))
         return 1;
     tp->to_free.push_back(tp->d_counters);
+    lap("tiles+upload");
     B2G_CUDA(cudaStreamSynchronize(ctx->stream));
+    lap("sync");
     p->stats.launches = (int64_t)tp->groups.size() + (int64_t)tp->tile_ranges.size();
     p->stats.n_large = (int64_t)n, p->stats.n_small = 0;
     return 0;

@@ -60,7 +60,7 @@ struct Unit {            // one CTA-tile x K-chunk
     int32_t idx;         // phase 1: pair index; phase 2: window index
     int32_t row0, col0;  // origin of the tile inside the output matrix (elements)
     int32_t seg_begin, seg_end; // phase 2: segment range (phase 1: unused)
-    int32_t pad;
+    int32_t pad;         // number of BK-deep stages of the unit
     int64_t poff;        // phase 2, deterministic mode: element offset of this unit's partial tile; else -1
 };
 

@@ -41,7 +41,8 @@ using namespace block2;
 struct Session {
     b2g_context *ctx = nullptr;
     std::atomic<bool> recording{false};
-    double t_plan = 0, t_matvec = 0;
+    double t_plan = 0, t_matvec = 0, t_precompute = 0, t_davidson = 0;
+    double t_contract_alloc = 0, t_contract_ensure = 0, t_contract_exec = 0, t_rotate_exec = 0, t_rotate_alloc = 0;
     size_t n_plan = 0, n_matvec = 0;
     // --verify: worst relative deviation ||sigma_gpu - sigma_cpu|| / ||sigma_cpu|| over all sites,
     // sigma_cpu from the reference's own BatchGEMMSeq::operator() on the same recorded list
@@ -79,10 +80,12 @@ struct Session {
     // Both frame stacks come from one allocation (core/allocator.hpp:536): page-locking it lets the
     // write-through copies of the renormalised environments go by DMA straight into stack 1.
     void pin_stacks() {
-        if (pinned != nullptr || frame_<double>() == nullptr || frame_<double>()->dallocs.empty())
+        if (pinned != nullptr || frame_<double>() == nullptr || frame_<double>()->dallocs.size() < 2)
             return;
-        void *base = frame_<double>()->dallocs[0]->data;
-        if (b2g_host_register(ctx, base, frame_<double>()->dsize * sizeof(double)) == 0)
+        // stack 1 only (the renormalised environments): page-locking touches every page, and most of the
+        // main stack is never used when use_main_stack is false
+        void *base = frame_<double>()->dallocs[1]->data;
+        if (b2g_host_register(ctx, base, frame_<double>()->dallocs[1]->size * sizeof(double)) == 0)
             pinned = base;
     }
     ~Session() {
@@ -224,6 +227,10 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
                 store().add(blk, m, blk->base + off, false);
             off += (m->total_memory + 1) & ~(size_t)1;
         }
+        {
+            const double d = t.get_time();
+            session->t_rotate_alloc += d, session->t_rotate += d;
+        }
         const SeqTypes saved = seq->mode;
         seq->mode = SeqTypes::Auto; // record only
         for (size_t i = 0; i < out_names.size(); i++)
@@ -238,7 +245,10 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
             store().template collect<S>(c, tab);
             store().apply(tab);
             b2g_plan_stats st;
+            Timer tx;
+            tx.get_time();
             const int rc = b2g_pairs_execute(session->ctx, &b0, &b1, 0, &st);
+            session->t_rotate_exec += tx.get_time();
             store().clear_map();
             if (rc != 0)
                 throw std::runtime_error(std::string("b2g_pairs_execute: ") + b2g_last_error());
@@ -316,6 +326,8 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
         }
         if (mirror) // the cached part may have been produced device-only under the other policy
             store().template materialize<S>(c);
+        Timer tx;
+        tx.get_time();
         shared_ptr<HostArena> arena = make_shared<HostArena>(total, mirror);
         shared_ptr<DevBlock> blk = store().new_block(total, true);
         vector<shared_ptr<SparseMatrix<S, FL>>> outs;
@@ -330,7 +342,9 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
             outs.push_back(m);
             off += (n + 1) & ~(size_t)1;
         }
+        session->t_contract_alloc += tx.get_time();
         store().template ensure_shadows<S>(a); // the environment: a partition loaded from its file, intermediates
+        session->t_contract_ensure += tx.get_time();
         // record-only walk: the operators are walked by the operator-level threads, as the stock method
         // does with parallel_for; every thread has its own term vector, pre-sum recorder and temporaries,
         // and an operator is walked by one thread, so its terms stay in expression order
@@ -410,6 +424,7 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
         b2g_blocking_stats st;
         int rc = 0;
         bool chained = false;
+        tx.get_time();
         for (auto &pre : pres) { // SumProd pre-sums into host temporaries (rare: stored intermediates cover most)
             if (pre->seq->batch[0]->gp.size() != 0)
                 rc = 1, chained = true;
@@ -429,6 +444,7 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
                 account(st);
         }
         store().clear_map();
+        session->t_contract_exec += tx.get_time();
         gopf->collector->clear();
         seq->clear();
         for (auto &pre : pres)
@@ -801,7 +817,10 @@ template <typename S> struct GPUDMRG : DMRG<S, double, double> {
                                                     const shared_ptr<EffectiveHamiltonian<S, double>> &h_eff,
                                                     const double davidson_conv_thrd, Timer &t) {
         frame_<double>()->activate(0);
+        Timer tq;
+        tq.get_time();
         h_eff->precompute();
+        gtf->session->t_precompute += tq.get_time();
         if (gtf->session->verify && h_eff->tf->opf->seq->batch[0]->gp.size() != 0) {
             const size_t n = h_eff->ket->total_memory;
             vector<double> x(n), y_gpu(n, 0.0), y_cpu(n, 0.0);
@@ -825,10 +844,13 @@ template <typename S> struct GPUDMRG : DMRG<S, double, double> {
         // under a parallel rule a rank without terms at this site still runs the solver: every rank joins the
         // sigma all-reduces of the replicated Davidson iteration
         if (h_eff->tf->opf->seq->batch[0]->gp.size() != 0 || me->para_rule != nullptr) {
+            gtf->get_plan();
+            tq.get_time();
             if (b2g_davidson(gtf->get_plan(), h_eff->diag->data, h_eff->ket->data, davidson_conv_thrd,
                              this->davidson_rel_conv_thrd, this->davidson_max_iter, this->davidson_soft_max_iter,
                              this->davidson_def_min_size, this->davidson_def_max_size, &e, &ndav) != 0)
                 throw std::runtime_error(std::string("b2g_davidson: ") + b2g_last_error());
+            gtf->session->t_davidson += tq.get_time();
             nflop = (size_t)ndav * (h_eff->tf->opf->seq->batch[0]->nflop + h_eff->tf->opf->seq->batch[1]->nflop);
         }
         h_eff->post_precompute();

@@ -310,7 +310,9 @@ int main(int argc, char **argv) {
            "\"diag_entries\": %zu, \"max_diag_rel_err\": %.3e, \"gpu_iadd\": %d, \"iadd_walks\": %zu, \"t_iadd\": %.3f, "
            "\"iadd_entries\": %zu, \"max_iadd_rel_err\": %.3e, \"host_mirror\": %d, \"pinned_stacks\": %d, "
            "\"resident_read_gbytes\": %.3f, \"mirrored_gbytes\": %.3f, \"resident_peak_gbytes\": %.3f, "
-           "\"resident_uploaded_gbytes\": %.3f, \"resident_downloaded_gbytes\": %.3f, \"resident_evicted_gbytes\": %.3f}\n",
+           "\"resident_uploaded_gbytes\": %.3f, \"resident_downloaded_gbytes\": %.3f, \"resident_evicted_gbytes\": %.3f, "
+           "\"t_precompute\": %.3f, \"t_davidson\": %.3f, \"t_contract_alloc\": %.3f, \"t_contract_ensure\": %.3f, "
+           "\"t_contract_exec\": %.3f, \"t_rotate_alloc\": %.3f, \"t_rotate_exec\": %.3f}\n",
            a.ranks, a.davidson.c_str(), a.bond, a.seed, gpu.energies.size(), gpu.total, ref.total, a.threads,
            gpu.energies.empty() ? 0.0 : gpu.energies.back(), ref.energies.empty() ? 0.0 : ref.energies.back(),
            maxdiff,
@@ -327,7 +329,8 @@ int main(int argc, char **argv) {
            session->t_iadd, session->iadd_entries, session->max_iadd_err, (int)session->host_mirror,
            (int)(session->pinned != nullptr), res_hit * 1e-9, res_mirrored * 1e-9, session->store->peak * 1e-9,
            session->store->uploaded_bytes * 1e-9, session->store->downloaded_bytes * 1e-9,
-           session->store->evicted_bytes * 1e-9);
+           session->store->evicted_bytes * 1e-9, session->t_precompute, session->t_davidson, session->t_contract_alloc,
+           session->t_contract_ensure, session->t_contract_exec, session->t_rotate_alloc, session->t_rotate_exec);
     fflush(stdout);
     _exit(0);
 }
