@@ -571,6 +571,15 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
                            std::chrono::steady_clock::time_point t_begin, const char *who) {
     const bool dst_zero = (flags & B2G_DST_ZERO) != 0;
     st.merged = (int64_t)he.size();
+    b2g_prof_record("blocking.parse", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count());
+    double prof_t = B2GProfScope::now();
+    auto prof_lap = [&prof_t](const char *label) {
+        if (b2g_prof_enabled()) {
+            const double now = B2GProfScope::now();
+            b2g_prof_record(label, now - prof_t);
+            prof_t = now;
+        }
+    };
     if (he.empty()) {
         if (stats)
             *stats = st;
@@ -777,6 +786,7 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
         return 1;
     }
     st.plan_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+    prof_lap("blocking.regroup");
     if (flags & B2G_PLAN_ONLY) { // the regrouping alone (host work, no device): counts for tests and tools
         st.units = (int64_t)(units.size() + gunits.size() + tunits.size());
         if (stats)
@@ -862,6 +872,7 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
             s.dst = xout(s.dst);
         }
     }
+    prof_lap("blocking.mirror+translate");
     // single-contribution linear units become self-contained streaming units
     std::vector<StreamUnit> sunits;
     std::vector<MultiUnit> munits;
@@ -907,6 +918,39 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
         }
         units.swap(rest);
     }
+    // Source-major order: the same environment block feeds several windows (a source is read by ~2 terms on
+    // average in an H_eff blocking step), and a kernel works through its unit array front to back with all
+    // warps of the grid, so units that read the same source run at the same time and the second reader finds
+    // the block in L2.  Outputs are written once whatever the order.  (B2G_BLK_NOSORT: list order, for A/B.)
+    static const bool source_major = getenv("B2G_BLK_NOSORT") == nullptr;
+    if (source_major) {
+        auto reorder = [](auto &vec, auto key_of) {
+            typedef typename std::remove_reference<decltype(vec)>::type Vec;
+            const size_t n = vec.size();
+            if (n < 2)
+                return;
+            std::vector<std::pair<uintptr_t, uint32_t>> key(n);
+            for (size_t i = 0; i < n; i++)
+                key[i] = std::make_pair((uintptr_t)key_of(vec[i]), (uint32_t)i);
+            std::sort(key.begin(), key.end());
+            Vec out(n);
+            for (size_t i = 0; i < n; i++)
+                out[i] = vec[key[i].second];
+            vec.swap(out);
+        };
+        reorder(sunits, [](const StreamUnit &u) { return u.src; });
+        reorder(munits, [](const MultiUnit &u) { return u.src[0]; });
+        reorder(tunits, [&dev_entries](const TileUnit &u) {
+            const BlkEntry &e = dev_entries[u.first];
+            return e.a + (int64_t)u.i0 * e.sa_i + (int64_t)u.j0 * e.sa_j;
+        });
+        reorder(units, [&dev_entries](const BlkUnit &u) {
+            const BlkEntry &e = dev_entries[u.first];
+            const int w = e.nd ? e.nd : u.n; // logical width of the addressing: i = e / w, j = e % w
+            return e.a + (w > 1 ? (int64_t)(u.e0 / w) * e.sa_i + (int64_t)(u.e0 % w) * e.sa_j : (int64_t)u.e0 * e.sa_i);
+        });
+    }
+    prof_lap("blocking.stream_units");
     // descriptors (pageable -> device; synchronised below before the vectors die)
     if (!dev_entries.empty()) {
         if (b2g_dmalloc(ctx, (void **)&d_entries, dev_entries.size() * sizeof(BlkEntry)) ||
@@ -952,8 +996,10 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
                             ctx->stream) != cudaSuccess)
             return fail("" + std::string(who) + ": descriptor upload failed");
     }
+    prof_lap("blocking.desc_upload_issue");
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)
         return fail("" + std::string(who) + ": operand upload failed");
+    prof_lap("blocking.desc_upload_sync");
     st.upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_up).count();
 
     // ---- 6. kernels
@@ -1036,6 +1082,8 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
     float ms = 0;
     cudaEventElapsedTime(&ms, ev0, ev1);
     st.kernel_ms = ms;
+    prof_lap("blocking.kernels+sync");
+    b2g_prof_record("blocking.kernels_gpu", ms * 1e-3);
     if (verbose) {
         float ms_s = 0;
         cudaEventElapsedTime(&ms_s, ev0, evs);
@@ -1058,6 +1106,7 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
         st.download_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_dn).count();
     }
     cleanup();
+    prof_lap("blocking.download+cleanup");
     if (stats)
         *stats = st;
     return 0;

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <mutex>
 #include <thread>
 
@@ -18,6 +19,51 @@ static thread_local std::string g_err;
 void b2g_set_error(const std::string &msg) { g_err = msg; }
 
 extern "C" const char *b2g_last_error(void) { return g_err.c_str(); }
+
+// ------------------------------------------------------------------ host profile (B2G_PROF)
+namespace {
+struct ProfEntry {
+    double seconds = 0;
+    int64_t calls = 0;
+};
+std::mutex g_prof_mutex;
+std::map<std::string, ProfEntry> g_prof;
+} // namespace
+double B2GProfScope::now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+extern "C" int b2g_prof_enabled(void) {
+    static const int on = getenv("B2G_PROF") != nullptr ? 1 : 0;
+    return on;
+}
+extern "C" void b2g_prof_record(const char *label, double seconds) {
+    if (!b2g_prof_enabled() || !label)
+        return;
+    std::lock_guard<std::mutex> lk(g_prof_mutex);
+    ProfEntry &e = g_prof[label];
+    e.seconds += seconds, e.calls++;
+}
+extern "C" int b2g_prof_dump(const char *path) {
+    if (!b2g_prof_enabled())
+        return 0;
+    FILE *f = (path == nullptr || strcmp(path, "-") == 0) ? stderr : fopen(path, "w");
+    if (!f) {
+        b2g_set_error(std::string("b2g_prof_dump: cannot open ") + path);
+        return 1;
+    }
+    std::lock_guard<std::mutex> lk(g_prof_mutex);
+    fprintf(f, "{");
+    bool first = true;
+    for (auto &kv : g_prof) {
+        fprintf(f, "%s\n \"%s\": {\"seconds\": %.6f, \"calls\": %lld}", first ? "" : ",", kv.first.c_str(),
+                kv.second.seconds, (long long)kv.second.calls);
+        first = false;
+    }
+    fprintf(f, "\n}\n");
+    if (f != stderr)
+        fclose(f);
+    return 0;
+}
 
 extern "C" int b2g_device_count(void) {
     int n = 0;
@@ -331,6 +377,7 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
         return 1;
     }
     B2G_CUDA(cudaSetDevice(ctx->device));
+    const auto t_enter = std::chrono::steady_clock::now();
     const int64_t n = b0->count;
     const char *force = getenv("B2G_FORCE_GENERIC");
     const bool force_generic = force && force[0] == '1';
@@ -412,14 +459,19 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
     const bool verbose = getenv("B2G_VERBOSE") != nullptr;
     auto tstart = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) {
-        if (verbose) {
+        if (verbose || b2g_prof_enabled()) {
             auto now = std::chrono::steady_clock::now();
-            fprintf(stderr, "[b2g] plan_create %-14s %8.3f ms\n", what,
-                    std::chrono::duration<double, std::milli>(now - tstart).count());
+            if (verbose)
+                fprintf(stderr, "[b2g] plan_create %-14s %8.3f ms\n", what,
+                        std::chrono::duration<double, std::milli>(now - tstart).count());
+            b2g_prof_record((std::string("plan_create.") + what).c_str(),
+                            std::chrono::duration<double>(now - tstart).count());
             tstart = now;
         }
     };
-    lap("scan pairs");
+    b2g_prof_record("plan_create.scan pairs",
+                    std::chrono::duration<double>(std::chrono::steady_clock::now() - t_enter).count());
+    tstart = std::chrono::steady_clock::now();
     // merge the referenced operator ranges into arenas
     std::sort(rg.begin(), rg.end(), [](const Range &x, const Range &y) { return x.lo < y.lo; });
     std::vector<Range> ar;
@@ -525,6 +577,7 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
 extern "C" int b2g_plan_destroy(b2g_plan *p) {
     if (!p)
         return 0;
+    B2G_PROF_SCOPE("plan_destroy");
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     b2g_dfree(p->ctx, p->d_operands);
@@ -656,6 +709,14 @@ extern "C" int b2g_pairs_execute(b2g_context *ctx, const b2g_batch *b0, const b2
     if (n == 0)
         return 0;
     auto t0 = std::chrono::steady_clock::now();
+    double prof_t = B2GProfScope::now();
+    auto prof_lap = [&prof_t](const char *label) {
+        if (b2g_prof_enabled()) {
+            const double now = B2GProfScope::now();
+            b2g_prof_record(label, now - prof_t);
+            prof_t = now;
+        }
+    };
     b2g_plan *p = new b2g_plan();
     p->ctx = ctx, p->npairs = n, p->max_work = max_work;
     std::vector<B2GPair> &hp = p->h_pairs;
@@ -731,6 +792,7 @@ extern "C" int b2g_pairs_execute(b2g_context *ctx, const b2g_batch *b0, const b2
         }
         rg.swap(ar);
     };
+    prof_lap("pairs.scan");
     size_t in_total = 0, out_total = 0;
     merge(in_rg, in_total), merge(out_rg, out_total);
     auto locate = [](const std::vector<Range> &ar, uintptr_t ptr) -> const Range & {
@@ -806,16 +868,20 @@ extern "C" int b2g_pairs_execute(b2g_context *ctx, const b2g_batch *b0, const b2
     }
     p->csize = (int64_t)in_total, p->vsize = (int64_t)out_total;
     const double t_up = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    prof_lap("pairs.mirror+translate");
     if (b2g_tiled_build(p))
         return fail("");
+    prof_lap("pairs.tiled_build");
     rc = b2g_tiled_launch(p, d_in, d_out, 1.0);
     if (rc)
         return fail("");
+    prof_lap("pairs.launch");
     // results: device -> pinned staging -> += into the host blocks (beta = 1 of the recorded GEMMs)
     {
         const size_t CH = B2G_UP_CHUNK / sizeof(double);
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)
             return fail("b2g_pairs_execute: kernel execution failed");
+        prof_lap("pairs.kernels_sync");
         for (const Range &r : out_rg) {
             const size_t len = (r.hi - r.lo) / sizeof(double);
             double *host = (double *)r.lo;
@@ -849,8 +915,10 @@ extern "C" int b2g_pairs_execute(b2g_context *ctx, const b2g_batch *b0, const b2
         stats->pairs = n, stats->nflop_mnk = nflop, stats->operand_doubles = (int64_t)in_total;
         stats->csize = (int64_t)in_total, stats->vsize = (int64_t)out_total, stats->upload_seconds = t_up;
     }
+    prof_lap("pairs.download");
     b2g_dfree(ctx, d_in), b2g_dfree(ctx, d_out);
     b2g_plan_destroy(p);
+    prof_lap("pairs.destroy");
     return 0;
 }
 
@@ -971,6 +1039,7 @@ extern "C" int b2g_download(b2g_context *ctx, int64_t count, double *const *host
         b2g_set_error("b2g_download: null argument");
         return 1;
     }
+    B2G_PROF_SCOPE("download_blocks");
     B2G_CUDA(cudaSetDevice(ctx->device));
     std::vector<B2GRange> staged; // pageable destinations: packed through the staging ring
     std::vector<const double *> staged_dev;
@@ -1001,6 +1070,7 @@ extern "C" int b2g_upload_blocks(b2g_context *ctx, int64_t count, double *const 
         b2g_set_error("b2g_upload_blocks: null argument");
         return 1;
     }
+    B2G_PROF_SCOPE("upload_blocks");
     B2G_CUDA(cudaSetDevice(ctx->device));
     if (ensure_upload_buffers(ctx))
         return 1;

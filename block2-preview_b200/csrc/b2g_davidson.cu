@@ -258,6 +258,16 @@ extern "C" int b2g_davidson(b2g_plan *plan, const double *diag_host, double *ket
     B2G_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int64_t n = plan->csize;
+    const bool prof = b2g_prof_enabled() != 0;
+    double prof_t = B2GProfScope::now();
+    auto prof_lap = [&prof_t, prof](const char *label) {
+        if (prof) {
+            const double now = B2GProfScope::now();
+            b2g_prof_record(label, now - prof_t);
+            prof_t = now;
+        }
+    };
+    std::vector<cudaEvent_t> prof_ev; // profile: pairs of events around every matvec (GPU time of the H.c products)
     const int k = 1;
     if (deflation_min_size < k)
         deflation_min_size = k;
@@ -295,6 +305,7 @@ extern "C" int b2g_davidson(b2g_plan *plan, const double *diag_host, double *ket
         dot_kernel<<<RED_BLOCKS, RED_THREADS, 0, st>>>(x, y, n, part, cnt, out);
         ctx->launches++;
     };
+    prof_lap("davidson.alloc+h2d_issue");
     // normalise the initial guess (:945-955)
     dot(bs, bs, scal + 0);
     double h_scal[8];
@@ -306,6 +317,7 @@ extern "C" int b2g_davidson(b2g_plan *plan, const double *diag_host, double *ket
     }
     scale_rsqrt_kernel<<<ew_grid, ew_thr, 0, st>>>(bs, n, scal + 0);
     ctx->launches++;
+    prof_lap("davidson.init_sync");
 
     int m = k, msig = 0, xiter = 0, ck = 0;
     double theta = 0.0, qq = 0.0;
@@ -315,8 +327,17 @@ extern "C" int b2g_davidson(b2g_plan *plan, const double *diag_host, double *ket
         xiter++;
         for (int i = msig; i < m; i++, msig++) {
             B2G_CUDA(cudaMemsetAsync(ss + (size_t)i * ld, 0, sizeof(double) * n, st));
+            if (prof) {
+                cudaEvent_t e0, e1;
+                B2G_CUDA(cudaEventCreate(&e0));
+                B2G_CUDA(cudaEventCreate(&e1));
+                prof_ev.push_back(e0), prof_ev.push_back(e1);
+                B2G_CUDA(cudaEventRecord(e0, st));
+            }
             if (b2g_launch_matvec(plan, bs + (size_t)i * ld, ss + (size_t)i * ld, 1.0))
                 return 1;
+            if (prof)
+                B2G_CUDA(cudaEventRecord(prof_ev.back(), st));
             if (ctx->nccl_comm && b2g_allreduce_sum(ctx, ss + (size_t)i * ld, n))
                 return 1;
         }
@@ -387,9 +408,29 @@ extern "C" int b2g_davidson(b2g_plan *plan, const double *diag_host, double *ket
         b2g_set_error("b2g_davidson: not converged within max_iter");
         return 4;
     }
+    prof_lap("davidson.iterations");
     B2G_CUDA(cudaMemcpyAsync(ket_host, bs, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     B2G_CUDA(cudaStreamSynchronize(st));
     B2G_CUDA(cudaGetLastError());
+    prof_lap("davidson.result_d2h");
+    if (prof) {
+        double gpu_s = 0, first_s = 0;
+        for (size_t i = 0; i + 1 < prof_ev.size(); i += 2) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, prof_ev[i], prof_ev[i + 1]);
+            gpu_s += ms * 1e-3;
+            if (i == 0)
+                first_s = ms * 1e-3;
+            cudaEventDestroy(prof_ev[i]), cudaEventDestroy(prof_ev[i + 1]);
+        }
+        b2g_prof_record("davidson.matvec_gpu", gpu_s);
+        b2g_prof_record("davidson.matvec_gpu_first", first_s);
+        fprintf(stderr,
+                "[b2g] davidson n=%lld pairs=%lld iters=%d matvec_gpu=%.1f ms (first %.1f ms) gflop/matvec=%.1f -> %.2f TFLOP/s\n",
+                (long long)n, (long long)plan->npairs, xiter, gpu_s * 1e3, first_s * 1e3,
+                2e-9 * (double)plan->stats.nflop_mnk,
+                gpu_s > 0 ? 2e-12 * (double)plan->stats.nflop_mnk * (double)(prof_ev.size() / 2) / gpu_s : 0.0);
+    }
     *eigenvalue = theta;
     *ndav = xiter;
     return 0;

@@ -81,6 +81,21 @@ struct b2g_plan {
 };
 
 void b2g_set_error(const std::string &msg);
+// host-side wall-clock profile (B2G_PROF): RAII section that adds to a label
+struct B2GProfScope {
+    const char *label;
+    bool on;
+    double t0;
+    static double now();
+    explicit B2GProfScope(const char *label) : label(label), on(b2g_prof_enabled() != 0), t0(on ? now() : 0.0) {}
+    ~B2GProfScope() {
+        if (on)
+            b2g_prof_record(label, now() - t0);
+    }
+};
+#define B2G_PROF_CAT2(a, b) a##b
+#define B2G_PROF_CAT(a, b) B2G_PROF_CAT2(a, b)
+#define B2G_PROF_SCOPE(label) B2GProfScope B2G_PROF_CAT(b2g_prof_scope_, __LINE__)(label)
 // stream-ordered pool allocations (cached by the driver mempool across plans / Davidson calls)
 int b2g_dmalloc(b2g_context *ctx, void **ptr, size_t bytes);
 void b2g_dfree(b2g_context *ctx, void *ptr);

@@ -70,6 +70,18 @@ template <class Cfg> __device__ __forceinline__ void warp_origin(int &wm0, int &
 __device__ __forceinline__ int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 // ------------------------------ phase 1 -------------------------------------
+// Programmatic dependent launch: the launches of one phase write disjoint outputs, so the next launch of the chain
+// may fill the SMs as the CTAs of this one run out of units (no idle tail between 30+ persistent launches).
+// Every CTA lets the dependents go at once and waits for its predecessor only when it is about to exit, which
+// makes grid completion transitive along the chain; the first launch of phase 2 (wait_first) waits up front,
+// because it reads the W panels of all phase-1 launches.  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_enter(int wait_first) {
+    if (wait_first)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_exit() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <class Cfg, bool B_KC> struct P1Src {
     const P1Seg *seg, *seg_end;
     const double *c;
@@ -105,10 +117,11 @@ template <class Cfg, bool B_KC>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
 phase1_kernel(const P1Group *__restrict__ groups, const P1Seg *__restrict__ segs, const Unit *__restrict__ units,
               int n_units, unsigned int *__restrict__ counter, const double *__restrict__ c,
-              double *__restrict__ wbuf) {
+              double *__restrict__ wbuf, int wait_first) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_unit;
     __shared__ double s_alpha[Cfg::STAGES];
+    pdl_enter(wait_first);
     int wm0, wn0;
     warp_origin<Cfg>(wm0, wn0);
     const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
@@ -152,6 +165,7 @@ phase1_kernel(const P1Group *__restrict__ groups, const P1Seg *__restrict__ segs
         u = s_unit; // written before the barriers of the main loop
         __syncthreads();
     }
+    pdl_exit();
 }
 
 // ------------------------------ phase 2 -------------------------------------
@@ -190,9 +204,10 @@ template <class Cfg, bool A_KC>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
 phase2_kernel(const P2Window *__restrict__ wins, const P2Seg *__restrict__ segs, const Unit *__restrict__ units,
               int n_units, unsigned int *__restrict__ counter, const double *__restrict__ wbuf,
-              double *__restrict__ v, double scale, double *__restrict__ pbuf) {
+              double *__restrict__ v, double scale, double *__restrict__ pbuf, int wait_first) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_unit;
+    pdl_enter(wait_first);
     int wm0, wn0;
     warp_origin<Cfg>(wm0, wn0);
     const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
@@ -251,6 +266,7 @@ phase2_kernel(const P2Window *__restrict__ wins, const P2Seg *__restrict__ segs,
         u = s_unit; // written before the barriers of the main loop
         __syncthreads();
     }
+    pdl_exit();
 }
 
 // ------------------------------ sigma reduce --------------------------------
@@ -400,32 +416,56 @@ template <class K> static int raise_smem_limit(K kern, int bytes, int device, st
     return 0;
 }
 
+// pdl: this launch follows another launch of the same chain on the same stream and may overlap its tail
+template <class... Params, class... Args>
+static int launch_ex(void (*kern)(Params...), int grid, int threads, size_t smem, cudaStream_t stream, bool pdl,
+                     Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = pdl ? 1 : 0;
+    B2G_CUDA(cudaLaunchKernelEx(&cfg, kern, Params(args)...));
+    return 0;
+}
+
 template <class Cfg, bool L> static int launch_p1(const LaunchGroup &g, const TiledPlan &tp, b2g_context *ctx,
-                                                  cudaStream_t stream, unsigned int *counter, const double *c) {
+                                                  cudaStream_t stream, unsigned int *counter, const double *c,
+                                                  bool pdl, int wait_first) {
     auto kern = phase1_kernel<Cfg, L>;
     static std::atomic<uint64_t> attr_mask{0};
     if (raise_smem_limit(kern, Cfg::SMEM_BYTES, ctx->device, attr_mask))
         return 1;
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::THREADS, Cfg::SMEM_BYTES);
+    static std::atomic<int> per_sm_cached{0}; // same on every B200 of the box
+    int per_sm = per_sm_cached.load(std::memory_order_relaxed);
+    if (per_sm == 0) {
+        per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::THREADS, Cfg::SMEM_BYTES);
+        per_sm_cached.store(per_sm, std::memory_order_relaxed);
+    }
     const int grid = std::min(g.n_units, ctx->sm_count * std::max(per_sm, 1));
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tp.d_p1g, tp.d_p1s, g.d_units, g.n_units, counter, c,
-                                                                tp.d_wbuf);
-    return 0;
+    return launch_ex(kern, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, pdl, tp.d_p1g, tp.d_p1s, g.d_units, g.n_units,
+                     counter, c, tp.d_wbuf, wait_first);
 }
 template <class Cfg, bool L> static int launch_p2(const LaunchGroup &g, const TiledPlan &tp, b2g_context *ctx,
                                                   cudaStream_t stream, unsigned int *counter, double *v,
-                                                  double scale) {
+                                                  double scale, bool pdl, int wait_first) {
     auto kern = phase2_kernel<Cfg, L>;
     static std::atomic<uint64_t> attr_mask{0};
     if (raise_smem_limit(kern, Cfg::SMEM_BYTES, ctx->device, attr_mask))
         return 1;
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::THREADS, Cfg::SMEM_BYTES);
+    static std::atomic<int> per_sm_cached{0}; // same on every B200 of the box
+    int per_sm = per_sm_cached.load(std::memory_order_relaxed);
+    if (per_sm == 0) {
+        per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::THREADS, Cfg::SMEM_BYTES);
+        per_sm_cached.store(per_sm, std::memory_order_relaxed);
+    }
     const int grid = std::min(g.n_units, ctx->sm_count * std::max(per_sm, 1));
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tp.d_win, tp.d_seg, g.d_units, g.n_units, counter,
-                                                                tp.d_wbuf, v, scale, tp.d_pbuf);
-    return 0;
+    return launch_ex(kern, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, pdl, tp.d_win, tp.d_seg, g.d_units, g.n_units,
+                     counter, tp.d_wbuf, v, scale, tp.d_pbuf, wait_first);
 }
 
 } // namespace b2g
@@ -957,6 +997,8 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
         B2G_CUDA(cudaEventRecord(ctx->fork_ev, ctx->stream));
     int gi = 0;
     bool phase2_open = false;
+    static const bool use_pdl = getenv("B2G_NO_PDL") == nullptr; // A/B switch
+    bool chain_open = false, first_p2 = true;
     for (const LaunchGroup &g : tp->groups) {
         if (g.phase == 2 && !phase2_open) { // every W panel is complete before the first phase-2 launch
             phase2_open = true;
@@ -975,6 +1017,13 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
         }
         unsigned int *counter = tp->d_counters + gi++;
         int rc = 0;
+        // chained launches on the context stream (no events, no side streams in between) overlap their tails
+        const bool chain = use_pdl && !fork && stats == nullptr;
+        const bool pdl = chain && chain_open;
+        const int wait_first = (g.phase == 2 && first_p2) ? 1 : 0;
+        if (g.phase == 2)
+            first_p2 = false;
+        chain_open = chain;
         char nm[64];
         snprintf(nm, sizeof(nm), "phase%d_%dx%d_%s", g.phase, kCfg[g.cfg].bm, kCfg[g.cfg].bn,
                  g.phase == 1 ? (g.layout ? "Bt" : "Bn") : (g.layout ? "At" : "An"));
@@ -983,38 +1032,38 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
 #define B2G_DISPATCH(PH, CFG, LAY, CALL)                                                \
     if (g.phase == PH && g.cfg == CFG && g.layout == LAY)                               \
         rc = CALL;
-        B2G_DISPATCH(1, 0, 0, (launch_p1<Cfg0, false>(g, *tp, ctx, gs, counter, c_dev)))
-        B2G_DISPATCH(1, 0, 1, (launch_p1<Cfg0, true>(g, *tp, ctx, gs, counter, c_dev)))
-        B2G_DISPATCH(1, 1, 0, (launch_p1<Cfg1, false>(g, *tp, ctx, gs, counter, c_dev)))
-        B2G_DISPATCH(1, 1, 1, (launch_p1<Cfg1, true>(g, *tp, ctx, gs, counter, c_dev)))
-        B2G_DISPATCH(1, 2, 0, (launch_p1<Cfg2, false>(g, *tp, ctx, gs, counter, c_dev)))
-        B2G_DISPATCH(1, 2, 1, (launch_p1<Cfg2, true>(g, *tp, ctx, gs, counter, c_dev)))
-        B2G_DISPATCH(1, 3, 0, (launch_p1<Cfg3, false>(g, *tp, ctx, gs, counter, c_dev)))
-        B2G_DISPATCH(1, 3, 1, (launch_p1<Cfg3, true>(g, *tp, ctx, gs, counter, c_dev)))
-        B2G_DISPATCH(1, 4, 0, (launch_p1<Cfg4, false>(g, *tp, ctx, gs, counter, c_dev)))
-        B2G_DISPATCH(1, 4, 1, (launch_p1<Cfg4, true>(g, *tp, ctx, gs, counter, c_dev)))
-        B2G_DISPATCH(1, 5, 0, (launch_p1<Cfg5, false>(g, *tp, ctx, gs, counter, c_dev)))
-        B2G_DISPATCH(1, 5, 1, (launch_p1<Cfg5, true>(g, *tp, ctx, gs, counter, c_dev)))
-        B2G_DISPATCH(1, 6, 0, (launch_p1<Cfg6, false>(g, *tp, ctx, gs, counter, c_dev)))
-        B2G_DISPATCH(1, 6, 1, (launch_p1<Cfg6, true>(g, *tp, ctx, gs, counter, c_dev)))
-        B2G_DISPATCH(1, 7, 0, (launch_p1<Cfg7, false>(g, *tp, ctx, gs, counter, c_dev)))
-        B2G_DISPATCH(1, 7, 1, (launch_p1<Cfg7, true>(g, *tp, ctx, gs, counter, c_dev)))
-        B2G_DISPATCH(2, 0, 0, (launch_p2<Cfg0, true>(g, *tp, ctx, gs, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 0, 1, (launch_p2<Cfg0, false>(g, *tp, ctx, gs, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 1, 0, (launch_p2<Cfg1, true>(g, *tp, ctx, gs, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 1, 1, (launch_p2<Cfg1, false>(g, *tp, ctx, gs, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 2, 0, (launch_p2<Cfg2, true>(g, *tp, ctx, gs, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 2, 1, (launch_p2<Cfg2, false>(g, *tp, ctx, gs, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 3, 0, (launch_p2<Cfg3, true>(g, *tp, ctx, gs, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 3, 1, (launch_p2<Cfg3, false>(g, *tp, ctx, gs, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 4, 0, (launch_p2<Cfg4, true>(g, *tp, ctx, gs, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 4, 1, (launch_p2<Cfg4, false>(g, *tp, ctx, gs, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 5, 0, (launch_p2<Cfg5, true>(g, *tp, ctx, gs, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 5, 1, (launch_p2<Cfg5, false>(g, *tp, ctx, gs, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 6, 0, (launch_p2<Cfg6, true>(g, *tp, ctx, gs, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 6, 1, (launch_p2<Cfg6, false>(g, *tp, ctx, gs, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 7, 0, (launch_p2<Cfg7, true>(g, *tp, ctx, gs, counter, v_dev, scale)))
-        B2G_DISPATCH(2, 7, 1, (launch_p2<Cfg7, false>(g, *tp, ctx, gs, counter, v_dev, scale)))
+        B2G_DISPATCH(1, 0, 0, (launch_p1<Cfg0, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
+        B2G_DISPATCH(1, 0, 1, (launch_p1<Cfg0, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
+        B2G_DISPATCH(1, 1, 0, (launch_p1<Cfg1, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
+        B2G_DISPATCH(1, 1, 1, (launch_p1<Cfg1, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
+        B2G_DISPATCH(1, 2, 0, (launch_p1<Cfg2, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
+        B2G_DISPATCH(1, 2, 1, (launch_p1<Cfg2, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
+        B2G_DISPATCH(1, 3, 0, (launch_p1<Cfg3, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
+        B2G_DISPATCH(1, 3, 1, (launch_p1<Cfg3, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
+        B2G_DISPATCH(1, 4, 0, (launch_p1<Cfg4, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
+        B2G_DISPATCH(1, 4, 1, (launch_p1<Cfg4, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
+        B2G_DISPATCH(1, 5, 0, (launch_p1<Cfg5, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
+        B2G_DISPATCH(1, 5, 1, (launch_p1<Cfg5, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
+        B2G_DISPATCH(1, 6, 0, (launch_p1<Cfg6, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
+        B2G_DISPATCH(1, 6, 1, (launch_p1<Cfg6, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
+        B2G_DISPATCH(1, 7, 0, (launch_p1<Cfg7, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
+        B2G_DISPATCH(1, 7, 1, (launch_p1<Cfg7, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
+        B2G_DISPATCH(2, 0, 0, (launch_p2<Cfg0, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
+        B2G_DISPATCH(2, 0, 1, (launch_p2<Cfg0, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
+        B2G_DISPATCH(2, 1, 0, (launch_p2<Cfg1, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
+        B2G_DISPATCH(2, 1, 1, (launch_p2<Cfg1, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
+        B2G_DISPATCH(2, 2, 0, (launch_p2<Cfg2, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
+        B2G_DISPATCH(2, 2, 1, (launch_p2<Cfg2, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
+        B2G_DISPATCH(2, 3, 0, (launch_p2<Cfg3, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
+        B2G_DISPATCH(2, 3, 1, (launch_p2<Cfg3, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
+        B2G_DISPATCH(2, 4, 0, (launch_p2<Cfg4, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
+        B2G_DISPATCH(2, 4, 1, (launch_p2<Cfg4, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
+        B2G_DISPATCH(2, 5, 0, (launch_p2<Cfg5, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
+        B2G_DISPATCH(2, 5, 1, (launch_p2<Cfg5, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
+        B2G_DISPATCH(2, 6, 0, (launch_p2<Cfg6, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
+        B2G_DISPATCH(2, 6, 1, (launch_p2<Cfg6, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
+        B2G_DISPATCH(2, 7, 0, (launch_p2<Cfg7, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
+        B2G_DISPATCH(2, 7, 1, (launch_p2<Cfg7, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
 #undef B2G_DISPATCH
         if (rc)
             return rc;

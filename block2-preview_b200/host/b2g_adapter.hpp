@@ -32,11 +32,26 @@
 #include "b2g_device_store.hpp"
 #include "b2g_shm_comm.hpp"
 #include <atomic>
+#include <chrono>
 #include <stdexcept>
 
 namespace b2g_host {
 
 using namespace block2;
+
+// B2G_PROF: wall-clock sections of the binding, accumulated by the library's profile (b2g_prof_record)
+struct ProfLap {
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    ProfLap() : on(b2g_prof_enabled() != 0), t(std::chrono::steady_clock::now()) {}
+    void lap(const char *label) {
+        if (!on)
+            return;
+        const auto now = std::chrono::steady_clock::now();
+        b2g_prof_record(label, std::chrono::duration<double>(now - t).count());
+        t = now;
+    }
+};
 
 struct Session {
     b2g_context *ctx = nullptr;
@@ -192,7 +207,9 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
                           const shared_ptr<Symbolic<S>> &names, bool trans) const {
         Timer t, td;
         t.get_time();
+        ProfLap pl;
         store().tick(), store().prune();
+        pl.lap("host.rotate.prune");
         auto &seq = opf->seq;
         if (seq->batch[0]->gp.size() != 0 || seq->batch[1]->gp.size() != 0)
             throw std::runtime_error("b2g: recorder not empty at rotate");
@@ -217,16 +234,19 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
             } else
                 m->allocate(m->info);
         }
+        pl.lap("host.rotate.host_alloc");
         size_t total = 0;
         for (auto &m : outs)
             total += (m->total_memory + 1) & ~(size_t)1;
         shared_ptr<DevBlock> blk = store().new_block(total, true);
+        pl.lap("host.rotate.new_block");
         size_t off = 0;
         for (auto &m : outs) {
             if (m->total_memory != 0)
                 store().add(blk, m, blk->base + off, false);
             off += (m->total_memory + 1) & ~(size_t)1;
         }
+        pl.lap("host.rotate.add_shadows");
         {
             const double d = t.get_time();
             session->t_rotate_alloc += d, session->t_rotate += d;
@@ -236,6 +256,7 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
         for (size_t i = 0; i < out_names.size(); i++)
             opf->tensor_rotate(a->ops.at(out_names[i]), outs[i], mpst_bra, mpst_ket, trans);
         seq->mode = saved;
+        pl.lap("host.rotate.record");
         if (session->verify || session->host_mirror)
             store().template materialize<S>(a);
         if (seq->batch[1]->gp.size() != 0) {
@@ -244,12 +265,14 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
             store().template collect<S>(a, tab);
             store().template collect<S>(c, tab);
             store().apply(tab);
+            pl.lap("host.rotate.map");
             b2g_plan_stats st;
             Timer tx;
             tx.get_time();
             const int rc = b2g_pairs_execute(session->ctx, &b0, &b1, 0, &st);
             session->t_rotate_exec += tx.get_time();
             store().clear_map();
+            pl.lap("host.rotate.pairs_execute");
             if (rc != 0)
                 throw std::runtime_error(std::string("b2g_pairs_execute: ") + b2g_last_error());
             session->rotate_pairs += (size_t)st.pairs, session->rotate_flops += 2.0 * (double)st.nflop_mnk;
@@ -271,6 +294,7 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
                 throw std::runtime_error(std::string("b2g_download: ") + b2g_last_error());
         }
         session->t_rotate_download += td.get_time();
+        pl.lap("host.rotate.write_through");
         if (session->verify && seq->batch[1]->gp.size() != 0) { // the reference executor on the same list
             vector<vector<double>> gpu;
             for (auto &m : outs) {
@@ -285,6 +309,7 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
                 memcpy(outs[z]->data, gpu[z].data(), sizeof(double) * outs[z]->total_memory);
         }
         seq->clear();
+        pl.lap("host.rotate.clear");
         session->t_rotate += t.get_time(), session->n_rotate++;
     }
     int run_blocking_list(BatchGEMM<FL> &bt, b2g_blocking_stats &st) const {
@@ -303,7 +328,9 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
                             const shared_ptr<Symbolic<S>> &names, OpNamesSet delayed, bool right) const {
         Timer t, tr;
         t.get_time();
+        ProfLap pl;
         store().tick(), store().prune();
+        pl.lap("host.contract.prune");
         auto &seq = opf->seq;
         if (seq->batch[0]->gp.size() != 0 || seq->batch[1]->gp.size() != 0)
             throw std::runtime_error("b2g: recorder not empty at contract");
@@ -328,8 +355,11 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
             store().template materialize<S>(c);
         Timer tx;
         tx.get_time();
+        pl.lap("host.contract.todo");
         shared_ptr<HostArena> arena = make_shared<HostArena>(total, mirror);
+        pl.lap("host.contract.arena");
         shared_ptr<DevBlock> blk = store().new_block(total, true);
+        pl.lap("host.contract.new_block");
         vector<shared_ptr<SparseMatrix<S, FL>>> outs;
         size_t off = 0;
         for (size_t i : todo) {
@@ -343,8 +373,10 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
             off += (n + 1) & ~(size_t)1;
         }
         session->t_contract_alloc += tx.get_time();
+        pl.lap("host.contract.add_shadows");
         store().template ensure_shadows<S>(a); // the environment: a partition loaded from its file, intermediates
         session->t_contract_ensure += tx.get_time();
+        pl.lap("host.contract.ensure_shadows");
         // record-only walk: the operators are walked by the operator-level threads, as the stock method
         // does with parallel_for; every thread has its own term vector, pre-sum recorder and temporaries,
         // and an operator is walked by one thread, so its terms stay in expression order
@@ -394,6 +426,7 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
                 temps.insert(temps.end(), tt.begin(), tt.end());
         }
         session->t_contract_record += tr.get_time();
+        pl.lap("host.contract.record");
         auto account = [&](const b2g_blocking_stats &st) {
             session->contract_entries += (size_t)st.entries, session->contract_kernel_ms += st.kernel_ms;
             session->contract_bytes += (double)(st.bytes_in + st.bytes_out);
@@ -421,6 +454,7 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
             if (Shadow *sh = store().find(m))
                 tab.add(*sh);
         store().apply(tab);
+        pl.lap("host.contract.map");
         b2g_blocking_stats st;
         int rc = 0;
         bool chained = false;
@@ -434,9 +468,11 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
                     account(st);
             }
         }
+        pl.lap("host.contract.presums");
         vector<b2g_tp_term> &terms = gopf->collector->per_thread[0];
         for (size_t k = 1; k < gopf->collector->per_thread.size(); k++)
             terms.insert(terms.end(), gopf->collector->per_thread[k].begin(), gopf->collector->per_thread[k].end());
+        pl.lap("host.contract.merge_terms");
         if (rc == 0 && terms.size() != 0) {
             rc = b2g_tensor_product_execute(session->ctx, (int64_t)terms.size(), terms.data(), B2G_OPERANDS_HOST,
                                             B2G_DST_ZERO, &st);
@@ -445,10 +481,12 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
         }
         store().clear_map();
         session->t_contract_exec += tx.get_time();
+        pl.lap("host.contract.tp_execute");
         gopf->collector->clear();
         seq->clear();
         for (auto &pre : pres)
             pre->seq->clear();
+        pl.lap("host.contract.clear");
         if (rc != 0)
             throw std::runtime_error(chained ? std::string("b2g: blocking list has chained pairs")
                                              : std::string("b2g blocking: ") + b2g_last_error());
@@ -486,6 +524,7 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
         }
         for (auto &m : temps)
             m->deallocate();
+        pl.lap("host.contract.tail");
         session->t_contract += t.get_time(), session->n_contract++;
     }
     bool on_device_ok() const { return !session->recording && !frame_<FL>()->use_main_stack; }
@@ -732,12 +771,14 @@ template <typename S, typename Base = TensorFunctions<S, double>> struct GPUTens
         t.get_time();
         drop();
         auto &seq = opf->seq;
+        ProfLap pl;
         b2g_batch b0 = as_b2g_batch(*seq->batch[0]), b1 = as_b2g_batch(*seq->batch[1]);
         store().tick(), store().prune();
         MapTable tab; // environments and blocked operators of this H_eff are read in place from HBM
         store().template collect<S>(plan_lopt, tab);
         store().template collect<S>(plan_ropt, tab);
         store().apply(tab);
+        pl.lap("host.plan.map");
         const int rc = b2g_plan_create(session->ctx, &b0, &b1, (int64_t)seq->max_work, (int64_t)csize, (int64_t)vsize,
                                        B2G_OPERANDS_HOST, &plan);
         store().clear_map();
@@ -799,8 +840,10 @@ template <typename S> struct GPUDMRG : DMRG<S, double, double> {
         }
         Timer t;
         t.get_time();
+        ProfLap pl0;
         shared_ptr<EffectiveHamiltonian<S, double>> h_eff =
             me->eff_ham(FuseTypes::FuseLR, forward, true, me->bra->tensors[i], me->ket->tensors[i]);
+        pl0.lap("host.eigs.eff_ham");
         this->sweep_max_eff_ham_size = max(this->sweep_max_eff_ham_size, h_eff->op->get_total_memory());
         this->sweep_max_eff_wfn_size = max(this->sweep_max_eff_wfn_size, (size_t)h_eff->ket->total_memory);
         this->teff += t.get_time();
@@ -819,8 +862,10 @@ template <typename S> struct GPUDMRG : DMRG<S, double, double> {
         frame_<double>()->activate(0);
         Timer tq;
         tq.get_time();
+        ProfLap pl;
         h_eff->precompute();
         gtf->session->t_precompute += tq.get_time();
+        pl.lap("host.eigs.precompute");
         if (gtf->session->verify && h_eff->tf->opf->seq->batch[0]->gp.size() != 0) {
             const size_t n = h_eff->ket->total_memory;
             vector<double> x(n), y_gpu(n, 0.0), y_cpu(n, 0.0);
@@ -844,20 +889,26 @@ template <typename S> struct GPUDMRG : DMRG<S, double, double> {
         // under a parallel rule a rank without terms at this site still runs the solver: every rank joins the
         // sigma all-reduces of the replicated Davidson iteration
         if (h_eff->tf->opf->seq->batch[0]->gp.size() != 0 || me->para_rule != nullptr) {
+            pl.lap("host.eigs.verify");
             gtf->get_plan();
+            pl.lap("host.eigs.plan");
             tq.get_time();
             if (b2g_davidson(gtf->get_plan(), h_eff->diag->data, h_eff->ket->data, davidson_conv_thrd,
                              this->davidson_rel_conv_thrd, this->davidson_max_iter, this->davidson_soft_max_iter,
                              this->davidson_def_min_size, this->davidson_def_max_size, &e, &ndav) != 0)
                 throw std::runtime_error(std::string("b2g_davidson: ") + b2g_last_error());
             gtf->session->t_davidson += tq.get_time();
+            pl.lap("host.eigs.davidson");
             nflop = (size_t)ndav * (h_eff->tf->opf->seq->batch[0]->nflop + h_eff->tf->opf->seq->batch[1]->nflop);
         }
         h_eff->post_precompute();
+        pl.lap("host.eigs.post_precompute");
         gtf->forget();
+        pl.lap("host.eigs.forget");
         double tdav = t.get_time();
         this->teig += tdav;
         h_eff->deallocate();
+        pl.lap("host.eigs.heff_deallocate");
         return make_tuple((FPLS)e, ndav, nflop, tdav);
     }
 };

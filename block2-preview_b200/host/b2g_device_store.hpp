@@ -140,6 +140,11 @@ struct DeviceStore {
                 dead.push_back(kv.first);
         for (const void *k : dead)
             erase_key(k);
+        for (size_t i = blocks.size(); i-- > 0;) // blocks that never got a shadow and are not part of this call
+            if (blocks[i]->keys.empty() && blocks[i]->last_use != clock) {
+                held -= blocks[i]->doubles * sizeof(double);
+                blocks.erase(blocks.begin() + (long)i);
+            }
     }
     // least recently used blocks whose every shadow also lives on the host make room
     void make_room(size_t need_bytes) {
@@ -160,6 +165,7 @@ struct DeviceStore {
             std::vector<const void *> keys = victim->keys;
             for (const void *k : keys)
                 erase_key(k);
+            drop_block(victim); // a block without shadows (nothing was added to it) is not dropped by erase_key
         }
     }
     shared_ptr<DevBlock> new_block(size_t doubles, bool zero) {

@@ -332,5 +332,6 @@ int main(int argc, char **argv) {
            session->store->evicted_bytes * 1e-9, session->t_precompute, session->t_davidson, session->t_contract_alloc,
            session->t_contract_ensure, session->t_contract_exec, session->t_rotate_alloc, session->t_rotate_exec);
     fflush(stdout);
+    b2g_prof_dump(getenv("B2G_PROF_FILE")); // B2G_PROF: wall-clock sections of the library and the binding
     _exit(0);
 }

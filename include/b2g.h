@@ -97,6 +97,14 @@ int64_t b2g_context_launches(const b2g_context *ctx);
 void *b2g_context_stream(const b2g_context *ctx);
 int b2g_context_synchronize(b2g_context *ctx);
 
+/* Host-side wall-clock profile of the library and its binding (measurement only; enabled by the environment
+ * variable B2G_PROF): seconds and calls accumulated per label.  b2g_prof_record adds to a label (the
+ * reference-side binding uses it for its own sections), b2g_prof_dump writes one JSON object to `path`
+ * (NULL or "-": stderr) and returns 0; both are no-ops when the profile is off. */
+int b2g_prof_enabled(void);
+void b2g_prof_record(const char *label, double seconds);
+int b2g_prof_dump(const char *path);
+
 /* Build the replay plan of one H_eff from the two recorded lists.
  * Pair i:  W = alpha0 * op(c + a0_i) * op(B0_i);   sigma + c1_i += alpha1 * scale * op(A1_i) * W
  * batch0->a[i] and batch1->c[i] are null-based offsets into c / sigma (the reference records
