@@ -209,13 +209,14 @@ b2g_blocking_kernel(const BlkUnit *__restrict__ units, int64_t nunits, const Blk
 // position inside the unit - 80-90 % of the bytes of a blocking step.  The descriptor is self-contained
 // (pre-offset pointers), the next unit's descriptor and scalar are fetched while the current unit
 // streams, and the source goes through the per-thread cp.async ring.
-struct StreamUnit { // 64 bytes
+struct StreamUnit { // 64 bytes: `rows` rows of `len` elements each (row pitches drow / srow)
     double *dst;
     const double *src;
     const double *b;
     double alpha;
-    int32_t len, dstep, sstep, pad;
-    int64_t pad2[2];
+    int32_t len, dstep, sstep, rows;
+    int32_t drow, srow;
+    int64_t pad2;
 };
 static_assert(sizeof(StreamUnit) == 64, "StreamUnit layout");
 
@@ -237,36 +238,43 @@ b2g_blocking_stream_kernel(const StreamUnit *__restrict__ units, int64_t nunits)
             N = units[u + nwarps]; // in flight while this unit streams
         double bnext = 0.0;
         const double f = U.alpha * bval;
-        const double *__restrict__ sptr = U.src;
-        double *__restrict__ dptr = U.dst;
-        const int64_t sstep = U.sstep, dstep = U.dstep;
+        const double *__restrict__ sptr = U.src; // row being issued
+        double *__restrict__ dptr = U.dst;       // row being written
+        const int64_t sstep = U.sstep, dstep = U.dstep, srow = U.srow, drow = U.drow;
         const int len = U.len;
-        const int nchunks = (len + 32 * STREAM_PER - 1) / (32 * STREAM_PER);
+        const int ncr = (len + 32 * STREAM_PER - 1) / (32 * STREAM_PER); // chunks per row
+        const int nchunks = ncr * U.rows;
+        int ic = 0; // chunk inside the row being issued
         auto issue = [&](int c) {
             if (c < nchunks) {
                 double *slot = my + (size_t)(c % RING_STAGES) * STREAM_PER * 32;
 #pragma unroll
                 for (int r = 0; r < STREAM_PER; r++) {
-                    const int l = c * 32 * STREAM_PER + r * 32 + lane;
+                    const int l = ic * 32 * STREAM_PER + r * 32 + lane;
                     if (l < len)
                         cp_async8(slot + r * 32, sptr + l * sstep);
                 }
+                if (++ic == ncr)
+                    ic = 0, sptr += srow;
             }
             asm volatile("cp.async.commit_group;\n" ::: "memory");
         };
 #pragma unroll
         for (int c = 0; c < RING_STAGES - 1; c++)
             issue(c);
+        int wc = 0; // chunk inside the row being written
         for (int c = 0; c < nchunks; c++) {
             issue(c + RING_STAGES - 1);
             asm volatile("cp.async.wait_group %0;\n" ::"n"(RING_STAGES - 1) : "memory");
             const double *slot = my + (size_t)(c % RING_STAGES) * STREAM_PER * 32;
 #pragma unroll
             for (int r = 0; r < STREAM_PER; r++) {
-                const int l = c * 32 * STREAM_PER + r * 32 + lane;
+                const int l = wc * 32 * STREAM_PER + r * 32 + lane;
                 if (l < len)
                     dptr[l * dstep] = f * slot[r * 32];
             }
+            if (++wc == ncr)
+                wc = 0, dptr += drow;
             if (c == 0 && more)
                 bnext = __ldg(N.b); // N has arrived by now; its scalar is ready when this unit ends
         }
@@ -287,9 +295,11 @@ struct MultiUnit { // 160 bytes
     double alpha[MULTI_MAX];
     double beta[MULTI_MAX];
     int32_t sstep[MULTI_MAX];
-    int32_t len, dstep, count, pad;
+    int32_t srow[MULTI_MAX]; // row pitch of every source
+    int32_t len, dstep, count, rows; // `rows` rows of `len` elements each
+    int32_t drow, pad;               // row pitch of the window
 };
-static_assert(sizeof(MultiUnit) == 8 + 4 * 8 * MULTI_MAX + 4 * MULTI_MAX + 16, "MultiUnit layout");
+static_assert(sizeof(MultiUnit) == 8 + 4 * 8 * MULTI_MAX + 8 * MULTI_MAX + 24, "MultiUnit layout");
 
 __global__ void __launch_bounds__(BLK_THREADS, 3)
 b2g_blocking_multi_kernel(const MultiUnit *__restrict__ units, int64_t nunits, int dst_zero) {
@@ -301,19 +311,19 @@ b2g_blocking_multi_kernel(const MultiUnit *__restrict__ units, int64_t nunits, i
     for (int64_t u = warp; u < nunits; u += nwarps) {
         const MultiUnit &G = units[u];
         const int count = G.count, len = G.len;
-        const int64_t dstep = G.dstep;
-        double *__restrict__ dptr = G.dst;
-        const double *sp[MULTI_MAX];
+        const int64_t dstep = G.dstep, drow = G.drow;
+        double *__restrict__ dptr = G.dst; // row being accumulated
+        const double *sp[MULTI_MAX];       // rows being issued
         double f[MULTI_MAX], bt[MULTI_MAX];
-        int64_t ss[MULTI_MAX];
+        int64_t ss[MULTI_MAX], sr[MULTI_MAX];
 #pragma unroll
         for (int t = 0; t < MULTI_MAX; t++) {
             const bool on = t < count;
-            sp[t] = on ? G.src[t] : nullptr, ss[t] = on ? G.sstep[t] : 0;
+            sp[t] = on ? G.src[t] : nullptr, ss[t] = on ? G.sstep[t] : 0, sr[t] = on ? G.srow[t] : 0;
             f[t] = on ? G.alpha[t] * __ldg(G.b[t]) : 0.0, bt[t] = on ? G.beta[t] : 1.0;
         }
-        const int nchunks = (len + 32 * STREAM_PER - 1) / (32 * STREAM_PER);
-        const int steps = nchunks * count;
+        const int ncr = (len + 32 * STREAM_PER - 1) / (32 * STREAM_PER); // chunks per row
+        const int steps = ncr * count * G.rows;
         int qi = 0, ci = 0, ti = 0;
         auto issue = [&]() {
             if (qi < steps) {
@@ -327,8 +337,15 @@ b2g_blocking_multi_kernel(const MultiUnit *__restrict__ units, int64_t nunits, i
                         cp_async8(slot + r * 32, s0 + l * st);
                 }
                 qi++;
-                if (++ti == count)
-                    ti = 0, ci++;
+                if (++ti == count) {
+                    ti = 0;
+                    if (++ci == ncr) { // next row of every source
+                        ci = 0;
+#pragma unroll
+                        for (int t = 0; t < MULTI_MAX; t++)
+                            sp[t] += sr[t];
+                    }
+                }
             }
             asm volatile("cp.async.commit_group;\n" ::: "memory");
         };
@@ -363,7 +380,9 @@ b2g_blocking_multi_kernel(const MultiUnit *__restrict__ units, int64_t nunits, i
                     if (l < len)
                         dptr[l * dstep] = acc[r];
                 }
-                tc = 0, cc++;
+                tc = 0;
+                if (++cc == ncr)
+                    cc = 0, dptr += drow;
             }
         }
     }
@@ -376,11 +395,12 @@ b2g_blocking_multi_kernel(const MultiUnit *__restrict__ units, int64_t nunits, i
 // ring, one contribution per step) and folded into the running values (TILE_R per lane, registers) in
 // list order.  The tile is written once, row by row.
 constexpr int TILE_R = 16, TILE_C = 32, TILE_LD = TILE_C + 1, TILE_STAGES = 3;
+constexpr int TILE_STRIP = 8; // column tiles per unit
 constexpr int TILE_SLOT = TILE_R * TILE_LD + 4; // tile + (b, alpha, beta, pad) of the step
 constexpr size_t TILE_RING_BYTES = (size_t)(BLK_THREADS / 32) * TILE_STAGES * TILE_SLOT * sizeof(double);
-struct TileUnit { // 40 bytes
+struct TileUnit { // 40 bytes: `ntiles` consecutive column tiles of one tile row, starting at (i0, j0)
     double *dst;  // window origin
-    int32_t i0, j0, m, n, ldc, first, count, pad;
+    int32_t i0, j0, m, n, ldc, first, count, ntiles;
 };
 static_assert(sizeof(TileUnit) == 40, "TileUnit layout");
 
@@ -392,8 +412,10 @@ b2g_blocking_tile_kernel(const TileUnit *__restrict__ units, int64_t nunits, con
     const int64_t warp = ((int64_t)blockIdx.x * BLK_THREADS + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * BLK_THREADS) >> 5;
     double *my = ring + (size_t)(threadIdx.x >> 5) * TILE_STAGES * TILE_SLOT;
-    for (int64_t u = warp; u < nunits; u += nwarps) {
-        const TileUnit U = units[u];
+    for (int64_t u = warp; u < nunits; u += nwarps)
+      for (int tj = 0, ntj = units[u].ntiles; tj < ntj; tj++) {
+        TileUnit U = units[u];
+        U.j0 += tj * TILE_C;
         const int rows = min(TILE_R, U.m - U.i0), cols = min(TILE_C, U.n - U.j0);
         double *__restrict__ dptr = U.dst + (int64_t)U.i0 * U.ldc + U.j0;
         BlkEntry Ep = entries[U.first];
@@ -696,6 +718,24 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
     std::vector<BlkEntry> dev_entries;
     std::vector<BlkUnit> units, gunits; // AXPY windows / windows with a general contribution
     std::vector<TileUnit> tunits;       // AXPY windows with transposed sources among several contributions
+    // windows whose 1..MULTI_MAX contributions are all linear (the bulk of a blocking step): rows [i0, i0 + rows)
+    // x columns [j0, j0 + len) per unit, turned into self-contained stream / multi descriptors once the operands
+    // have their device addresses.  One unit spans several rows, so the descriptor count follows the bytes of
+    // the step (M^2), not the number of window rows times the number of terms.
+    struct LinUnit {
+        double *dst;
+        int32_t i0, rows, j0, len, n, ldc, first, count;
+    };
+    std::vector<LinUnit> lunits;
+    int64_t lin_target = UNIT_ELEMS; // elements x contributions per linear unit: ~32 units per warp of the grid
+    {
+        int64_t tot = 0;
+        for (size_t ci = 0; ci < cl.size(); ci++)
+            if (!irregular[ci])
+                tot += (int64_t)he[idx[cl[ci].first]].m * he[idx[cl[ci].first]].n * cl[ci].count;
+        const int64_t warps = (int64_t)(ctx ? ctx->sm_count : 148) * 3 * (BLK_THREADS / 32);
+        lin_target = std::min<int64_t>(16384, std::max<int64_t>(UNIT_ELEMS, tot / (warps * 32) / 256 * 256));
+    }
     static const bool tile_on = getenv("B2G_BLK_NOTILE") == nullptr;
     dev_entries.reserve(he.size());
     std::vector<BlkSerial> serial;
@@ -727,19 +767,44 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
         static const int64_t cap_num = getenv("B2G_BLK_CAPNUM") ? atoll(getenv("B2G_BLK_CAPNUM")) : 4 * UNIT_ELEMS;
         const int64_t cap = std::max<int64_t>(cap_min, std::min<int64_t>(UNIT_ELEMS, cap_num / cl[ci].count) / 128 * 128);
         bool transposed_src = false;
+        // every contribution linear in the window element, read (alpha != 0) and k = 1
+        bool lin = axpy && cl[ci].count <= MULTI_MAX && (w.n >= ROW_MIN || w.n == 1);
         for (int q = 0; q < cl[ci].count; q++) {
             const BlkEntry &e = dev_entries[first + q];
             transposed_src = transposed_src || (e.alpha != 0.0 && e.sa_j != 1);
+            lin = lin && e.nd == 0 && e.alpha != 0.0 && e.k == 1;
         }
+        if (cl[ci].count == 1) // a single contribution overwrites the window
+            lin = lin && (dst_zero || dev_entries[first].beta == 0.0);
         // tile units: several contributions with transposed sources among them, and every 2-D window of
         // 32..127 columns (too narrow for row units: the tile kernel needs no per-element division and reads
         // transposed sources along their contiguous direction)
         static const bool tile_narrow = getenv("B2G_BLK_NOTILE_NARROW") == nullptr;
         if (axpy && tile_on && w.n >= TILE_C && w.m >= 2 &&
             ((transposed_src && cl[ci].count >= 2) || (tile_narrow && w.n < ROW_MIN))) {
+            // a unit = up to TILE_STRIP column tiles of one tile row (cost: tiles x contributions)
+            const int64_t strip = std::max<int64_t>(1, std::min<int64_t>(TILE_STRIP, 4 * TILE_STRIP / cl[ci].count));
             for (int64_t i0 = 0; i0 < w.m; i0 += TILE_R)
-                for (int64_t j0 = 0; j0 < w.n; j0 += TILE_C)
-                    tunits.push_back(TileUnit{w.dst, (int32_t)i0, (int32_t)j0, w.m, w.n, w.ldc, first, cl[ci].count, 0});
+                for (int64_t j0 = 0; j0 < w.n; j0 += TILE_C * strip)
+                    tunits.push_back(TileUnit{w.dst, (int32_t)i0, (int32_t)j0, w.m, w.n, w.ldc, first, cl[ci].count,
+                                              (int32_t)std::min<int64_t>(strip, (w.n - j0 + TILE_C - 1) / TILE_C)});
+        } else if (lin) {
+            const int64_t per = std::max<int64_t>(256, lin_target / cl[ci].count / 256 * 256); // elements per unit
+            if (w.n == 1) { // a column (or a dense window addressed flat): one "row" of elements ldc apart
+                for (int64_t e0 = 0; e0 < total; e0 += per)
+                    lunits.push_back(LinUnit{w.dst, 0, 1, (int32_t)e0, (int32_t)std::min<int64_t>(per, total - e0), w.n,
+                                             w.ldc, first, cl[ci].count});
+            } else if (w.n > per) {
+                for (int64_t i = 0; i < w.m; i++)
+                    for (int64_t j0 = 0; j0 < w.n; j0 += per)
+                        lunits.push_back(LinUnit{w.dst, (int32_t)i, 1, (int32_t)j0, (int32_t)std::min<int64_t>(per, w.n - j0),
+                                                 w.n, w.ldc, first, cl[ci].count});
+            } else {
+                const int64_t rows = std::max<int64_t>(1, per / w.n);
+                for (int64_t i0 = 0; i0 < w.m; i0 += rows)
+                    lunits.push_back(LinUnit{w.dst, (int32_t)i0, (int32_t)std::min<int64_t>(rows, w.m - i0), 0, w.n, w.n,
+                                             w.ldc, first, cl[ci].count});
+            }
         } else if (!axpy || w.n < ROW_MIN) {
             for (int64_t e0 = 0; e0 < total; e0 += cap)
                 dstu.push_back(BlkUnit{w.dst, (int32_t)e0, (int32_t)std::min<int64_t>(cap, total - e0), w.n, w.ldc, first,
@@ -788,7 +853,10 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
     st.plan_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
     prof_lap("blocking.regroup");
     if (flags & B2G_PLAN_ONLY) { // the regrouping alone (host work, no device): counts for tests and tools
-        st.units = (int64_t)(units.size() + gunits.size() + tunits.size());
+        st.units = (int64_t)(units.size() + gunits.size() + tunits.size() + lunits.size());
+        if (getenv("B2G_VERBOSE"))
+            fprintf(stderr, "[b2g] blocking plan: %zu accumulate units, %zu general, %zu tile, %zu linear, %zu serial\n",
+                    units.size(), gunits.size(), tunits.size(), lunits.size(), serial.size());
         if (stats)
             *stats = st;
         return 0;
@@ -866,6 +934,8 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
             u.dst = xout(u.dst);
         for (TileUnit &u : tunits)
             u.dst = xout(u.dst);
+        for (LinUnit &u : lunits)
+            u.dst = xout(u.dst);
         for (BlkSerial &s : serial) {
             if (s.e.alpha != 0.0 && s.e.k > 0)
                 s.e.a = xin(s.e.a), s.e.b = xin(s.e.b);
@@ -873,50 +943,35 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
         }
     }
     prof_lap("blocking.mirror+translate");
-    // single-contribution linear units become self-contained streaming units
+    // linear units become self-contained stream (one contribution) / multi (2..MULTI_MAX) descriptors
     std::vector<StreamUnit> sunits;
     std::vector<MultiUnit> munits;
-    {
-        // every contribution linear, read (alpha != 0) and k = 1
-        auto multi_ok = [&dev_entries](const BlkUnit &u) {
+    for (const LinUnit &u : lunits) {
+        const bool flat = u.n == 1;
+        const int64_t doff = flat ? (int64_t)u.j0 * u.ldc : (int64_t)u.i0 * u.ldc + u.j0;
+        auto soff = [&](const BlkEntry &E) {
+            return flat ? (int64_t)u.j0 * E.sa_i : (int64_t)u.i0 * E.sa_i + (int64_t)u.j0 * E.sa_j;
+        };
+        if (u.count == 1) {
+            const BlkEntry &E = dev_entries[u.first];
+            StreamUnit su;
+            su.dst = u.dst + doff, su.src = E.a + soff(E), su.b = E.b, su.alpha = E.alpha;
+            su.len = u.len, su.dstep = flat ? u.ldc : 1, su.sstep = flat ? E.sa_i : E.sa_j;
+            su.rows = u.rows, su.drow = flat ? 0 : u.ldc, su.srow = flat ? 0 : E.sa_i, su.pad2 = 0;
+            sunits.push_back(su);
+        } else {
+            MultiUnit mu;
+            memset(&mu, 0, sizeof(mu));
+            mu.dst = u.dst + doff;
             for (int t = 0; t < u.count; t++) {
                 const BlkEntry &Et = dev_entries[u.first + t];
-                if (Et.nd != 0 || Et.alpha == 0.0 || Et.k != 1)
-                    return false;
+                mu.src[t] = Et.a + soff(Et), mu.b[t] = Et.b, mu.alpha[t] = Et.alpha, mu.beta[t] = Et.beta;
+                mu.sstep[t] = flat ? Et.sa_i : Et.sa_j, mu.srow[t] = flat ? 0 : Et.sa_i;
             }
-            return true;
-        };
-        std::vector<BlkUnit> rest;
-        rest.reserve(units.size());
-        for (const BlkUnit &u : units) {
-            const BlkEntry &E = dev_entries[u.first];
-            const bool rowu = u.n >= ROW_MIN, flat = u.n == 1;
-            if (u.count == 1 && E.nd == 0 && (rowu || flat) && E.alpha != 0.0 && E.k == 1 && (dst_zero || E.beta == 0.0)) {
-                const int64_t i0 = rowu ? u.e0 / u.n : 0, j0 = rowu ? u.e0 - i0 * u.n : 0;
-                StreamUnit su;
-                su.dst = u.dst + (rowu ? i0 * u.ldc + j0 : (int64_t)u.e0 * u.ldc);
-                su.src = E.a + (rowu ? i0 * E.sa_i + j0 * E.sa_j : (int64_t)u.e0 * E.sa_i);
-                su.b = E.b, su.alpha = E.alpha;
-                su.len = u.len, su.dstep = rowu ? 1 : u.ldc, su.sstep = rowu ? E.sa_j : E.sa_i, su.pad = 0;
-                su.pad2[0] = su.pad2[1] = 0;
-                sunits.push_back(su);
-            } else if (u.count >= 2 && u.count <= MULTI_MAX && (rowu || flat) && multi_ok(u)) {
-                const int64_t i0 = rowu ? u.e0 / u.n : 0, j0 = rowu ? u.e0 - i0 * u.n : 0;
-                MultiUnit mu;
-                memset(&mu, 0, sizeof(mu));
-                mu.dst = u.dst + (rowu ? i0 * u.ldc + j0 : (int64_t)u.e0 * u.ldc);
-                for (int t = 0; t < u.count; t++) {
-                    const BlkEntry &Et = dev_entries[u.first + t];
-                    mu.src[t] = Et.a + (rowu ? i0 * Et.sa_i + j0 * Et.sa_j : (int64_t)u.e0 * Et.sa_i);
-                    mu.b[t] = Et.b, mu.alpha[t] = Et.alpha, mu.beta[t] = Et.beta;
-                    mu.sstep[t] = rowu ? Et.sa_j : Et.sa_i;
-                }
-                mu.len = u.len, mu.dstep = rowu ? 1 : u.ldc, mu.count = u.count;
-                munits.push_back(mu);
-            } else
-                rest.push_back(u);
+            mu.len = u.len, mu.dstep = flat ? u.ldc : 1, mu.count = u.count, mu.rows = u.rows;
+            mu.drow = flat ? 0 : u.ldc;
+            munits.push_back(mu);
         }
-        units.swap(rest);
     }
     // Source-major order: the same environment block feeds several windows (a source is read by ~2 terms on
     // average in an H_eff blocking step), and a kernel works through its unit array front to back with all

@@ -125,11 +125,17 @@ phase1_kernel(const P1Group *__restrict__ groups, const P1Seg *__restrict__ segs
     int wm0, wn0;
     warp_origin<Cfg>(wm0, wn0);
     const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
-    // units are claimed one ahead: the atomic for the next unit is in flight while this one runs
-    int u = blockIdx.x;
+    // Units are claimed one ahead (the atomic for the next unit is in flight while this one runs), the first one
+    // included: under programmatic dependent launch the CTAs of a grid start as slots free up, and a CTA that
+    // starts late must not sit on one of the most expensive units (the list is in cost order).
+    if (threadIdx.x == 0)
+        s_unit = (int)atomicAdd(counter, 1u);
+    __syncthreads();
+    int u = s_unit;
+    __syncthreads();
     while (u < n_units) {
         if (threadIdx.x == 0)
-            s_unit = (int)(atomicAdd(counter, 1u) + gridDim.x);
+            s_unit = (int)atomicAdd(counter, 1u);
         const Unit un = units[u];
         const P1Group g = groups[un.idx];
         const int row0 = un.row0, col0 = un.col0;
@@ -211,11 +217,17 @@ phase2_kernel(const P2Window *__restrict__ wins, const P2Seg *__restrict__ segs,
     int wm0, wn0;
     warp_origin<Cfg>(wm0, wn0);
     const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
-    // units are claimed one ahead: the atomic for the next unit is in flight while this one runs
-    int u = blockIdx.x;
+    // Units are claimed one ahead (the atomic for the next unit is in flight while this one runs), the first one
+    // included: under programmatic dependent launch the CTAs of a grid start as slots free up, and a CTA that
+    // starts late must not sit on one of the most expensive units (the list is in cost order).
+    if (threadIdx.x == 0)
+        s_unit = (int)atomicAdd(counter, 1u);
+    __syncthreads();
+    int u = s_unit;
+    __syncthreads();
     while (u < n_units) {
         if (threadIdx.x == 0)
-            s_unit = (int)(atomicAdd(counter, 1u) + gridDim.x);
+            s_unit = (int)atomicAdd(counter, 1u);
         const Unit un = units[u];
         const P2Window win = wins[un.idx];
         P2Src<Cfg, A_KC> src;
