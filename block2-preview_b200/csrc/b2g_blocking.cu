@@ -220,65 +220,84 @@ struct StreamUnit { // 64 bytes: `rows` rows of `len` elements each (row pitches
 };
 static_assert(sizeof(StreamUnit) == 64, "StreamUnit layout");
 
+// One CTA per unit.  A unit (rows x len) is cut into pieces of up to PIECE_CHUNKS chunks of one row (a chunk =
+// 32 lanes x STREAM_PER elements); the warps of the CTA take the pieces in turn (piece w, w + 8, ...), so the
+// pieces in flight on the chip are neighbours in source and destination - as with one descriptor per row or
+// per 2048 elements - at a fraction of the descriptors, and the cp.async ring of a warp keeps running from one
+// piece into the next.
+constexpr int PIECE_CHUNKS = 8;
 __global__ void __launch_bounds__(BLK_THREADS, 3)
 b2g_blocking_stream_kernel(const StreamUnit *__restrict__ units, int64_t nunits) {
     extern __shared__ double ring[];
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * BLK_THREADS + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * BLK_THREADS) >> 5;
-    if (warp >= nunits)
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr int NW = BLK_THREADS / 32;
+    if (blockIdx.x >= nunits)
         return;
-    double *my = ring + ((size_t)(threadIdx.x >> 5) * RING_STAGES * STREAM_PER) * 32 + lane;
-    StreamUnit U = units[warp];
+    double *my = ring + ((size_t)wib * RING_STAGES * STREAM_PER) * 32 + lane;
+    StreamUnit U = units[blockIdx.x];
     double bval = __ldg(U.b);
-    for (int64_t u = warp; u < nunits; u += nwarps) {
-        const bool more = u + nwarps < nunits;
+    for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+        const bool more = u + gridDim.x < nunits;
         StreamUnit N = U;
         if (more)
-            N = units[u + nwarps]; // in flight while this unit streams
-        double bnext = 0.0;
+            N = units[u + gridDim.x]; // in flight while this unit streams
         const double f = U.alpha * bval;
-        const double *__restrict__ sptr = U.src; // row being issued
-        double *__restrict__ dptr = U.dst;       // row being written
-        const int64_t sstep = U.sstep, dstep = U.dstep, srow = U.srow, drow = U.drow;
+        const int64_t sstep = U.sstep, dstep = U.dstep;
         const int len = U.len;
         const int ncr = (len + 32 * STREAM_PER - 1) / (32 * STREAM_PER); // chunks per row
-        const int nchunks = ncr * U.rows;
-        int ic = 0; // chunk inside the row being issued
-        auto issue = [&](int c) {
-            if (c < nchunks) {
-                double *slot = my + (size_t)(c % RING_STAGES) * STREAM_PER * 32;
+        const int ngr = (ncr + PIECE_CHUNKS - 1) / PIECE_CHUNKS;         // pieces per row
+        const int npieces = U.rows * ngr;
+        // issue side: piece ip, chunks [ic, ic_end) of its row, row base isrc
+        int ip = wib, ic = 0, ic_end = 0, qi = 0;
+        const double *__restrict__ isrc = U.src;
+        auto open_issue = [&]() {
+            if (ip < npieces) {
+                const int r = ip / ngr, g = ip - r * ngr;
+                isrc = U.src + (int64_t)r * U.srow;
+                ic = g * PIECE_CHUNKS, ic_end = min(ncr, ic + PIECE_CHUNKS);
+            }
+        };
+        open_issue();
+        auto issue = [&]() {
+            if (ip < npieces) {
+                double *slot = my + (size_t)(qi % RING_STAGES) * STREAM_PER * 32;
 #pragma unroll
                 for (int r = 0; r < STREAM_PER; r++) {
                     const int l = ic * 32 * STREAM_PER + r * 32 + lane;
                     if (l < len)
-                        cp_async8(slot + r * 32, sptr + l * sstep);
+                        cp_async8(slot + r * 32, isrc + l * sstep);
                 }
-                if (++ic == ncr)
-                    ic = 0, sptr += srow;
+                qi++;
+                if (++ic == ic_end)
+                    ip += NW, open_issue();
             }
             asm volatile("cp.async.commit_group;\n" ::: "memory");
         };
 #pragma unroll
         for (int c = 0; c < RING_STAGES - 1; c++)
-            issue(c);
-        int wc = 0; // chunk inside the row being written
-        for (int c = 0; c < nchunks; c++) {
-            issue(c + RING_STAGES - 1);
-            asm volatile("cp.async.wait_group %0;\n" ::"n"(RING_STAGES - 1) : "memory");
-            const double *slot = my + (size_t)(c % RING_STAGES) * STREAM_PER * 32;
+            issue();
+        // write side: the same walk, RING_STAGES - 1 steps behind
+        int q = 0;
+        for (int wp = wib; wp < npieces; wp += NW) {
+            const int r = wp / ngr, g = wp - r * ngr;
+            double *__restrict__ dptr = U.dst + (int64_t)r * U.drow;
+            const int wc_end = min(ncr, (g + 1) * PIECE_CHUNKS);
+            for (int wc = g * PIECE_CHUNKS; wc < wc_end; wc++, q++) {
+                issue();
+                asm volatile("cp.async.wait_group %0;\n" ::"n"(RING_STAGES - 1) : "memory");
+                const double *slot = my + (size_t)(q % RING_STAGES) * STREAM_PER * 32;
 #pragma unroll
-            for (int r = 0; r < STREAM_PER; r++) {
-                const int l = wc * 32 * STREAM_PER + r * 32 + lane;
-                if (l < len)
-                    dptr[l * dstep] = f * slot[r * 32];
+                for (int rr = 0; rr < STREAM_PER; rr++) {
+                    const int l = wc * 32 * STREAM_PER + rr * 32 + lane;
+                    if (l < len)
+                        dptr[l * dstep] = f * slot[rr * 32];
+                }
             }
-            if (++wc == ncr)
-                wc = 0, dptr += drow;
-            if (c == 0 && more)
-                bnext = __ldg(N.b); // N has arrived by now; its scalar is ready when this unit ends
         }
-        U = N, bval = bnext;
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        U = N;
+        if (more)
+            bval = __ldg(U.b); // N arrived long ago; one dependent load per unit
     }
 }
 
@@ -304,47 +323,54 @@ static_assert(sizeof(MultiUnit) == 8 + 4 * 8 * MULTI_MAX + 8 * MULTI_MAX + 24, "
 __global__ void __launch_bounds__(BLK_THREADS, 3)
 b2g_blocking_multi_kernel(const MultiUnit *__restrict__ units, int64_t nunits, int dst_zero) {
     extern __shared__ double ring[];
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * BLK_THREADS + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * BLK_THREADS) >> 5;
-    double *my = ring + ((size_t)(threadIdx.x >> 5) * RING_STAGES * STREAM_PER) * 32 + lane;
-    for (int64_t u = warp; u < nunits; u += nwarps) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr int NW = BLK_THREADS / 32;
+    double *my = ring + ((size_t)wib * RING_STAGES * STREAM_PER) * 32 + lane;
+    for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) { // one CTA per unit, warps take its pieces in turn
         const MultiUnit &G = units[u];
         const int count = G.count, len = G.len;
-        const int64_t dstep = G.dstep, drow = G.drow;
-        double *__restrict__ dptr = G.dst; // row being accumulated
-        const double *sp[MULTI_MAX];       // rows being issued
+        const int64_t dstep = G.dstep;
+        const double *s0[MULTI_MAX]; // unit origin of every source
+        const double *sp[MULTI_MAX]; // row of the piece being issued
         double f[MULTI_MAX], bt[MULTI_MAX];
         int64_t ss[MULTI_MAX], sr[MULTI_MAX];
 #pragma unroll
         for (int t = 0; t < MULTI_MAX; t++) {
             const bool on = t < count;
-            sp[t] = on ? G.src[t] : nullptr, ss[t] = on ? G.sstep[t] : 0, sr[t] = on ? G.srow[t] : 0;
+            s0[t] = on ? G.src[t] : nullptr, sp[t] = s0[t], ss[t] = on ? G.sstep[t] : 0, sr[t] = on ? G.srow[t] : 0;
             f[t] = on ? G.alpha[t] * __ldg(G.b[t]) : 0.0, bt[t] = on ? G.beta[t] : 1.0;
         }
         const int ncr = (len + 32 * STREAM_PER - 1) / (32 * STREAM_PER); // chunks per row
-        const int steps = ncr * count * G.rows;
-        int qi = 0, ci = 0, ti = 0;
+        const int ngr = (ncr + PIECE_CHUNKS - 1) / PIECE_CHUNKS;         // pieces per row
+        const int npieces = G.rows * ngr;
+        // issue side: piece ip, chunk ci of [.., ci_end) of its row, contribution ti
+        int ip = wib, ci = 0, ci_end = 0, ti = 0, qi = 0;
+        auto open_issue = [&]() {
+            if (ip < npieces) {
+                const int r = ip / ngr, g = ip - r * ngr;
+#pragma unroll
+                for (int t = 0; t < MULTI_MAX; t++)
+                    sp[t] = s0[t] + (int64_t)r * sr[t];
+                ci = g * PIECE_CHUNKS, ci_end = min(ncr, ci + PIECE_CHUNKS);
+            }
+        };
+        open_issue();
         auto issue = [&]() {
-            if (qi < steps) {
+            if (ip < npieces) {
                 double *slot = my + (size_t)(qi % RING_STAGES) * STREAM_PER * 32;
-                const double *s0 = ti == 0 ? sp[0] : (ti == 1 ? sp[1] : (ti == 2 ? sp[2] : sp[3]));
+                const double *sx = ti == 0 ? sp[0] : (ti == 1 ? sp[1] : (ti == 2 ? sp[2] : sp[3]));
                 const int64_t st = ti == 0 ? ss[0] : (ti == 1 ? ss[1] : (ti == 2 ? ss[2] : ss[3]));
 #pragma unroll
                 for (int r = 0; r < STREAM_PER; r++) {
                     const int l = ci * 32 * STREAM_PER + r * 32 + lane;
                     if (l < len)
-                        cp_async8(slot + r * 32, s0 + l * st);
+                        cp_async8(slot + r * 32, sx + l * st);
                 }
                 qi++;
                 if (++ti == count) {
                     ti = 0;
-                    if (++ci == ncr) { // next row of every source
-                        ci = 0;
-#pragma unroll
-                        for (int t = 0; t < MULTI_MAX; t++)
-                            sp[t] += sr[t];
-                    }
+                    if (++ci == ci_end)
+                        ip += NW, open_issue();
                 }
             }
             asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -353,38 +379,42 @@ b2g_blocking_multi_kernel(const MultiUnit *__restrict__ units, int64_t nunits, i
         for (int p = 0; p < RING_STAGES - 1; p++)
             issue();
         double acc[STREAM_PER];
-        int tc = 0, cc = 0;
-        for (int q = 0; q < steps; q++) {
-            issue();
-            asm volatile("cp.async.wait_group %0;\n" ::"n"(RING_STAGES - 1) : "memory");
-            const double *slot = my + (size_t)(q % RING_STAGES) * STREAM_PER * 32;
-            if (tc == 0) {
+        int q = 0;
+        for (int wp = wib; wp < npieces; wp += NW) { // write side: the same walk, RING_STAGES - 1 steps behind
+            const int r = wp / ngr, g = wp - r * ngr;
+            double *__restrict__ dptr = G.dst + (int64_t)r * G.drow;
+            const int cc_end = min(ncr, (g + 1) * PIECE_CHUNKS);
+            for (int cc = g * PIECE_CHUNKS; cc < cc_end; cc++)
+                for (int tc = 0; tc < count; tc++, q++) {
+                    issue();
+                    asm volatile("cp.async.wait_group %0;\n" ::"n"(RING_STAGES - 1) : "memory");
+                    const double *slot = my + (size_t)(q % RING_STAGES) * STREAM_PER * 32;
+                    if (tc == 0) {
 #pragma unroll
-                for (int r = 0; r < STREAM_PER; r++) {
-                    const int l = cc * 32 * STREAM_PER + r * 32 + lane;
-                    acc[r] = (!dst_zero && l < len) ? dptr[l * dstep] : 0.0;
+                        for (int rr = 0; rr < STREAM_PER; rr++) {
+                            const int l = cc * 32 * STREAM_PER + rr * 32 + lane;
+                            acc[rr] = (!dst_zero && l < len) ? dptr[l * dstep] : 0.0;
+                        }
+                    }
+                    const double ft = tc == 0 ? f[0] : (tc == 1 ? f[1] : (tc == 2 ? f[2] : f[3]));
+                    const double be = tc == 0 ? bt[0] : (tc == 1 ? bt[1] : (tc == 2 ? bt[2] : bt[3]));
+#pragma unroll
+                    for (int rr = 0; rr < STREAM_PER; rr++) {
+                        const int l = cc * 32 * STREAM_PER + rr * 32 + lane;
+                        if (l < len)
+                            acc[rr] = fma(ft, slot[rr * 32], be == 1.0 ? acc[rr] : (be == 0.0 ? 0.0 : be * acc[rr]));
+                    }
+                    if (tc == count - 1) {
+#pragma unroll
+                        for (int rr = 0; rr < STREAM_PER; rr++) {
+                            const int l = cc * 32 * STREAM_PER + rr * 32 + lane;
+                            if (l < len)
+                                dptr[l * dstep] = acc[rr];
+                        }
+                    }
                 }
-            }
-            const double ft = tc == 0 ? f[0] : (tc == 1 ? f[1] : (tc == 2 ? f[2] : f[3]));
-            const double be = tc == 0 ? bt[0] : (tc == 1 ? bt[1] : (tc == 2 ? bt[2] : bt[3]));
-#pragma unroll
-            for (int r = 0; r < STREAM_PER; r++) {
-                const int l = cc * 32 * STREAM_PER + r * 32 + lane;
-                if (l < len)
-                    acc[r] = fma(ft, slot[r * 32], be == 1.0 ? acc[r] : (be == 0.0 ? 0.0 : be * acc[r]));
-            }
-            if (++tc == count) {
-#pragma unroll
-                for (int r = 0; r < STREAM_PER; r++) {
-                    const int l = cc * 32 * STREAM_PER + r * 32 + lane;
-                    if (l < len)
-                        dptr[l * dstep] = acc[r];
-                }
-                tc = 0;
-                if (++cc == ncr)
-                    cc = 0, dptr += drow;
-            }
         }
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     }
 }
 
@@ -395,10 +425,10 @@ b2g_blocking_multi_kernel(const MultiUnit *__restrict__ units, int64_t nunits, i
 // ring, one contribution per step) and folded into the running values (TILE_R per lane, registers) in
 // list order.  The tile is written once, row by row.
 constexpr int TILE_R = 16, TILE_C = 32, TILE_LD = TILE_C + 1, TILE_STAGES = 3;
-constexpr int TILE_STRIP = 8; // column tiles per unit
+constexpr int TILE_STRIP = 32; // column tiles per unit (a CTA of 8 warps works on one unit)
 constexpr int TILE_SLOT = TILE_R * TILE_LD + 4; // tile + (b, alpha, beta, pad) of the step
 constexpr size_t TILE_RING_BYTES = (size_t)(BLK_THREADS / 32) * TILE_STAGES * TILE_SLOT * sizeof(double);
-struct TileUnit { // 40 bytes: `ntiles` consecutive column tiles of one tile row, starting at (i0, j0)
+struct TileUnit { // 40 bytes: `ntiles` tiles, row-major over the tile rows of the window that start at row i0
     double *dst;  // window origin
     int32_t i0, j0, m, n, ldc, first, count, ntiles;
 };
@@ -408,14 +438,14 @@ __global__ void __launch_bounds__(BLK_THREADS, 2)
 b2g_blocking_tile_kernel(const TileUnit *__restrict__ units, int64_t nunits, const BlkEntry *__restrict__ entries,
                          int dst_zero) {
     extern __shared__ double ring[];
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * BLK_THREADS + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * BLK_THREADS) >> 5;
-    double *my = ring + (size_t)(threadIdx.x >> 5) * TILE_STAGES * TILE_SLOT;
-    for (int64_t u = warp; u < nunits; u += nwarps)
-      for (int tj = 0, ntj = units[u].ntiles; tj < ntj; tj++) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr int NW = BLK_THREADS / 32;
+    double *my = ring + (size_t)wib * TILE_STAGES * TILE_SLOT;
+    for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) // one CTA per unit, warps take its tiles in turn
+      for (int tt = wib, ntt = units[u].ntiles; tt < ntt; tt += NW) {
         TileUnit U = units[u];
-        U.j0 += tj * TILE_C;
+        const int tpr = (U.n + TILE_C - 1) / TILE_C, trow = tt / tpr; // tiles per tile row
+        U.i0 += trow * TILE_R, U.j0 = (tt - trow * tpr) * TILE_C;
         const int rows = min(TILE_R, U.m - U.i0), cols = min(TILE_C, U.n - U.j0);
         double *__restrict__ dptr = U.dst + (int64_t)U.i0 * U.ldc + U.j0;
         BlkEntry Ep = entries[U.first];
@@ -782,24 +812,23 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
         static const bool tile_narrow = getenv("B2G_BLK_NOTILE_NARROW") == nullptr;
         if (axpy && tile_on && w.n >= TILE_C && w.m >= 2 &&
             ((transposed_src && cl[ci].count >= 2) || (tile_narrow && w.n < ROW_MIN))) {
-            // a unit = up to TILE_STRIP column tiles of one tile row (cost: tiles x contributions)
-            const int64_t strip = std::max<int64_t>(1, std::min<int64_t>(TILE_STRIP, 4 * TILE_STRIP / cl[ci].count));
-            for (int64_t i0 = 0; i0 < w.m; i0 += TILE_R)
-                for (int64_t j0 = 0; j0 < w.n; j0 += TILE_C * strip)
-                    tunits.push_back(TileUnit{w.dst, (int32_t)i0, (int32_t)j0, w.m, w.n, w.ldc, first, cl[ci].count,
-                                              (int32_t)std::min<int64_t>(strip, (w.n - j0 + TILE_C - 1) / TILE_C)});
+            // a unit = whole tile rows, about TILE_STRIP tiles (cost: tiles x contributions)
+            const int64_t tpr = (w.n + TILE_C - 1) / TILE_C;
+            const int64_t want = std::max<int64_t>(8, std::min<int64_t>(TILE_STRIP, 4 * TILE_STRIP / cl[ci].count));
+            const int64_t trows = std::max<int64_t>(1, want / tpr); // tile rows per unit
+            for (int64_t i0 = 0; i0 < w.m; i0 += TILE_R * trows) {
+                const int64_t nrows = std::min<int64_t>(trows, (w.m - i0 + TILE_R - 1) / TILE_R);
+                tunits.push_back(TileUnit{w.dst, (int32_t)i0, 0, w.m, w.n, w.ldc, first, cl[ci].count,
+                                          (int32_t)(nrows * tpr)});
+            }
         } else if (lin) {
-            const int64_t per = std::max<int64_t>(256, lin_target / cl[ci].count / 256 * 256); // elements per unit
+            // elements per unit: the warps of a CTA share a unit piece by piece (b2g_blocking_stream_kernel)
+            const int64_t per = std::max<int64_t>(2048, lin_target / cl[ci].count / 256 * 256);
             if (w.n == 1) { // a column (or a dense window addressed flat): one "row" of elements ldc apart
                 for (int64_t e0 = 0; e0 < total; e0 += per)
                     lunits.push_back(LinUnit{w.dst, 0, 1, (int32_t)e0, (int32_t)std::min<int64_t>(per, total - e0), w.n,
                                              w.ldc, first, cl[ci].count});
-            } else if (w.n > per) {
-                for (int64_t i = 0; i < w.m; i++)
-                    for (int64_t j0 = 0; j0 < w.n; j0 += per)
-                        lunits.push_back(LinUnit{w.dst, (int32_t)i, 1, (int32_t)j0, (int32_t)std::min<int64_t>(per, w.n - j0),
-                                                 w.n, w.ldc, first, cl[ci].count});
-            } else {
+            } else { // whole rows
                 const int64_t rows = std::max<int64_t>(1, per / w.n);
                 for (int64_t i0 = 0; i0 < w.m; i0 += rows)
                     lunits.push_back(LinUnit{w.dst, (int32_t)i0, (int32_t)std::min<int64_t>(rows, w.m - i0), 0, w.n, w.n,
@@ -1079,21 +1108,18 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
         ctx->blocking_attr_set = true;
     }
     if (!sunits.empty()) {
-        const int64_t want = ((int64_t)sunits.size() * 32 + BLK_THREADS - 1) / BLK_THREADS;
-        const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 3); // 3 resident CTAs per SM
+        const int grid = (int)std::min<int64_t>((int64_t)sunits.size(), (int64_t)ctx->sm_count * 3); // 3 CTAs per SM
         b2g_blocking_stream_kernel<<<grid, BLK_THREADS, RING_BYTES, ctx->stream>>>(d_sunits, (int64_t)sunits.size());
         ctx->launches++, st.launches++;
     }
     if (!munits.empty()) {
-        const int64_t want = ((int64_t)munits.size() * 32 + BLK_THREADS - 1) / BLK_THREADS;
-        const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 3);
+        const int grid = (int)std::min<int64_t>((int64_t)munits.size(), (int64_t)ctx->sm_count * 3);
         b2g_blocking_multi_kernel<<<grid, BLK_THREADS, RING_BYTES, ctx->stream>>>(d_munits, (int64_t)munits.size(),
                                                                                   dst_zero ? 1 : 0);
         ctx->launches++, st.launches++;
     }
     if (!tunits.empty()) {
-        const int64_t want = ((int64_t)tunits.size() * 32 + BLK_THREADS - 1) / BLK_THREADS;
-        const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 2);
+        const int grid = (int)std::min<int64_t>((int64_t)tunits.size(), (int64_t)ctx->sm_count * 2);
         b2g_blocking_tile_kernel<<<grid, BLK_THREADS, TILE_RING_BYTES, ctx->stream>>>(d_tunits, (int64_t)tunits.size(),
                                                                                       d_entries, dst_zero ? 1 : 0);
         ctx->launches++, st.launches++;

@@ -101,7 +101,11 @@ extern "C" int b2g_context_create(int device, b2g_context **out) {
     // site would otherwise pay cudaMalloc/cudaFree every time
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
+        // unused pool memory beyond this is returned to the driver at the next synchronisation: the blocks of
+        // consecutive sites differ in size, and a pool that never lets go fragments (Cr2 M=4000: 132 GB reserved
+        // for ~100 GB in use, then out of memory)
+        const char *keep = getenv("B2G_POOL_KEEP_GB");
+        uint64_t thr = (uint64_t)((keep ? atof(keep) : 32.0) * 1e9);
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     ctx->up_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
@@ -116,8 +120,38 @@ extern "C" int b2g_context_create(int device, b2g_context **out) {
     return 0;
 }
 
+static void trim_pool(b2g_context *ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess)
+        cudaMemPoolTrimTo(pool, 0);
+}
 int b2g_dmalloc(b2g_context *ctx, void **ptr, size_t bytes) {
-    B2G_CUDA(cudaMallocAsync(ptr, std::max<size_t>(bytes, 16), ctx->stream));
+    const size_t want = std::max<size_t>(bytes, 16);
+    cudaError_t e = cudaMallocAsync(ptr, want, ctx->stream);
+    if (e == cudaErrorMemoryAllocation) { // unused blocks of the pool that do not fit: give them back, try again
+        cudaGetLastError();
+        trim_pool(ctx);
+        e = cudaMallocAsync(ptr, want, ctx->stream);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        size_t f = 0, t = 0;
+        cudaMemGetInfo(&f, &t);
+        b2g_set_error("device allocation of " + std::to_string(want) + " bytes failed (" + cudaGetErrorString(e) +
+                      "; out of memory: " + std::to_string(f >> 20) + " MiB free of " + std::to_string(t >> 20) + ")");
+        *ptr = nullptr;
+        return 1;
+    }
+    return 0;
+}
+extern "C" int b2g_mem_trim(b2g_context *ctx) {
+    if (!ctx) {
+        b2g_set_error("b2g_mem_trim: null context");
+        return 1;
+    }
+    B2G_CUDA(cudaSetDevice(ctx->device));
+    trim_pool(ctx);
     return 0;
 }
 void b2g_dfree(b2g_context *ctx, void *ptr) {
@@ -572,6 +606,45 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
     }
     *out = p;
     return 0;
+}
+
+// Host-side regrouping of a chained pair list into the two-phase tile plan, without a device (timing and
+// tests of the planner): seconds = wall time of the regrouping, units = CTA work units, launches = kernel launches.
+extern "C" int b2g_debug_tiled_plan(const b2g_batch *b0, const b2g_batch *b1, double *seconds, int64_t *units,
+                                    int64_t *launches) {
+    if (!b0 || !b1 || b0->count != b1->count) {
+        b2g_set_error("b2g_debug_tiled_plan: bad argument");
+        return 1;
+    }
+    b2g_plan *p = new b2g_plan();
+    p->ctx = nullptr, p->npairs = b0->count;
+    p->h_pairs.resize((size_t)b0->count);
+    for (int64_t i = 0; i < b0->count; i++) {
+        B2GPair &q = p->h_pairs[(size_t)i];
+        q.b0 = b0->b[i], q.a1 = b1->a[i];
+        q.alpha0 = b0->alpha[i], q.alpha1 = b1->alpha[i];
+        q.a0_off = (int64_t)((uintptr_t)b0->a[i] / sizeof(double)), q.c1_off = (int64_t)((uintptr_t)b1->c[i] / sizeof(double));
+        q.m0 = b0->m[i], q.n0 = b0->n[i], q.k0 = b0->k[i], q.m1 = b1->m[i];
+        q.lda0 = b0->lda[i], q.ldb0 = b0->ldb[i], q.lda1 = b1->lda[i], q.ldc1 = b1->ldc[i];
+        q.flags = (is_trans(b0->tb[i]) ? B2G_F_TB0 : 0) | (is_trans(b1->ta[i]) ? B2G_F_TA1 : 0);
+        q.pad = 0;
+    }
+    std::stable_sort(p->h_pairs.begin(), p->h_pairs.end(), [](const B2GPair &x, const B2GPair &y) {
+        if (x.c1_off != y.c1_off)
+            return x.c1_off < y.c1_off;
+        return x.a0_off < y.a0_off;
+    });
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = b2g_tiled_build(p);
+    if (seconds)
+        *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (units)
+        *units = p->stats.n_large;
+    if (launches)
+        *launches = p->stats.launches;
+    b2g_tiled_destroy(p->tiled);
+    delete p;
+    return rc;
 }
 
 extern "C" int b2g_plan_destroy(b2g_plan *p) {

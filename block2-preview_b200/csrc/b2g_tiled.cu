@@ -498,6 +498,30 @@ struct Key4Hash {
         return (size_t)(h ^ (h >> 32));
     }
 };
+// Key4 -> int, open addressing with linear probing (the regrouping does a few lookups per pair of lists with
+// 10^5 pairs, once per site: node-based maps were a third of the plan construction time)
+struct FlatMap4 {
+    std::vector<Key4> keys;
+    std::vector<int> vals; // -1 = empty
+    size_t mask = 0;
+    explicit FlatMap4(size_t expected) {
+        size_t cap = 16;
+        while (cap < 2 * expected + 2)
+            cap <<= 1;
+        keys.resize(cap), vals.assign(cap, -1), mask = cap - 1;
+    }
+    // value of key, inserting `fresh` when absent; second = inserted
+    std::pair<int, bool> get_or_insert(const Key4 &k, int fresh) {
+        size_t i = Key4Hash()(k) & mask;
+        while (vals[i] >= 0) {
+            if (keys[i] == k)
+                return std::make_pair(vals[i], false);
+            i = (i + 1) & mask;
+        }
+        keys[i] = k, vals[i] = fresh;
+        return std::make_pair(fresh, true);
+    }
+};
 } // namespace
 
 void b2g_tiled_destroy(void *h) {
@@ -505,7 +529,8 @@ void b2g_tiled_destroy(void *h) {
     if (!tp)
         return;
     for (void *p : tp->to_free)
-        b2g_dfree(tp->ctx, p);
+        if (tp->ctx)
+            b2g_dfree(tp->ctx, p);
     delete tp;
 }
 
@@ -525,10 +550,13 @@ int b2g_tiled_build(b2g_plan *p) {
     static const bool verbose = getenv("B2G_VERBOSE") != nullptr;
     auto tstart = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) {
-        if (verbose) {
+        if (verbose || b2g_prof_enabled()) {
             auto now = std::chrono::steady_clock::now();
-            fprintf(stderr, "[b2g] tiled_build %-14s %8.3f ms\n", what,
-                    std::chrono::duration<double, std::milli>(now - tstart).count());
+            if (verbose)
+                fprintf(stderr, "[b2g] tiled_build %-14s %8.3f ms\n", what,
+                        std::chrono::duration<double, std::milli>(now - tstart).count());
+            b2g_prof_record((std::string("tiled_build.") + what).c_str(),
+                            std::chrono::duration<double>(now - tstart).count());
             tstart = now;
         }
     };
@@ -540,7 +568,7 @@ int b2g_tiled_build(b2g_plan *p) {
         int64_t lo, hi;
         int block, row, col, panel, layer;
     };
-    std::unordered_map<Key4, int, Key4Hash> wid;
+    FlatMap4 wid(n);
     std::vector<Win> wv;
     std::vector<int> pair_win(n, -1);
     for (size_t i = 0; i < n; i++) {
@@ -548,13 +576,11 @@ int b2g_tiled_build(b2g_plan *p) {
         if (q.m0 == 0 || q.n0 == 0 || q.m1 == 0)
             continue;
         const Key4 key{(uint64_t)q.c1_off, (uint64_t)(uint32_t)q.m1, (uint64_t)(uint32_t)q.n0, (uint64_t)(uint32_t)q.ldc1};
-        auto it = wid.find(key);
-        if (it == wid.end()) {
-            it = wid.emplace(key, (int)wv.size()).first;
+        const std::pair<int, bool> it = wid.get_or_insert(key, (int)wv.size());
+        if (it.second)
             wv.push_back(Win{q.c1_off, q.m1, q.n0, q.ldc1, q.c1_off,
                              q.c1_off + (int64_t)(q.m1 - 1) * q.ldc1 + q.n0, -1, 0, 0, -1, 0});
-        }
-        pair_win[i] = it->second;
+        pair_win[i] = it.first;
     }
     {
         std::vector<int> order(wv.size());
@@ -649,27 +675,27 @@ int b2g_tiled_build(b2g_plan *p) {
         int64_t w_off;
         int wld, col_lo, col_hi;
     };
-    std::unordered_map<Key4, int, Key4Hash> sid;
+    FlatMap4 sid(n);
     std::vector<HostSeg> hsegs;
     // (segment, window) -> group; a (segment, window) fed through both operand layouts of B0 needs two W slots:
     // the second layout gets a twin segment (same A1, K longer by m0) so that no W element is written twice
     struct HostGroup {
         int seg, win, tb0;
-        std::vector<size_t> pairs;
+        int count, first; // pairs of the group: pair_of[first .. first + count)
+        int64_t ksum;     // sum of k0 over the pairs
+        int nsteps;       // BK-deep stages (every tile configuration has BK = 16)
     };
-    std::unordered_map<Key4, int, Key4Hash> gid;
+    std::vector<int> pair_group(n, -1);
+    FlatMap4 gid(2 * n);
     std::vector<HostGroup> hgroups;
-    std::unordered_map<int, int> twin;
     auto seg_of = [&](int panel, int layer, const B2GPair &q, int variant) -> int {
         const int ta1 = (q.flags & B2G_F_TA1) ? 1 : 0;
         const Key4 sk{(uint64_t)(uintptr_t)q.a1, ((uint64_t)(uint32_t)panel << 32) | (uint32_t)q.lda1,
                       ((uint64_t)(uint32_t)q.m0 << 32) | (uint32_t)layer, (uint64_t)(ta1 | (variant << 1))};
-        auto it = sid.find(sk);
-        if (it == sid.end()) {
-            it = sid.emplace(sk, (int)hsegs.size()).first;
+        const std::pair<int, bool> r = sid.get_or_insert(sk, (int)hsegs.size());
+        if (r.second)
             hsegs.push_back(HostSeg{panel, layer, ta1, q.lda1, q.m0, q.a1, 0, 0, INT32_MAX, 0});
-        }
-        return it->second;
+        return r.first;
     };
     for (size_t i = 0; i < n; i++) {
         if (pair_win[i] < 0)
@@ -679,30 +705,36 @@ int b2g_tiled_build(b2g_plan *p) {
         const int tb0 = (q.flags & B2G_F_TB0) ? 1 : 0;
         int seg = seg_of(x.panel, x.layer, q, 0);
         const Key4 gk{(uint64_t)(uint32_t)seg, (uint64_t)(uint32_t)pair_win[i], 0, 0};
-        auto it = gid.find(gk);
-        int g;
-        if (it == gid.end()) {
-            g = (int)hgroups.size();
-            gid.emplace(gk, g);
-            hgroups.push_back(HostGroup{seg, pair_win[i], tb0, {}});
-        } else {
-            g = it->second;
-            if (hgroups[g].tb0 != tb0) { // the other layout: same window, twin segment
-                seg = seg_of(x.panel, x.layer, q, 1);
-                const Key4 gk2{(uint64_t)(uint32_t)seg, (uint64_t)(uint32_t)pair_win[i], 0, 0};
-                auto it2 = gid.find(gk2);
-                if (it2 == gid.end()) {
-                    g = (int)hgroups.size();
-                    gid.emplace(gk2, g);
-                    hgroups.push_back(HostGroup{seg, pair_win[i], tb0, {}});
-                } else
-                    g = it2->second;
-            }
+        std::pair<int, bool> r = gid.get_or_insert(gk, (int)hgroups.size());
+        int g = r.first;
+        if (r.second)
+            hgroups.push_back(HostGroup{seg, pair_win[i], tb0, 0, 0, 0, 0});
+        else if (hgroups[g].tb0 != tb0) { // the other layout: same window, twin segment
+            seg = seg_of(x.panel, x.layer, q, 1);
+            const Key4 gk2{(uint64_t)(uint32_t)seg, (uint64_t)(uint32_t)pair_win[i], 0, 0};
+            r = gid.get_or_insert(gk2, (int)hgroups.size());
+            g = r.first;
+            if (r.second)
+                hgroups.push_back(HostGroup{seg, pair_win[i], tb0, 0, 0, 0, 0});
         }
         HostSeg &hs = hsegs[hgroups[g].seg];
         hs.col_lo = std::min(hs.col_lo, x.col), hs.col_hi = std::max(hs.col_hi, x.col + x.n0);
-        hgroups[g].pairs.push_back(i);
+        hgroups[g].count++, hgroups[g].ksum += q.k0, hgroups[g].nsteps += (q.k0 + 15) / 16;
+        pair_group[i] = g;
     }
+    // pairs by group, in list order (= ascending a0_off: neighbours read the same wavefunction window)
+    std::vector<int> pair_of(n);
+    {
+        int acc = 0;
+        for (HostGroup &hg : hgroups)
+            hg.first = acc, acc += hg.count, hg.count = 0;
+        for (size_t i = 0; i < n; i++)
+            if (pair_group[i] >= 0) {
+                HostGroup &hg = hgroups[pair_group[i]];
+                pair_of[hg.first + hg.count++] = (int)i;
+            }
+    }
+    lap("groups.hash");
     // W panels: m0 x wld per segment, wld = the column span its groups cover (even, so that rows stay 16-byte
     // aligned); columns of the span no group writes stay zero from the one memset below
     size_t woff = 0;
@@ -723,11 +755,11 @@ int b2g_tiled_build(b2g_plan *p) {
         g.w_off = hs.w_off + (x.col - hs.col_lo), g.wld = hs.wld, g.m0 = hs.m0, g.n0 = x.n0;
         g.seg_begin = (int)p1s.size();
         // neighbours read the same wavefunction window (L2 reuse of c inside the group)
-        if (hg.pairs.size() > 1)
-            std::stable_sort(hg.pairs.begin(), hg.pairs.end(),
-                             [&hp](size_t a, size_t b) { return hp[a].a0_off < hp[b].a0_off; });
-        for (size_t i : hg.pairs) {
-            const B2GPair &q = hp[i];
+        if (hg.count > 1)
+            std::stable_sort(pair_of.begin() + hg.first, pair_of.begin() + hg.first + hg.count,
+                             [&hp](int a, int b) { return hp[a].a0_off < hp[b].a0_off; });
+        for (int z = 0; z < hg.count; z++) {
+            const B2GPair &q = hp[pair_of[hg.first + z]];
             p1s.push_back(P1Seg{q.b0, q.a0_off, q.alpha0 * q.alpha1, q.lda0, q.ldb0, q.k0, 0});
         }
         g.seg_end = (int)p1s.size(), g.pad = 0;
@@ -740,23 +772,28 @@ int b2g_tiled_build(b2g_plan *p) {
         Unit u;
         double cost, flops;
     };
-    std::map<std::tuple<int, int, int>, std::vector<HostUnit>> groups; // (phase, cfg, layout)
+    // (phase, cfg, layout) -> units; flat table (a map lookup per unit costs more than the unit itself)
+    constexpr int N_CFG = 8;
+    std::vector<HostUnit> unit_tab[2 * N_CFG * 2];
+    auto units_of = [&unit_tab](int phase, int cfg, int layout) -> std::vector<HostUnit> & {
+        return unit_tab[((phase - 1) * N_CFG + cfg) * 2 + layout];
+    };
     for (size_t gi = 0; gi < hgroups.size(); gi++) {
         const HostGroup &hg = hgroups[gi];
         const P1Group &g = p1g[gi];
-        int64_t ksum = 0;
-        int nsteps = 0; // every tile configuration has BK = 16
-        for (size_t i : hg.pairs)
-            ksum += hp[i].k0, nsteps += (hp[i].k0 + 15) / 16;
-        for (const Strip &rs : split_rows(g.m0))
-            for (const Strip &cs : split_cols(g.n0)) {
+        const int64_t ksum = hg.ksum;
+        const int nsteps = hg.nsteps;
+        const std::vector<Strip> rsv1 = split_rows(g.m0), csv1 = split_cols(g.n0);
+        for (const Strip &rs : rsv1)
+            for (const Strip &cs : csv1) {
                 const int c = cfg_of(rs.tile, cs.tile);
-                groups[std::make_tuple(1, c, hg.tb0)].push_back(HostUnit{
+                units_of(1, c, hg.tb0).push_back(HostUnit{
                     Unit{(int)gi, rs.origin, cs.origin, 0, 0, nsteps, -1},
-                    (double)rs.tile * cs.tile * (double)(ksum + 32 * (int64_t)hg.pairs.size()),
+                    (double)rs.tile * cs.tile * (double)(ksum + 32 * (int64_t)hg.count),
                     2.0 * std::min(rs.tile, g.m0 - rs.origin) * std::min(cs.tile, g.n0 - cs.origin) * (double)ksum});
             }
     }
+    lap("units.p1");
     std::vector<P2Window> wins(panels.size());
     for (size_t k = 0; k < panels.size(); k++)
         wins[k] = P2Window{panels[k].c_off, panels[k].ldc, panels[k].m1, panels[k].col_hi - panels[k].col_lo, 0};
@@ -781,10 +818,11 @@ int b2g_tiled_build(b2g_plan *p) {
                     ks += hsegs[k].m0;
                 tile_k += ks * (double)split_rows(wins[w].m1).size() * (double)split_cols(wins[w].n0).size();
             }
-        const double want_units = 24.0 * ctx->sm_count;
+        const double want_units = 24.0 * (ctx ? ctx->sm_count : 148);
         kchunk_eff = (int64_t)std::min<double>(2048.0, std::max(128.0, tile_k / want_units));
         kchunk_eff = (kchunk_eff + 15) / 16 * 16;
     }
+    lap("units.kchunk");
     std::vector<P2Seg> segs;
     for (int lay = 0; lay < 2; lay++)
         for (size_t w = 0; w < panels.size(); w++) {
@@ -803,7 +841,7 @@ int b2g_tiled_build(b2g_plan *p) {
                     if (s1 == s0)
                         return;
                     for (const Strip &rs : rsv)
-                        groups[std::make_tuple(2, cfg_of(rs.tile, cs.tile), lay)].push_back(
+                        units_of(2, cfg_of(rs.tile, cs.tile), lay).push_back(
                             HostUnit{Unit{(int)w, rs.origin, cs.origin, (int)s0, (int)s1, nsteps, -1},
                                      (double)rs.tile * cs.tile * (double)(ksum + 32),
                                      2.0 * std::min(rs.tile, wins[w].m1 - rs.origin) * (t_hi - t_lo) * (double)ksum});
@@ -822,7 +860,20 @@ int b2g_tiled_build(b2g_plan *p) {
             }
         }
 
+    std::map<std::tuple<int, int, int>, std::vector<HostUnit>> groups; // non-empty (phase, cfg, layout), in order
+    for (int ph = 1; ph <= 2; ph++)
+        for (int c = 0; c < N_CFG; c++)
+            for (int lay = 0; lay < 2; lay++)
+                if (!units_of(ph, c, lay).empty())
+                    groups[std::make_tuple(ph, c, lay)].swap(units_of(ph, c, lay));
     lap("units");
+    if (ctx == nullptr) { // b2g_debug_tiled_plan: the host-side regrouping alone (no device)
+        int64_t nu = 0;
+        for (auto &kv : groups)
+            nu += (int64_t)kv.second.size();
+        p->stats.launches = (int64_t)groups.size(), p->stats.n_large = nu;
+        return 0;
+    }
     // ---- 5. upload
     auto upload = [&](const void *src, size_t bytes, void **dst) -> int {
         if (b2g_dmalloc(ctx, dst, bytes))
@@ -1009,7 +1060,9 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
         B2G_CUDA(cudaEventRecord(ctx->fork_ev, ctx->stream));
     int gi = 0;
     bool phase2_open = false;
-    static const bool use_pdl = getenv("B2G_NO_PDL") == nullptr; // A/B switch
+    // Measured on the Cr2 M=4000 list: 81.8 - 82.7 ms with the chain against 73.7 - 74.1 ms without (also with the
+    // first unit claimed dynamically), so it is an experiment switch (B2G_PDL=1), off by default.
+    static const bool use_pdl = getenv("B2G_PDL") != nullptr;
     bool chain_open = false, first_p2 = true;
     for (const LaunchGroup &g : tp->groups) {
         if (g.phase == 2 && !phase2_open) { // every W panel is complete before the first phase-2 launch

@@ -58,7 +58,7 @@ struct Session {
     std::atomic<bool> recording{false};
     double t_plan = 0, t_matvec = 0, t_precompute = 0, t_davidson = 0;
     double t_contract_alloc = 0, t_contract_ensure = 0, t_contract_exec = 0, t_rotate_exec = 0, t_rotate_alloc = 0;
-    size_t n_plan = 0, n_matvec = 0;
+    size_t n_plan = 0, n_matvec = 0, n_oom_retries = 0;
     // --verify: worst relative deviation ||sigma_gpu - sigma_cpu|| / ||sigma_cpu|| over all sites,
     // sigma_cpu from the reference's own BatchGEMMSeq::operator() on the same recorded list
     bool verify = false;
@@ -890,13 +890,29 @@ template <typename S> struct GPUDMRG : DMRG<S, double, double> {
         // sigma all-reduces of the replicated Davidson iteration
         if (h_eff->tf->opf->seq->batch[0]->gp.size() != 0 || me->para_rule != nullptr) {
             pl.lap("host.eigs.verify");
-            gtf->get_plan();
-            pl.lap("host.eigs.plan");
-            tq.get_time();
-            if (b2g_davidson(gtf->get_plan(), h_eff->diag->data, h_eff->ket->data, davidson_conv_thrd,
-                             this->davidson_rel_conv_thrd, this->davidson_max_iter, this->davidson_soft_max_iter,
-                             this->davidson_def_min_size, this->davidson_def_max_size, &e, &ndav) != 0)
-                throw std::runtime_error(std::string("b2g_davidson: ") + b2g_last_error());
+            // The plan workspace (W panels, partial tiles) and the Davidson basis are allocated outside the budget
+            // of the resident environments.  When the device is full, the least recently used written-through
+            // environments go (they are re-read from their host blocks on demand) and the site is tried again.
+            for (int attempt = 0;; attempt++) {
+                try {
+                    gtf->get_plan();
+                    pl.lap("host.eigs.plan");
+                    tq.get_time();
+                    if (b2g_davidson(gtf->get_plan(), h_eff->diag->data, h_eff->ket->data, davidson_conv_thrd,
+                                     this->davidson_rel_conv_thrd, this->davidson_max_iter, this->davidson_soft_max_iter,
+                                     this->davidson_def_min_size, this->davidson_def_max_size, &e, &ndav) != 0)
+                        throw std::runtime_error(std::string("b2g_davidson: ") + b2g_last_error());
+                    break;
+                } catch (const std::runtime_error &err) {
+                    const bool oom = std::string(err.what()).find("out of memory") != std::string::npos ||
+                                     std::string(err.what()).find("failed") != std::string::npos;
+                    gtf->drop(), gtf->stale = true;
+                    gtf->store().tick(); // nothing of the failed attempt is "in use"
+                    if (!oom || attempt >= 2 || gtf->store().shrink(0.5) == 0)
+                        throw;
+                    gtf->session->n_oom_retries++;
+                }
+            }
             gtf->session->t_davidson += tq.get_time();
             pl.lap("host.eigs.davidson");
             nflop = (size_t)ndav * (h_eff->tf->opf->seq->batch[0]->nflop + h_eff->tf->opf->seq->batch[1]->nflop);

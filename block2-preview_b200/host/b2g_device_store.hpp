@@ -168,9 +168,27 @@ struct DeviceStore {
             drop_block(victim); // a block without shadows (nothing was added to it) is not dropped by erase_key
         }
     }
+    // Memory pressure outside the store's own budget (the W workspace and the Davidson basis of a large site):
+    // evict the least recently used written-through blocks until `fraction` of what is held is left, and hand
+    // the unused pool memory back to the driver.  Returns the bytes released.
+    size_t shrink(double fraction) {
+        const size_t before = held, saved = budget;
+        budget = (size_t)(fraction * (double)held);
+        make_room(0);
+        budget = saved;
+        b2g_mem_trim(ctx);
+        return before - held;
+    }
     shared_ptr<DevBlock> new_block(size_t doubles, bool zero) {
         make_room(doubles * sizeof(double));
-        shared_ptr<DevBlock> b = make_shared<DevBlock>(ctx, doubles);
+        shared_ptr<DevBlock> b;
+        try {
+            b = make_shared<DevBlock>(ctx, doubles);
+        } catch (const std::runtime_error &) { // the device is full although the budget is not: make room, once
+            if (shrink(0.5) == 0)
+                throw;
+            b = make_shared<DevBlock>(ctx, doubles);
+        }
         b->last_use = clock;
         if (zero && doubles != 0 && b2g_memset_zero(ctx, b->base, doubles * sizeof(double)) != 0)
             throw std::runtime_error(std::string("b2g_memset_zero: ") + b2g_last_error());

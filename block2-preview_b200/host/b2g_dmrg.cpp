@@ -312,7 +312,7 @@ int main(int argc, char **argv) {
            "\"resident_read_gbytes\": %.3f, \"mirrored_gbytes\": %.3f, \"resident_peak_gbytes\": %.3f, "
            "\"resident_uploaded_gbytes\": %.3f, \"resident_downloaded_gbytes\": %.3f, \"resident_evicted_gbytes\": %.3f, "
            "\"t_precompute\": %.3f, \"t_davidson\": %.3f, \"t_contract_alloc\": %.3f, \"t_contract_ensure\": %.3f, "
-           "\"t_contract_exec\": %.3f, \"t_rotate_alloc\": %.3f, \"t_rotate_exec\": %.3f}\n",
+           "\"t_contract_exec\": %.3f, \"t_rotate_alloc\": %.3f, \"t_rotate_exec\": %.3f, \"oom_retries\": %zu}\n",
            a.ranks, a.davidson.c_str(), a.bond, a.seed, gpu.energies.size(), gpu.total, ref.total, a.threads,
            gpu.energies.empty() ? 0.0 : gpu.energies.back(), ref.energies.empty() ? 0.0 : ref.energies.back(),
            maxdiff,
@@ -330,7 +330,8 @@ int main(int argc, char **argv) {
            (int)(session->pinned != nullptr), res_hit * 1e-9, res_mirrored * 1e-9, session->store->peak * 1e-9,
            session->store->uploaded_bytes * 1e-9, session->store->downloaded_bytes * 1e-9,
            session->store->evicted_bytes * 1e-9, session->t_precompute, session->t_davidson, session->t_contract_alloc,
-           session->t_contract_ensure, session->t_contract_exec, session->t_rotate_alloc, session->t_rotate_exec);
+           session->t_contract_ensure, session->t_contract_exec, session->t_rotate_alloc, session->t_rotate_exec,
+           session->n_oom_retries);
     fflush(stdout);
     b2g_prof_dump(getenv("B2G_PROF_FILE")); // B2G_PROF: wall-clock sections of the library and the binding
     _exit(0);

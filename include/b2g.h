@@ -101,6 +101,9 @@ int b2g_context_synchronize(b2g_context *ctx);
  * variable B2G_PROF): seconds and calls accumulated per label.  b2g_prof_record adds to a label (the
  * reference-side binding uses it for its own sections), b2g_prof_dump writes one JSON object to `path`
  * (NULL or "-": stderr) and returns 0; both are no-ops when the profile is off. */
+/* Host-side regrouping of a chained pair list into the two-phase tile plan, without a device (planner timing). */
+int b2g_debug_tiled_plan(const b2g_batch *batch0, const b2g_batch *batch1, double *seconds, int64_t *units,
+                         int64_t *launches);
 int b2g_prof_enabled(void);
 void b2g_prof_record(const char *label, double seconds);
 int b2g_prof_dump(const char *path);
@@ -242,6 +245,8 @@ int b2g_malloc(b2g_context *ctx, size_t bytes, void **dev);
 int b2g_free(b2g_context *ctx, void *dev);
 /* free (including memory parked in the allocation pool) and total device memory */
 int b2g_mem_info(b2g_context *ctx, int64_t *free_bytes, int64_t *total_bytes);
+/* synchronise and return every unused block of the stream-ordered pool to the driver (after evicting shadows) */
+int b2g_mem_trim(b2g_context *ctx);
 int b2g_memcpy_h2d(b2g_context *ctx, void *dev, const void *host, size_t bytes);
 int b2g_memcpy_d2h(b2g_context *ctx, void *host, const void *dev, size_t bytes);
 int b2g_memset_zero(b2g_context *ctx, void *dev, size_t bytes);

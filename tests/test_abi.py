@@ -37,3 +37,22 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".h", ".hpp", ".cpp", ".cuh")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("# oracle-free", ""), f
+
+
+@pytest.mark.parametrize("name", ["n2_su2_m30_s8.b2seq", "n2_su2_m60_s4.b2seq", "h10_sz_m40_s4.b2seq"])
+def test_tile_plan_regrouping_runs_on_the_host(b2g, name):
+    """b2g_debug_tiled_plan: the two-phase regrouping of a recorded H.C pair list needs no device; the number
+    of work units and launches is a function of the list alone (same twice)."""
+    import ctypes
+    sf = b2g.load_seqfile(os.path.join(ROOT, "tests", "golden", name))
+    d0, d1 = sf.as_batches(1 << 40)
+    (b0, b1), keep = b2g._make_batches(d0, d1)
+    got = []
+    for _ in range(2):
+        sec, units, launches = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+        rc = b2g.lib().b2g_debug_tiled_plan(ctypes.byref(b0), ctypes.byref(b1), ctypes.byref(sec), ctypes.byref(units),
+                                            ctypes.byref(launches))
+        assert rc == 0
+        got.append((units.value, launches.value))
+    assert got[0] == got[1]
+    assert got[0][0] >= 2 and 2 <= got[0][1] <= 32  # at least one unit per phase; at most 8 shapes x 2 layouts x 2 phases
