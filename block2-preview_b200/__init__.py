@@ -62,7 +62,8 @@ class _Batch(ctypes.Structure):
 class PlanStats(ctypes.Structure):
     _fields_ = [("pairs", c_int64), ("csize", c_int64), ("vsize", c_int64), ("nflop_mnk", c_int64),
                 ("operand_doubles", c_int64), ("arenas", c_int64), ("launches", c_int64),
-                ("n_small", c_int64), ("n_large", c_int64), ("upload_seconds", c_double)]
+                ("n_small", c_int64), ("n_large", c_int64), ("upload_seconds", c_double),
+                ("mirrored_doubles", c_int64), ("workspace_doubles", c_int64)]
 
 
 class BlockingStats(ctypes.Structure):

@@ -247,8 +247,11 @@ b2g_blocking_stream_kernel(const StreamUnit *__restrict__ units, int64_t nunits)
         const int ncr = (len + 32 * STREAM_PER - 1) / (32 * STREAM_PER); // chunks per row
         const int ngr = (ncr + PIECE_CHUNKS - 1) / PIECE_CHUNKS;         // pieces per row
         const int npieces = U.rows * ngr;
+        // the warp that takes piece 0 rotates with the unit: the first (npieces mod 8) warps get one piece more,
+        // and with a fixed start they would be the same warps in every unit
+        const int w0 = (wib + NW - (int)(u & (NW - 1))) & (NW - 1);
         // issue side: piece ip, chunks [ic, ic_end) of its row, row base isrc
-        int ip = wib, ic = 0, ic_end = 0, qi = 0;
+        int ip = w0, ic = 0, ic_end = 0, qi = 0;
         const double *__restrict__ isrc = U.src;
         auto open_issue = [&]() {
             if (ip < npieces) {
@@ -278,7 +281,7 @@ b2g_blocking_stream_kernel(const StreamUnit *__restrict__ units, int64_t nunits)
             issue();
         // write side: the same walk, RING_STAGES - 1 steps behind
         int q = 0;
-        for (int wp = wib; wp < npieces; wp += NW) {
+        for (int wp = w0; wp < npieces; wp += NW) {
             const int r = wp / ngr, g = wp - r * ngr;
             double *__restrict__ dptr = U.dst + (int64_t)r * U.drow;
             const int wc_end = min(ncr, (g + 1) * PIECE_CHUNKS);
@@ -343,8 +346,9 @@ b2g_blocking_multi_kernel(const MultiUnit *__restrict__ units, int64_t nunits, i
         const int ncr = (len + 32 * STREAM_PER - 1) / (32 * STREAM_PER); // chunks per row
         const int ngr = (ncr + PIECE_CHUNKS - 1) / PIECE_CHUNKS;         // pieces per row
         const int npieces = G.rows * ngr;
+        const int w0 = (wib + NW - (int)(u & (NW - 1))) & (NW - 1); // rotates with the unit (see the stream kernel)
         // issue side: piece ip, chunk ci of [.., ci_end) of its row, contribution ti
-        int ip = wib, ci = 0, ci_end = 0, ti = 0, qi = 0;
+        int ip = w0, ci = 0, ci_end = 0, ti = 0, qi = 0;
         auto open_issue = [&]() {
             if (ip < npieces) {
                 const int r = ip / ngr, g = ip - r * ngr;
@@ -380,7 +384,7 @@ b2g_blocking_multi_kernel(const MultiUnit *__restrict__ units, int64_t nunits, i
             issue();
         double acc[STREAM_PER];
         int q = 0;
-        for (int wp = wib; wp < npieces; wp += NW) { // write side: the same walk, RING_STAGES - 1 steps behind
+        for (int wp = w0; wp < npieces; wp += NW) { // write side: the same walk, RING_STAGES - 1 steps behind
             const int r = wp / ngr, g = wp - r * ngr;
             double *__restrict__ dptr = G.dst + (int64_t)r * G.drow;
             const int cc_end = min(ncr, (g + 1) * PIECE_CHUNKS);
@@ -442,7 +446,7 @@ b2g_blocking_tile_kernel(const TileUnit *__restrict__ units, int64_t nunits, con
     constexpr int NW = BLK_THREADS / 32;
     double *my = ring + (size_t)wib * TILE_STAGES * TILE_SLOT;
     for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) // one CTA per unit, warps take its tiles in turn
-      for (int tt = wib, ntt = units[u].ntiles; tt < ntt; tt += NW) {
+      for (int tt = (wib + NW - (int)(u & (NW - 1))) & (NW - 1), ntt = units[u].ntiles; tt < ntt; tt += NW) {
         TileUnit U = units[u];
         const int tpr = (U.n + TILE_C - 1) / TILE_C, trow = tt / tpr; // tiles per tile row
         U.i0 += trow * TILE_R, U.j0 = (tt - trow * tpr) * TILE_C;

@@ -101,11 +101,12 @@ extern "C" int b2g_context_create(int device, b2g_context **out) {
     // site would otherwise pay cudaMalloc/cudaFree every time
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        // unused pool memory beyond this is returned to the driver at the next synchronisation: the blocks of
-        // consecutive sites differ in size, and a pool that never lets go fragments (Cr2 M=4000: 132 GB reserved
-        // for ~100 GB in use, then out of memory)
+        // Freed blocks stay in the pool (one plan and one Davidson call per site would otherwise pay the driver's
+        // map / unmap every time: measured 5 s of a 37 s Cr2 M=1000 run with a 32 GB threshold).  The price is
+        // fragmentation at large M (Cr2 M=4000: 132 GB reserved for ~100 GB in use); b2g_dmalloc hands the unused
+        // part back and retries when an allocation fails.  B2G_POOL_KEEP_GB sets a finite threshold.
         const char *keep = getenv("B2G_POOL_KEEP_GB");
-        uint64_t thr = (uint64_t)((keep ? atof(keep) : 32.0) * 1e9);
+        uint64_t thr = keep ? (uint64_t)(atof(keep) * 1e9) : UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     ctx->up_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
@@ -527,6 +528,7 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
     for (const Range &r : ar)
         op_doubles += (r.hi - r.lo) / sizeof(double);
     p->stats.operand_doubles = (int64_t)op_doubles;
+    p->stats.mirrored_doubles = operand_space == B2G_OPERANDS_HOST ? (int64_t)total : 0;
 
     auto t0 = std::chrono::steady_clock::now();
     if (operand_space == B2G_OPERANDS_HOST && total > 0) {

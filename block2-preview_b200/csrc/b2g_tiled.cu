@@ -966,6 +966,7 @@ int b2g_tiled_build(b2g_plan *p) {
             tp->tile_ranges[to.first].second = (int)tiles.size();
         }
         tp->pbuf_doubles = poff;
+        p->stats.workspace_doubles = (int64_t)(tp->wbuf_doubles + tp->pbuf_doubles);
         tp->n_tiles = (int)tiles.size();
         if (upload(tiles.data(), tiles.size() * sizeof(OutTile), (void **)&tp->d_tiles))
             return 1;

@@ -906,15 +906,42 @@ template <typename S> struct GPUDMRG : DMRG<S, double, double> {
                 } catch (const std::runtime_error &err) {
                     const bool oom = std::string(err.what()).find("out of memory") != std::string::npos ||
                                      std::string(err.what()).find("failed") != std::string::npos;
+                    b2g_plan_stats pst;
+                    memset(&pst, 0, sizeof(pst));
+                    if (gtf->plan != nullptr)
+                        b2g_plan_get_stats(gtf->plan, &pst);
                     gtf->drop(), gtf->stale = true;
                     gtf->store().tick(); // nothing of the failed attempt is "in use"
-                    if (!oom || attempt >= 2 || gtf->store().shrink(0.5) == 0)
+                    int64_t mf = 0, mt = 0;
+                    b2g_mem_info(gtf->session->ctx, &mf, &mt);
+                    const std::pair<size_t, size_t> cs = gtf->store().census();
+                    fprintf(stderr,
+                            "[b2g] eigs attempt %d failed: %s\n[b2g]   |psi| %zu doubles, plan: workspace %.2f GB, mirrored "
+                            "operands %.2f GB; store: %.2f GB evictable + %.2f GB device-only of budget %.2f GB in %zu "
+                            "blocks; device: %.2f GB free of %.2f GB\n",
+                            attempt, err.what(), (size_t)h_eff->ket->total_memory, pst.workspace_doubles * 8e-9,
+                            pst.mirrored_doubles * 8e-9, cs.first * 1e-9, cs.second * 1e-9, gtf->store().budget * 1e-9,
+                            gtf->store().blocks.size(), mf * 1e-9, mt * 1e-9);
+                    // first retry: half of the evictable environments go; second: all of them
+                    if (!oom || attempt >= 2 || gtf->store().shrink(attempt == 0 ? 0.5 : 0.0) == 0)
                         throw;
                     gtf->session->n_oom_retries++;
                 }
             }
             gtf->session->t_davidson += tq.get_time();
             pl.lap("host.eigs.davidson");
+            if (b2g_prof_enabled()) { // memory of the site, beside the library's own per-site Davidson line
+                b2g_plan_stats pst;
+                memset(&pst, 0, sizeof(pst));
+                b2g_plan_get_stats(gtf->get_plan(), &pst);
+                int64_t mf = 0, mt = 0;
+                b2g_mem_info(gtf->session->ctx, &mf, &mt);
+                const std::pair<size_t, size_t> cs = gtf->store().census();
+                fprintf(stderr, "[b2g] site memory: plan workspace %.2f GB, mirrored operands %.2f GB; store %.2f GB evictable "
+                                "+ %.2f GB device-only / in use; device %.2f GB free (pool included) of %.2f GB\n",
+                        pst.workspace_doubles * 8e-9, pst.mirrored_doubles * 8e-9, cs.first * 1e-9, cs.second * 1e-9,
+                        mf * 1e-9, mt * 1e-9);
+            }
             nflop = (size_t)ndav * (h_eff->tf->opf->seq->batch[0]->nflop + h_eff->tf->opf->seq->batch[1]->nflop);
         }
         h_eff->post_precompute();

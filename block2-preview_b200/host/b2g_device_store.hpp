@@ -171,6 +171,17 @@ struct DeviceStore {
     // Memory pressure outside the store's own budget (the W workspace and the Davidson basis of a large site):
     // evict the least recently used written-through blocks until `fraction` of what is held is left, and hand
     // the unused pool memory back to the driver.  Returns the bytes released.
+    // what is held, for diagnostics: (evictable bytes, pinned bytes = device-only blocks and blocks in use)
+    std::pair<size_t, size_t> census() const {
+        size_t ev = 0, pin = 0;
+        for (auto &b : blocks) {
+            bool ok = b->last_use != clock;
+            for (const void *k : b->keys)
+                ok = ok && shadows.at(k).host_valid;
+            (ok ? ev : pin) += b->doubles * sizeof(double);
+        }
+        return std::make_pair(ev, pin);
+    }
     size_t shrink(double fraction) {
         const size_t before = held, saved = budget;
         budget = (size_t)(fraction * (double)held);

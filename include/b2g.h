@@ -77,6 +77,8 @@ typedef struct b2g_plan_stats {
     int64_t launches;       /* kernel launches per matvec */
     int64_t n_small, n_large; /* pairs executed by the generic one-CTA-per-pair kernel / by the DMMA tile engine */
     double upload_seconds;  /* host->device mirror time of the operands */
+    int64_t mirrored_doubles;  /* operator doubles copied into the plan's own arena (0: all read in place) */
+    int64_t workspace_doubles; /* W panels + partial sigma tiles of the tile engine */
 } b2g_plan_stats;
 
 /* per-launch record of one profiled matvec (b2g_plan_profile) */
