@@ -430,8 +430,12 @@ def run_b200(args) -> None:
             pass
         alg_bytes = 8.0 * (sf.operand_doubles + sf.csize + sf.vsize)
         traffic = None  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+        traffic_source = "profiles/r02_ncu_phase2_128x64_full.json (ncu --set full, 1-GPU list, this round's engine)"
         try:
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_phase2_128x64_full.json")))
+            caps = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_phase2_128x64_full.json")))["kernels"]
+            # the capture holds both operand layouts of the 128x64 phase-2 kernel: take the one that dominates here
+            lay = "0>" if dom["name"].endswith("At") else "1>"  # At = phase2_kernel<Cfg, false>
+            cap = next((k for k in caps if (lay + "(") in k["Kernel Name"]), caps[0])
             to_b = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             traffic = sum(float(cap[k].split()[0]) * to_b[cap[k].split()[1]]
                           for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
@@ -452,7 +456,7 @@ def run_b200(args) -> None:
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": dom["name"], "achieved": dom["tflops"], "peak": peak,
                          "unit": "TFLOP/s", "frac": dom["tflops"] / peak if peak else None, "traffic": traffic,
-                         "traffic_source": "profiles/r01_ncu_phase2_128x64_full.json (ncu --set full, 1-GPU list)",
+                         "traffic_source": traffic_source,
                          "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (FP64 tensor pipe, of measured); "
                                         "MEASURED_PEAKS.json has no FP64 entry; DMMA issue ceiling 37.05 TFLOP/s "
                                         "(profiles/r01_fp64_probe.json)",

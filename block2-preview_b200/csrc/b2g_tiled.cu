@@ -389,7 +389,8 @@ static std::vector<Strip> split_cols(int n) {
     return out;
 }
 
-struct LaunchGroup { // one kernel launch: units of one (phase, cfg, layout)
+struct LaunchGroup { // one kernel launch: units of one (slab, phase, cfg, layout)
+    int slab = 0;
     int phase, cfg, layout;
     Unit *d_units = nullptr;
     int n_units = 0;
@@ -414,6 +415,10 @@ struct TiledPlan {
     double *d_wbuf = nullptr;
     unsigned int *d_counters = nullptr;
     size_t wbuf_doubles = 0;
+    // W slabs: the row panels are cut into groups whose W panels fit a bounded workspace; a slab runs its phase 1,
+    // then its phase 2, and the next slab reuses the same workspace (zeroed again: slab_doubles[s] of it)
+    std::vector<size_t> slab_doubles;
+    int n_counters = 0;
     std::vector<LaunchGroup> groups;
     std::vector<void *> to_free;
 };
@@ -737,14 +742,38 @@ int b2g_tiled_build(b2g_plan *p) {
     lap("groups.hash");
     // W panels: m0 x wld per segment, wld = the column span its groups cover (even, so that rows stay 16-byte
     // aligned); columns of the span no group writes stay zero from the one memset below
-    size_t woff = 0;
+    // The workspace is bounded (B2G_WCAP_GB, default 24 GB): at the NC/CN switch site of Cr2 M=4000 the W panels
+    // of one H_eff are 75+ GB next to 96 GB of operators.  Row panels go to slabs in panel order; all segments of
+    // a panel share its slab.
+    const char *env_cap = getenv("B2G_WCAP_GB");
+    const size_t wcap = (size_t)((env_cap ? atof(env_cap) : 24.0) * 1e9 / 8.0);
+    std::vector<size_t> panel_w(panels.size(), 0);
     for (HostSeg &hs : hsegs) {
         hs.col_lo &= ~1;
         hs.wld = ((hs.col_hi - hs.col_lo) + 1) & ~1;
-        hs.w_off = (int64_t)woff;
-        woff += (size_t)hs.m0 * hs.wld;
+        panel_w[hs.panel] += (size_t)hs.m0 * hs.wld;
     }
+    std::vector<int> panel_slab(panels.size(), 0);
+    {
+        size_t acc = 0;
+        int slab = 0;
+        for (size_t k = 0; k < panels.size(); k++) {
+            if (acc != 0 && acc + panel_w[k] > wcap)
+                slab++, acc = 0;
+            panel_slab[k] = slab, acc += panel_w[k];
+        }
+        tp->slab_doubles.assign((size_t)slab + 1, 0);
+    }
+    for (HostSeg &hs : hsegs) {
+        size_t &cur = tp->slab_doubles[panel_slab[hs.panel]];
+        hs.w_off = (int64_t)cur;
+        cur += (size_t)hs.m0 * hs.wld;
+    }
+    size_t woff = 0;
+    for (size_t v : tp->slab_doubles)
+        woff = std::max(woff, v);
     tp->wbuf_doubles = woff;
+    const int n_slabs = (int)tp->slab_doubles.size();
     std::vector<P1Group> p1g;
     std::vector<P1Seg> p1s;
     p1g.reserve(hgroups.size()), p1s.reserve(n);
@@ -774,9 +803,9 @@ int b2g_tiled_build(b2g_plan *p) {
     };
     // (phase, cfg, layout) -> units; flat table (a map lookup per unit costs more than the unit itself)
     constexpr int N_CFG = 8;
-    std::vector<HostUnit> unit_tab[2 * N_CFG * 2];
-    auto units_of = [&unit_tab](int phase, int cfg, int layout) -> std::vector<HostUnit> & {
-        return unit_tab[((phase - 1) * N_CFG + cfg) * 2 + layout];
+    std::vector<std::vector<HostUnit>> unit_tab((size_t)n_slabs * 2 * N_CFG * 2);
+    auto units_of = [&unit_tab](int slab, int phase, int cfg, int layout) -> std::vector<HostUnit> & {
+        return unit_tab[(((size_t)slab * 2 + (phase - 1)) * N_CFG + cfg) * 2 + layout];
     };
     for (size_t gi = 0; gi < hgroups.size(); gi++) {
         const HostGroup &hg = hgroups[gi];
@@ -787,7 +816,7 @@ int b2g_tiled_build(b2g_plan *p) {
         for (const Strip &rs : rsv1)
             for (const Strip &cs : csv1) {
                 const int c = cfg_of(rs.tile, cs.tile);
-                units_of(1, c, hg.tb0).push_back(HostUnit{
+                units_of(panel_slab[hsegs[hg.seg].panel], 1, c, hg.tb0).push_back(HostUnit{
                     Unit{(int)gi, rs.origin, cs.origin, 0, 0, nsteps, -1},
                     (double)rs.tile * cs.tile * (double)(ksum + 32 * (int64_t)hg.count),
                     2.0 * std::min(rs.tile, g.m0 - rs.origin) * std::min(cs.tile, g.n0 - cs.origin) * (double)ksum});
@@ -841,7 +870,7 @@ int b2g_tiled_build(b2g_plan *p) {
                     if (s1 == s0)
                         return;
                     for (const Strip &rs : rsv)
-                        units_of(2, cfg_of(rs.tile, cs.tile), lay).push_back(
+                        units_of(panel_slab[w], 2, cfg_of(rs.tile, cs.tile), lay).push_back(
                             HostUnit{Unit{(int)w, rs.origin, cs.origin, (int)s0, (int)s1, nsteps, -1},
                                      (double)rs.tile * cs.tile * (double)(ksum + 32),
                                      2.0 * std::min(rs.tile, wins[w].m1 - rs.origin) * (t_hi - t_lo) * (double)ksum});
@@ -860,12 +889,14 @@ int b2g_tiled_build(b2g_plan *p) {
             }
         }
 
-    std::map<std::tuple<int, int, int>, std::vector<HostUnit>> groups; // non-empty (phase, cfg, layout), in order
-    for (int ph = 1; ph <= 2; ph++)
-        for (int c = 0; c < N_CFG; c++)
-            for (int lay = 0; lay < 2; lay++)
-                if (!units_of(ph, c, lay).empty())
-                    groups[std::make_tuple(ph, c, lay)].swap(units_of(ph, c, lay));
+    // non-empty (slab, phase, cfg, layout), in launch order
+    std::map<std::tuple<int, int, int, int>, std::vector<HostUnit>> groups;
+    for (int sl = 0; sl < n_slabs; sl++)
+        for (int ph = 1; ph <= 2; ph++)
+            for (int c = 0; c < N_CFG; c++)
+                for (int lay = 0; lay < 2; lay++)
+                    if (!units_of(sl, ph, c, lay).empty())
+                        groups[std::make_tuple(sl, ph, c, lay)].swap(units_of(sl, ph, c, lay));
     lap("units");
     if (ctx == nullptr) { // b2g_debug_tiled_plan: the host-side regrouping alone (no device)
         int64_t nu = 0;
@@ -904,10 +935,10 @@ int b2g_tiled_build(b2g_plan *p) {
     if (!(env_atomic && env_atomic[0] == '1')) {
         std::map<std::tuple<int, int, int>, std::vector<std::pair<int, HostUnit *>>> by_tile; // (panel,row0,col0)
         for (auto &kv : groups)
-            if (std::get<0>(kv.first) == 2)
+            if (std::get<1>(kv.first) == 2)
                 for (HostUnit &hu : kv.second)
                     by_tile[std::make_tuple(hu.u.idx, hu.u.row0, hu.u.col0)].push_back(
-                        std::make_pair(std::get<1>(kv.first), &hu));
+                        std::make_pair(std::get<2>(kv.first), &hu));
         // colour the panels so that panels sharing sigma elements never share a launch
         std::vector<int> colour(wins.size(), 0);
         {
@@ -986,7 +1017,8 @@ int b2g_tiled_build(b2g_plan *p) {
         for (size_t i = 0; i < hu.size(); i++)
             keep.back()[i] = hu[i].u;
         LaunchGroup g;
-        g.phase = std::get<0>(kv.first), g.cfg = std::get<1>(kv.first), g.layout = std::get<2>(kv.first);
+        g.slab = std::get<0>(kv.first), g.phase = std::get<1>(kv.first), g.cfg = std::get<2>(kv.first);
+        g.layout = std::get<3>(kv.first);
         g.n_units = (int)hu.size();
         for (const HostUnit &x : hu)
             g.flops += x.flops;
@@ -994,9 +1026,11 @@ int b2g_tiled_build(b2g_plan *p) {
             return 1;
         tp->groups.push_back(g);
     }
-    std::stable_sort(tp->groups.begin(), tp->groups.end(),
-                     [](const LaunchGroup &a, const LaunchGroup &b) { return a.phase < b.phase; });
-    if (b2g_dmalloc(ctx, (void **)&tp->d_counters, sizeof(unsigned int) * 64))
+    std::stable_sort(tp->groups.begin(), tp->groups.end(), [](const LaunchGroup &a, const LaunchGroup &b) {
+        return a.slab != b.slab ? a.slab < b.slab : a.phase < b.phase;
+    });
+    tp->n_counters = std::max<int>(64, (int)tp->groups.size());
+    if (b2g_dmalloc(ctx, (void **)&tp->d_counters, sizeof(unsigned int) * tp->n_counters))
         return 1;
     tp->to_free.push_back(tp->d_counters);
     lap("tiles+upload");
@@ -1015,7 +1049,7 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
         *count = 0;
     if (!tp || tp->groups.empty())
         return 0;
-    B2G_CUDA(cudaMemsetAsync(tp->d_counters, 0, sizeof(unsigned int) * 64, ctx->stream));
+    B2G_CUDA(cudaMemsetAsync(tp->d_counters, 0, sizeof(unsigned int) * tp->n_counters, ctx->stream));
     struct Rec {
         std::string name;
         double flops;
@@ -1042,7 +1076,8 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
     // the next phase; with profiling everything stays on the context stream (timed one by one).
     // Forking pays when no single launch fills the chip (measured: up to ~2x on the C2 / H10 lists,
     // -5 % on the 2 TFLOP Cr2 list where the big persistent kernels then compete), hence the bound.
-    const bool fork_all = stats == nullptr && 2.0 * (double)p->stats.nflop_mnk < 3e11;
+    const bool multi_slab = tp->slab_doubles.size() > 1;
+    const bool fork_all = stats == nullptr && 2.0 * (double)p->stats.nflop_mnk < 3e11 && !multi_slab;
     // Large lists, experiment (B2G_FORK_SMALL=<flops>): only the minor launches (edge-strip and 64-row
     // configurations, a few % of the FLOPs each) go to the low-priority side streams, to fill the tails of
     // the big persistent launches that stay on the context stream.  Measured on the Cr2 M=4000 list: 81.5 /
@@ -1059,13 +1094,18 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
     };
     if (fork)
         B2G_CUDA(cudaEventRecord(ctx->fork_ev, ctx->stream));
-    int gi = 0;
+    int gi = 0, cur_slab = -1;
     bool phase2_open = false;
     // Measured on the Cr2 M=4000 list: 81.8 - 82.7 ms with the chain against 73.7 - 74.1 ms without (also with the
     // first unit claimed dynamically), so it is an experiment switch (B2G_PDL=1), off by default.
     static const bool use_pdl = getenv("B2G_PDL") != nullptr;
     bool chain_open = false, first_p2 = true;
     for (const LaunchGroup &g : tp->groups) {
+        if (g.slab != cur_slab) { // next slab: same workspace; what its groups do not cover must read as zero again
+            cur_slab = g.slab, phase2_open = false, first_p2 = true, chain_open = false;
+            if (multi_slab)
+                B2G_CUDA(cudaMemsetAsync(tp->d_wbuf, 0, tp->slab_doubles[g.slab] * sizeof(double), ctx->stream));
+        }
         if (g.phase == 2 && !phase2_open) { // every W panel is complete before the first phase-2 launch
             phase2_open = true;
             if (fork) {

@@ -20,6 +20,7 @@
 #pragma once
 #include "b2g.h"
 #include "block2_core.hpp"
+#include <chrono>
 #include <stdexcept>
 #include <sys/mman.h>
 #include <unordered_map>
@@ -191,7 +192,17 @@ struct DeviceStore {
         return before - held;
     }
     shared_ptr<DevBlock> new_block(size_t doubles, bool zero) {
+        const bool prof = b2g_prof_enabled() != 0;
+        auto t0 = std::chrono::steady_clock::now();
+        auto lap = [&](const char *label) {
+            if (prof) {
+                const auto t1 = std::chrono::steady_clock::now();
+                b2g_prof_record(label, std::chrono::duration<double>(t1 - t0).count());
+                t0 = t1;
+            }
+        };
         make_room(doubles * sizeof(double));
+        lap("store.new_block.make_room");
         shared_ptr<DevBlock> b;
         try {
             b = make_shared<DevBlock>(ctx, doubles);
@@ -200,9 +211,11 @@ struct DeviceStore {
                 throw;
             b = make_shared<DevBlock>(ctx, doubles);
         }
+        lap("store.new_block.malloc");
         b->last_use = clock;
         if (zero && doubles != 0 && b2g_memset_zero(ctx, b->base, doubles * sizeof(double)) != 0)
             throw std::runtime_error(std::string("b2g_memset_zero: ") + b2g_last_error());
+        lap("store.new_block.memset_issue");
         blocks.push_back(b);
         held += doubles * sizeof(double), peak = std::max(peak, held);
         return b;

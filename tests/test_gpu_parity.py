@@ -214,7 +214,7 @@ def sigma_block_list(rng, blocks=((150, 71), (40, 200), (9, 9), (130, 81), (64, 
 
 
 @pytest.mark.parametrize("env", [{}, {"B2G_NO_PANELS": "1"}, {"B2G_NO_TILE72": "1"}, {"B2G_KCHUNK": "64"},
-                                 {"B2G_ATOMIC_SIGMA": "1"}])
+                                 {"B2G_ATOMIC_SIGMA": "1"}, {"B2G_WCAP_GB": "1e-7"}])
 def test_sigma_blocks_with_sub_windows_merge_into_row_panels(b2g, ctx, monkeypatch, env):
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -230,6 +230,29 @@ def test_sigma_blocks_with_sub_windows_merge_into_row_panels(b2g, ctx, monkeypat
         if "B2G_ATOMIC_SIGMA" not in env:
             assert np.array_equal(got, again)  # W panels are rebuilt, not re-added; fixed summation order
         plan.close()
+
+
+def test_bounded_w_workspace_gives_the_same_bits(b2g, ctx, monkeypatch):
+    """B2G_WCAP_GB bounds the W workspace: the row panels run slab after slab through one reused buffer
+    (zeroed again per slab).  The partial sigma tiles and their summation order do not depend on the slabs, so
+    sigma is bit for bit what the single-slab plan gives, also on a second replay of the same plan."""
+    for name in ("n2_su2_m60_s4.b2seq", "h10_sz_m40_s4.b2seq"):
+        d = sd.load(os.path.join(GOLDEN, name))
+        plan = b2g.SeqPlan.from_seqfile(ctx, as_seqfile(b2g, d), d.arenas)
+        one = np.zeros(d.vsize)
+        plan(d.c, one)
+        n_one = plan.stats.launches
+        plan.close()
+        monkeypatch.setenv("B2G_WCAP_GB", "2e-6")  # 250 doubles: nearly one slab per row panel
+        plan = b2g.SeqPlan.from_seqfile(ctx, as_seqfile(b2g, d), d.arenas)
+        many, again = np.zeros(d.vsize), np.zeros(d.vsize)
+        plan(d.c, many)
+        plan(d.c, again)
+        assert plan.stats.launches > n_one
+        plan.close()
+        monkeypatch.delenv("B2G_WCAP_GB")
+        assert np.array_equal(one, many) and np.array_equal(many, again), name
+        assert rel(one, sd.replay(d, nthreads=4)) < TOL
 
 
 def test_matvec_is_repeatable_on_one_plan(b2g, ctx):
