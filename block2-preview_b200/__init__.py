@@ -42,7 +42,7 @@ EXPORTS = [
     "b2g_upload_blocks", "b2g_host_register", "b2g_host_unregister", "b2g_mem_info", "b2g_debug_upload_slices", "b2g_davidson", "b2g_comm_unique_id",
     "b2g_comm_init", "b2g_comm_destroy", "b2g_allreduce_sum", "b2g_malloc", "b2g_free",
     "b2g_memcpy_h2d", "b2g_memcpy_d2h", "b2g_memset_zero",
-    "b2g_prof_enabled", "b2g_prof_record", "b2g_prof_dump", "b2g_debug_tiled_plan", "b2g_mem_trim",
+    "b2g_prof_enabled", "b2g_prof_record", "b2g_prof_dump", "b2g_debug_tiled_plan", "b2g_mem_trim", "b2g_syevd",
 ]
 
 

@@ -290,6 +290,7 @@ extern "C" int b2g_context_destroy(b2g_context *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->nccl_comm)
         b2g_comm_destroy(ctx);
+    b2g_eig_destroy(ctx);
     if (ctx->h_stage)
         cudaFreeHost(ctx->h_stage);
     for (int i = 0; i < 2; i++) {

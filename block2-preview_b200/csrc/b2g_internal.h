@@ -61,6 +61,7 @@ struct b2g_context {
     std::vector<B2GMapEntry> rmap; // sorted by lo, disjoint (b2g_resident_map)
     int64_t resident_hits = 0, resident_hit_bytes = 0, mirrored_bytes = 0;
     bool blocking_attr_set = false; // dynamic shared memory limits of the blocking kernels raised on this device
+    void *eig_pool = nullptr; // b2g_eig.cu: streams / cuSOLVER handles of b2g_syevd (created at first use)
     void *h_up[2] = {nullptr, nullptr};
     cudaEvent_t up_done[2] = {nullptr, nullptr};
     size_t up_bytes = 0;
@@ -81,6 +82,7 @@ struct b2g_plan {
 };
 
 void b2g_set_error(const std::string &msg);
+void b2g_eig_destroy(b2g_context *ctx);
 // host-side wall-clock profile (B2G_PROF): RAII section that adds to a label
 struct B2GProfScope {
     const char *label;

@@ -39,6 +39,30 @@ namespace b2g_host {
 
 using namespace block2;
 
+// Density-matrix split: the reference diagonalises every block of the density matrix with LAPACK
+// dsyev, one block per OpenMP thread (MovingEnvironment::truncate_density_matrix, dmrg/moving_environment.hpp:
+// 3716-3790).  The build maps the reference's dsyev_ symbol to b2g_host_dsyev_ (blas_rename.h); with the hook armed
+// (Session::gpu_split, b2g_dmrg --gpu-split) blocks of at least `min_n` rows go to b2g_syevd (cuSOLVER on the
+// device, library-backed), everything else - workspace queries, small blocks, any failure - to the CPU routine.
+struct SplitHook {
+    static b2g_context *&ctx() {
+        static b2g_context *c = nullptr;
+        return c;
+    }
+    static int &min_n() {
+        static int n = 256;
+        return n;
+    }
+    static std::atomic<size_t> &calls_gpu() {
+        static std::atomic<size_t> c{0};
+        return c;
+    }
+    static std::atomic<size_t> &calls_cpu() {
+        static std::atomic<size_t> c{0};
+        return c;
+    }
+};
+
 // B2G_PROF: wall-clock sections of the binding, accumulated by the library's profile (b2g_prof_record)
 struct ProfLap {
     bool on;
@@ -78,6 +102,12 @@ struct Session {
     bool gpu_iadd = true;
     double t_iadd = 0, max_iadd_err = 0;
     size_t n_iadd = 0, iadd_entries = 0;
+    // dense eigenproblems of the density-matrix split on the device (cuSOLVER behind b2g_syevd); opt-in
+    bool gpu_split = false;
+    void arm_split(bool on) {
+        gpu_split = on;
+        SplitHook::ctx() = on ? ctx : nullptr;
+    }
     // H_eff diagonal (tensor_product_diagonal) on the device
     bool gpu_diag = true;
     double t_diag = 0, max_diag_err = 0;
@@ -104,6 +134,8 @@ struct Session {
             pinned = base;
     }
     ~Session() {
+        if (SplitHook::ctx() == ctx)
+            SplitHook::ctx() = nullptr;
         store->drop_all();
         store = nullptr;
         if (pinned != nullptr)
@@ -991,3 +1023,4 @@ inline shared_ptr<Session> install_parallel(const shared_ptr<MPO<S, double>> &mp
 }
 
 } // namespace b2g_host
+

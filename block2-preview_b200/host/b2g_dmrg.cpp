@@ -17,6 +17,25 @@ using namespace std;
 #define B2G_S SU2
 #endif
 
+// ---- LAPACK hook of the density-matrix split (b2g_adapter.hpp: SplitHook); one definition per binary
+extern "C" void scipy_dsyev_(const char *jobz, const char *uplo, const MKL_INT *n, double *a, const MKL_INT *lda,
+                             double *w, double *work, const MKL_INT *lwork, MKL_INT *info);
+// the symbol the reference's dsyev_ calls resolve to in this build (blas_rename.h)
+extern "C" void b2g_host_dsyev_(const char *jobz, const char *uplo, const MKL_INT *n, double *a,
+                                       const MKL_INT *lda, double *w, double *work, const MKL_INT *lwork,
+                                       MKL_INT *info) {
+    b2g_context *ctx = b2g_host::SplitHook::ctx();
+    if (ctx != nullptr && *lwork != -1 && *n >= b2g_host::SplitHook::min_n() && (jobz[0] == 'V' || jobz[0] == 'v') &&
+        b2g_syevd(ctx, (int)*n, a, (int)*lda, w) == 0) {
+        *info = 0;
+        b2g_host::SplitHook::calls_gpu()++;
+        return;
+    }
+    if (ctx != nullptr && *lwork != -1)
+        b2g_host::SplitHook::calls_cpu()++;
+    scipy_dsyev_(jobz, uplo, n, a, lda, w, work, lwork, info);
+}
+
 struct Args {
     string fcidump, pg = "d2h", occ = "", scratch = "/tmp/b2g_scratch", davidson = "device";
     int bond = 250, n_sweeps = 6, threads = 8, device = 0, ranks = 1, rank = 0;
@@ -25,7 +44,7 @@ struct Args {
     int seed = 1234;
     string shm = "b2g";
     bool compare = false, verify = false, gpu_rotate = true, gpu_contract = true, gpu_diag = true, gpu_iadd = true,
-         host_mirror = false, pin = true, cpu_only = false, classic = false;
+         host_mirror = false, pin = true, cpu_only = false, classic = false, gpu_split = false;
     int restart_sweeps = 0; // --compare: zero-noise sweeps both arms run from the CPU arm's final MPS (same state)
     int noise_sweeps = 2;   // sweeps per noise level: {noise x k, 0.1 noise x k, 0 ...}
     double dav_thrd = 0;    // > 0: Davidson threshold of every sweep (default: the reference's noise-derived schedule)
@@ -178,6 +197,8 @@ int main(int argc, char **argv) {
         else if (k == "--no-gpu-contract") a.gpu_contract = false;
         else if (k == "--no-gpu-diag") a.gpu_diag = false;
         else if (k == "--no-gpu-iadd") a.gpu_iadd = false;
+        else if (k == "--gpu-split") a.gpu_split = true; // density-matrix eigenproblems through b2g_syevd (cuSOLVER)
+        else if (k == "--split-min-n") b2g_host::SplitHook::min_n() = atoi(nxt().c_str());
         else if (k == "--noise-sweeps") a.noise_sweeps = atoi(nxt().c_str());
         else if (k == "--dav-thrd") a.dav_thrd = atof(nxt().c_str());
         else if (k == "--restart-sweeps") a.restart_sweeps = atoi(nxt().c_str());
@@ -267,6 +288,7 @@ int main(int argc, char **argv) {
     session->gpu_diag = a.gpu_diag;
     session->gpu_iadd = a.gpu_iadd;
     session->host_mirror = a.host_mirror;
+    session->arm_split(a.gpu_split);
     if (a.pin)
         session->pin_stacks();
     RunResult gpu = run_dmrg<S>(a, mpo, hamil, target, true);
@@ -312,7 +334,7 @@ int main(int argc, char **argv) {
            "\"resident_read_gbytes\": %.3f, \"mirrored_gbytes\": %.3f, \"resident_peak_gbytes\": %.3f, "
            "\"resident_uploaded_gbytes\": %.3f, \"resident_downloaded_gbytes\": %.3f, \"resident_evicted_gbytes\": %.3f, "
            "\"t_precompute\": %.3f, \"t_davidson\": %.3f, \"t_contract_alloc\": %.3f, \"t_contract_ensure\": %.3f, "
-           "\"t_contract_exec\": %.3f, \"t_rotate_alloc\": %.3f, \"t_rotate_exec\": %.3f, \"oom_retries\": %zu}\n",
+           "\"t_contract_exec\": %.3f, \"t_rotate_alloc\": %.3f, \"t_rotate_exec\": %.3f, \"oom_retries\": %zu, \"gpu_split\": %d, \"syevd_gpu\": %zu, \"syevd_cpu\": %zu}\n",
            a.ranks, a.davidson.c_str(), a.bond, a.seed, gpu.energies.size(), gpu.total, ref.total, a.threads,
            gpu.energies.empty() ? 0.0 : gpu.energies.back(), ref.energies.empty() ? 0.0 : ref.energies.back(),
            maxdiff,
@@ -331,7 +353,8 @@ int main(int argc, char **argv) {
            session->store->uploaded_bytes * 1e-9, session->store->downloaded_bytes * 1e-9,
            session->store->evicted_bytes * 1e-9, session->t_precompute, session->t_davidson, session->t_contract_alloc,
            session->t_contract_ensure, session->t_contract_exec, session->t_rotate_alloc, session->t_rotate_exec,
-           session->n_oom_retries);
+           session->n_oom_retries, (int)session->gpu_split, b2g_host::SplitHook::calls_gpu().load(),
+           b2g_host::SplitHook::calls_cpu().load());
     fflush(stdout);
     b2g_prof_dump(getenv("B2G_PROF_FILE")); // B2G_PROF: wall-clock sections of the library and the binding
     _exit(0);

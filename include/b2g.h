@@ -247,6 +247,12 @@ int b2g_malloc(b2g_context *ctx, size_t bytes, void **dev);
 int b2g_free(b2g_context *ctx, void *dev);
 /* free (including memory parked in the allocation pool) and total device memory */
 int b2g_mem_info(b2g_context *ctx, int64_t *free_bytes, int64_t *total_bytes);
+/* Dense symmetric eigenproblem on the device, LIBRARY-BACKED (cuSOLVER cusolverDnDsyevd, loaded with dlopen at
+ * first use): a (n x n, leading dimension lda, host) is overwritten by its eigenvectors exactly as LAPACK
+ * dsyev("V", "U") leaves them, w receives the eigenvalues in ascending order.  Thread-safe, synchronous.  Replaces
+ * the dsyev calls of MovingEnvironment::truncate_density_matrix (dmrg/moving_environment.hpp:3716-3790) when the
+ * binding routes them here (not on the north-star path).  Non-zero: a is unchanged. */
+int b2g_syevd(b2g_context *ctx, int n, double *a_host, int lda, double *w_host);
 /* synchronise and return every unused block of the stream-ordered pool to the driver (after evicting shadows) */
 int b2g_mem_trim(b2g_context *ctx);
 int b2g_memcpy_h2d(b2g_context *ctx, void *dev, const void *host, size_t bytes);

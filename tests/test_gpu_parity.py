@@ -447,3 +447,40 @@ def test_rank_lists_of_parallel_reference_on_gpu(b2g, ctx):
         plan(sf.c, v)
         plan.close()
     assert rel(v, sf.v_ref) < TOL
+
+
+def test_syevd_matches_lapack_convention(b2g, ctx):
+    """b2g_syevd (library-backed: cuSOLVER) against numpy.linalg.eigh: eigenvalues ascending, eigenvector k in ROW k
+    of the row-major matrix (what LAPACK dsyev("V") leaves for the reference, core/matrix_functions.hpp:1672-1688),
+    with a leading dimension larger than n and from several host threads at once."""
+    import ctypes
+    import threading
+    L = b2g.lib()
+    rng = np.random.default_rng(77)
+
+    def run(n, lda, out):
+        x = rng.standard_normal((n, n))
+        sym = x + x.T
+        a = np.zeros((n, lda))
+        a[:, :n] = sym
+        w = np.zeros(n)
+        rc = L.b2g_syevd(ctx._h, ctypes.c_int(n), ctypes.c_void_p(a.ctypes.data), ctypes.c_int(lda),
+                         ctypes.c_void_p(w.ctypes.data))
+        out.append((rc, sym, a[:, :n].copy(), w))
+
+    jobs = [(1, 1), (7, 9), (64, 64), (300, 300), (513, 520)]
+    results = []
+    threads = [threading.Thread(target=run, args=(n, lda, results)) for n, lda in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert len(results) == len(jobs)
+    for rc, sym, vecs, w in results:
+        assert rc == 0
+        n = sym.shape[0]
+        assert np.all(np.diff(w) >= 0)
+        assert np.allclose(w, np.linalg.eigvalsh(sym), rtol=0, atol=1e-11 * max(1.0, np.abs(w).max()))
+        # rows are eigenvectors: sym @ v_k = w_k v_k, orthonormal
+        assert np.linalg.norm(vecs @ sym - w[:, None] * vecs) < 1e-10 * max(1.0, np.abs(w).max()) * n
+        assert np.linalg.norm(vecs @ vecs.T - np.eye(n)) < 1e-11 * n
