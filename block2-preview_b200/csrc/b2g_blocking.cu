@@ -768,7 +768,11 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
             if (!irregular[ci])
                 tot += (int64_t)he[idx[cl[ci].first]].m * he[idx[cl[ci].first]].n * cl[ci].count;
         const int64_t warps = (int64_t)(ctx ? ctx->sm_count : 148) * 3 * (BLK_THREADS / 32);
-        lin_target = std::min<int64_t>(16384, std::max<int64_t>(UNIT_ELEMS, tot / (warps * 32) / 256 * 256));
+        // upper bound: the sources of a step are read by several windows (5 x on average in an H_eff blocking step),
+        // and the second reader finds them in L2 only if it runs within one "round" of the grid after the first:
+        // 444 CTAs x unit bytes has to stay well below the 126 MB of L2
+        static const int64_t lin_max = getenv("B2G_BLK_LINMAX") ? atoll(getenv("B2G_BLK_LINMAX")) : 4096;
+        lin_target = std::min<int64_t>(lin_max, std::max<int64_t>(UNIT_ELEMS, tot / (warps * 32) / 256 * 256));
     }
     static const bool tile_on = getenv("B2G_BLK_NOTILE") == nullptr;
     dev_entries.reserve(he.size());
