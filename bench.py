@@ -488,7 +488,12 @@ def run_b200(args) -> None:
             except Exception as exc:
                 line["small_sector"] = {"unavailable": str(exc)}
             try:  # complete sweeps through block2's own driver: recorded runs of this round, not timed here
-                line["sweep"] = json.load(open(os.path.join(ROOT, "profiles", "r02_sweeps.json")))
+                rec = json.load(open(os.path.join(ROOT, "profiles", "r02_sweeps.json")))
+                line["sweep"] = {"what": rec["what"], "source": "profiles/r02_sweeps.json (logs beside it)",
+                                 "runs": [{"config": r["config"], "bond": r.get("bond"), "threads": r.get("threads"),
+                                           "arms": [{"arm": a["arm"], "sweep_seconds": a["sweep_seconds"],
+                                                     "tflop_per_sweep": a["tflop_per_sweep"]} for a in r["arms"]],
+                                           "speedup_per_sweep": r.get("speedup_per_sweep")} for r in rec["runs"]]}
             except Exception:
                 pass
         if world == 1:

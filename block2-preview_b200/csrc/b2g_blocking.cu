@@ -768,10 +768,10 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
             if (!irregular[ci])
                 tot += (int64_t)he[idx[cl[ci].first]].m * he[idx[cl[ci].first]].n * cl[ci].count;
         const int64_t warps = (int64_t)(ctx ? ctx->sm_count : 148) * 3 * (BLK_THREADS / 32);
-        // upper bound: the sources of a step are read by several windows (5 x on average in an H_eff blocking step),
-        // and the second reader finds them in L2 only if it runs within one "round" of the grid after the first:
-        // 444 CTAs x unit bytes has to stay well below the 126 MB of L2
-        static const int64_t lin_max = getenv("B2G_BLK_LINMAX") ? atoll(getenv("B2G_BLK_LINMAX")) : 4096;
+        // upper bound of a unit (B2G_BLK_LINMAX).  Measured on the Cr2 M=4000 H_eff list: 9.2 / 9.0 / 6.6 / 4.8 ms with
+        // 2048 / 4096 / 8192 / 16384 elements - a CTA pays the latency of its descriptor and of the first loads of
+        // its warps once per unit, so small units lose more than the shorter L2 reuse distance gains
+        static const int64_t lin_max = getenv("B2G_BLK_LINMAX") ? atoll(getenv("B2G_BLK_LINMAX")) : 16384;
         lin_target = std::min<int64_t>(lin_max, std::max<int64_t>(UNIT_ELEMS, tot / (warps * 32) / 256 * 256));
     }
     static const bool tile_on = getenv("B2G_BLK_NOTILE") == nullptr;
@@ -831,7 +831,10 @@ static int execute_entries(b2g_context *ctx, std::vector<HostEntry> &he, int ope
             }
         } else if (lin) {
             // elements per unit: the warps of a CTA share a unit piece by piece (b2g_blocking_stream_kernel)
-            const int64_t per = std::max<int64_t>(2048, lin_target / cl[ci].count / 256 * 256);
+            // (not divided by the number of contributions: a multi-source unit needs at least one piece per warp
+            // to keep the rings of all 8 warps busy - ncu showed the multi kernel at 0.86 TB/s with 2048-element units)
+            static const bool per_div = getenv("B2G_BLK_PERDIV") != nullptr; // A/B: the old rule
+            const int64_t per = std::max<int64_t>(2048, lin_target / (per_div ? cl[ci].count : 1) / 256 * 256);
             if (w.n == 1) { // a column (or a dense window addressed flat): one "row" of elements ldc apart
                 for (int64_t e0 = 0; e0 < total; e0 += per)
                     lunits.push_back(LinUnit{w.dst, 0, 1, (int32_t)e0, (int32_t)std::min<int64_t>(per, total - e0), w.n,

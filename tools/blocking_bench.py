@@ -70,13 +70,12 @@ def run(args, ctx=None):
     gbs = alg_bytes / (kernel_ms * 1e-3) * 1e-9
     distinct = 8 * (int(tp.in_sizes.sum()) + int(st.bytes_out) // 8)
     traffic, traffic_source = None, None
-    try:  # DRAM bytes of the kernels of this call, from the committed ncu launch list of the same workload
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_blocking_kernels_v3.json")))
-        key = "call39" if "call39" in os.path.basename(args.workload) else "call18" if "call18" in args.workload else None
-        if key is not None:
-            traffic = 1e9 * sum(k["dram_read_GB"] + k["dram_write_GB"] for k in cap["launch_lists"][key])
-            traffic_source = ("profiles/r01_ncu_blocking_kernels_v3.json: dram__bytes_read.sum + dram__bytes_write.sum "
-                              "summed over the kernels of one call")
+    try:  # DRAM bytes of the kernels of one call, from the committed ncu launch list of the H_eff blocking list
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_blocking.json")))
+        if "call39" in os.path.basename(args.workload):
+            traffic = 1e9 * (cap["one_call"]["dram_read_GB"] + cap["one_call"]["dram_write_GB"])
+            traffic_source = ("profiles/r02_ncu_blocking.json: dram__bytes_read.sum + dram__bytes_write.sum summed over "
+                              "the four kernels of one call (ncu pass of the same command)")
     except Exception:
         pass
 
