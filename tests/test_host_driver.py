@@ -71,8 +71,16 @@ def test_n2_device_resident_environments_energy_per_sweep():
 
 
 def test_h10_sto6g_sz_energy_per_sweep_and_lists():
-    r, out = run_driver("b2g_dmrg_sz", *H10, *TIGHT, "--bond", "500", "--nsweeps", "8", "--compare")
-    assert r["max_sweep_diff"] < 1e-8, (r, [ln for ln in out.splitlines() if ln.startswith("SWEEP")])
+    """The 1e-8 Ha bar per sweep is asserted where it is well defined: on the zero-noise sweeps both arms run from
+    the SAME state (the CPU arm's final MPS, --restart-sweeps) and on the converged energy.  Inside the noisy sweeps
+    from the random MPS the truncation with density-matrix noise amplifies rounding differences: the two arms are
+    6e-8 .. 1.3e-7 apart in sweeps 1-2 from run to run, as far as the unmodified reference is from itself when
+    only its thread count changes (profiles/r02_energy_parity.md section 3) - bounded here by 1e-6."""
+    r, out = run_driver("b2g_dmrg_sz", *H10, *TIGHT, "--bond", "500", "--nsweeps", "8", "--compare",
+                        "--restart-sweeps", "2")
+    sweeps = [ln for ln in out.splitlines() if "SWEEP" in ln]
+    assert r["restart_sweeps"] == 2 and r["max_restart_sweep_diff"] < 1e-8, (r, sweeps)
+    assert abs(r["final_diff"]) < 1e-8 and r["max_sweep_diff"] < 1e-6, (r, sweeps)
     assert abs(r["e_gpu"] - E_H10) < 1e-7, r               # the reference's own tolerance for this value
     r, _ = run_driver("b2g_dmrg_sz", *H10, "--bond", "300", "--nsweeps", "6", "--verify")
     assert r["max_matvec_rel_err"] < 1e-11 and r["max_contract_rel_err"] < 1e-11, r
