@@ -82,6 +82,10 @@ __device__ __forceinline__ void pdl_enter(int wait_first) {
 }
 __device__ __forceinline__ void pdl_exit() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+__global__ void set_args_kernel(MatvecArgs *a, const double *c, double *v, double scale) {
+    a->c = c, a->v = v, a->scale = scale;
+}
+
 template <class Cfg, bool B_KC> struct P1Src {
     const P1Seg *seg, *seg_end;
     const double *c;
@@ -117,10 +121,12 @@ template <class Cfg, bool B_KC>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
 phase1_kernel(const P1Group *__restrict__ groups, const P1Seg *__restrict__ segs, const Unit *__restrict__ units,
               int n_units, unsigned int *__restrict__ counter, const double *__restrict__ c,
-              double *__restrict__ wbuf, int wait_first) {
+              double *__restrict__ wbuf, int wait_first, const MatvecArgs *__restrict__ ind) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_unit;
     __shared__ double s_alpha[Cfg::STAGES];
+    if (ind) // replay of a captured graph: the wavefunction of this call
+        c = ind->c;
     pdl_enter(wait_first);
     int wm0, wn0;
     warp_origin<Cfg>(wm0, wn0);
@@ -210,9 +216,12 @@ template <class Cfg, bool A_KC>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
 phase2_kernel(const P2Window *__restrict__ wins, const P2Seg *__restrict__ segs, const Unit *__restrict__ units,
               int n_units, unsigned int *__restrict__ counter, const double *__restrict__ wbuf,
-              double *__restrict__ v, double scale, double *__restrict__ pbuf, int wait_first) {
+              double *__restrict__ v, double scale, double *__restrict__ pbuf, int wait_first,
+              const MatvecArgs *__restrict__ ind) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_unit;
+    if (ind)
+        v = ind->v, scale = ind->scale;
     pdl_enter(wait_first);
     int wm0, wn0;
     warp_origin<Cfg>(wm0, wn0);
@@ -288,7 +297,9 @@ constexpr int RED_SPLIT = 8; // CTAs per sigma tile
 __global__ void __launch_bounds__(256)
 reduce_kernel(const OutTile *__restrict__ tiles, int n_tiles, const int64_t *__restrict__ part_off,
               const P2Window *__restrict__ wins, const double *__restrict__ pbuf, double *__restrict__ v,
-              double scale) {
+              double scale, const MatvecArgs *__restrict__ ind) {
+    if (ind)
+        v = ind->v, scale = ind->scale;
     for (int job = blockIdx.x; job < n_tiles * RED_SPLIT; job += gridDim.x) {
         const OutTile ot = tiles[job / RED_SPLIT];
         const int part = job % RED_SPLIT;
@@ -419,6 +430,13 @@ struct TiledPlan {
     // then its phase 2, and the next slab reuses the same workspace (zeroed again: slab_doubles[s] of it)
     std::vector<size_t> slab_doubles;
     int n_counters = 0;
+    // small lists (launch-bound): the whole matvec - counters, forked phase-1 launches, join, phase-2 launches,
+    // join, sigma reduce - is captured once into a CUDA graph and replayed with one launch; c, sigma and scale of
+    // a replay come through d_args
+    MatvecArgs *d_args = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_state = 0; // 0 = first call runs eagerly (function attributes, occupancy), 1 = capture next, 2 = replay, -1 = off
+    int graph_kernels = 0;
     std::vector<LaunchGroup> groups;
     std::vector<void *> to_free;
 };
@@ -450,7 +468,7 @@ static int launch_ex(void (*kern)(Params...), int grid, int threads, size_t smem
 
 template <class Cfg, bool L> static int launch_p1(const LaunchGroup &g, const TiledPlan &tp, b2g_context *ctx,
                                                   cudaStream_t stream, unsigned int *counter, const double *c,
-                                                  bool pdl, int wait_first) {
+                                                  bool pdl, int wait_first, const MatvecArgs *ind) {
     auto kern = phase1_kernel<Cfg, L>;
     static std::atomic<uint64_t> attr_mask{0};
     if (raise_smem_limit(kern, Cfg::SMEM_BYTES, ctx->device, attr_mask))
@@ -464,11 +482,11 @@ template <class Cfg, bool L> static int launch_p1(const LaunchGroup &g, const Ti
     }
     const int grid = std::min(g.n_units, ctx->sm_count * std::max(per_sm, 1));
     return launch_ex(kern, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, pdl, tp.d_p1g, tp.d_p1s, g.d_units, g.n_units,
-                     counter, c, tp.d_wbuf, wait_first);
+                     counter, c, tp.d_wbuf, wait_first, ind);
 }
 template <class Cfg, bool L> static int launch_p2(const LaunchGroup &g, const TiledPlan &tp, b2g_context *ctx,
                                                   cudaStream_t stream, unsigned int *counter, double *v,
-                                                  double scale, bool pdl, int wait_first) {
+                                                  double scale, bool pdl, int wait_first, const MatvecArgs *ind) {
     auto kern = phase2_kernel<Cfg, L>;
     static std::atomic<uint64_t> attr_mask{0};
     if (raise_smem_limit(kern, Cfg::SMEM_BYTES, ctx->device, attr_mask))
@@ -482,7 +500,7 @@ template <class Cfg, bool L> static int launch_p2(const LaunchGroup &g, const Ti
     }
     const int grid = std::min(g.n_units, ctx->sm_count * std::max(per_sm, 1));
     return launch_ex(kern, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, pdl, tp.d_win, tp.d_seg, g.d_units, g.n_units,
-                     counter, tp.d_wbuf, v, scale, tp.d_pbuf, wait_first);
+                     counter, tp.d_wbuf, v, scale, tp.d_pbuf, wait_first, ind);
 }
 
 } // namespace b2g
@@ -533,6 +551,8 @@ void b2g_tiled_destroy(void *h) {
     TiledPlan *tp = (TiledPlan *)h;
     if (!tp)
         return;
+    if (tp->graph_exec)
+        cudaGraphExecDestroy(tp->graph_exec);
     for (void *p : tp->to_free)
         if (tp->ctx)
             b2g_dfree(tp->ctx, p);
@@ -1029,6 +1049,9 @@ int b2g_tiled_build(b2g_plan *p) {
     std::stable_sort(tp->groups.begin(), tp->groups.end(), [](const LaunchGroup &a, const LaunchGroup &b) {
         return a.slab != b.slab ? a.slab < b.slab : a.phase < b.phase;
     });
+    if (b2g_dmalloc(ctx, (void **)&tp->d_args, sizeof(MatvecArgs)))
+        return 1;
+    tp->to_free.push_back(tp->d_args);
     tp->n_counters = std::max<int>(64, (int)tp->groups.size());
     if (b2g_dmalloc(ctx, (void **)&tp->d_counters, sizeof(unsigned int) * tp->n_counters))
         return 1;
@@ -1049,7 +1072,57 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
         *count = 0;
     if (!tp || tp->groups.empty())
         return 0;
-    B2G_CUDA(cudaMemsetAsync(tp->d_counters, 0, sizeof(unsigned int) * tp->n_counters, ctx->stream));
+    // ---- CUDA graph replay of small lists (B2G_NO_GRAPH: off)
+    static const bool graphs_on = getenv("B2G_NO_GRAPH") == nullptr;
+    const bool small_list = 2.0 * (double)p->stats.nflop_mnk < 3e11 && tp->slab_doubles.size() <= 1;
+    const MatvecArgs *ind = nullptr;
+    bool capturing = false;
+    if (graphs_on && small_list && stats == nullptr && tp->graph_state >= 0) {
+        if (tp->graph_state == 2) {
+            set_args_kernel<<<1, 1, 0, ctx->stream>>>(tp->d_args, c_dev, v_dev, scale);
+            B2G_CUDA(cudaGraphLaunch(tp->graph_exec, ctx->stream));
+            ctx->launches += tp->graph_kernels + 1;
+            return 0;
+        }
+        if (tp->graph_state == 1) {
+            set_args_kernel<<<1, 1, 0, ctx->stream>>>(tp->d_args, c_dev, v_dev, scale);
+            ctx->launches++;
+            if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess)
+                capturing = true, ind = tp->d_args;
+            else
+                cudaGetLastError(), tp->graph_state = -1;
+        } else
+            tp->graph_state = 1; // this call runs eagerly
+    }
+    const int64_t launches_before = ctx->launches;
+    // 0: the graph was instantiated and launched; 1: capture failed - the caller runs the launches eagerly
+    auto finish_capture = [&]() -> int {
+        capturing = false;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamEndCapture(ctx->stream, &graph) != cudaSuccess || graph == nullptr) {
+            cudaGetLastError();
+            if (graph)
+                cudaGraphDestroy(graph);
+            tp->graph_state = -1;
+            return 1;
+        }
+        const cudaError_t e = cudaGraphInstantiate(&tp->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            tp->graph_exec = nullptr, tp->graph_state = -1;
+            return 1;
+        }
+        tp->graph_kernels = (int)(ctx->launches - launches_before);
+        if (cudaGraphLaunch(tp->graph_exec, ctx->stream) != cudaSuccess) { // the captured work has not run yet
+            cudaGetLastError();
+            cudaGraphExecDestroy(tp->graph_exec);
+            tp->graph_exec = nullptr, tp->graph_state = -1;
+            return 1;
+        }
+        tp->graph_state = 2;
+        return 0;
+    };
     struct Rec {
         std::string name;
         double flops;
@@ -1072,6 +1145,8 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
             B2G_CUDA(cudaEventRecord(recs.back().e1, ctx->stream));
         return 0;
     };
+    auto body = [&]() -> int { // every launch of one matvec (eager, or recorded into the graph being captured)
+    B2G_CUDA(cudaMemsetAsync(tp->d_counters, 0, sizeof(unsigned int) * tp->n_counters, ctx->stream));
     // Without profiling, the launches of one phase are forked onto side streams and joined before
     // the next phase; with profiling everything stays on the context stream (timed one by one).
     // Forking pays when no single launch fills the chip (measured: up to ~2x on the C2 / H10 lists,
@@ -1138,38 +1213,38 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
 #define B2G_DISPATCH(PH, CFG, LAY, CALL)                                                \
     if (g.phase == PH && g.cfg == CFG && g.layout == LAY)                               \
         rc = CALL;
-        B2G_DISPATCH(1, 0, 0, (launch_p1<Cfg0, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
-        B2G_DISPATCH(1, 0, 1, (launch_p1<Cfg0, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
-        B2G_DISPATCH(1, 1, 0, (launch_p1<Cfg1, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
-        B2G_DISPATCH(1, 1, 1, (launch_p1<Cfg1, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
-        B2G_DISPATCH(1, 2, 0, (launch_p1<Cfg2, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
-        B2G_DISPATCH(1, 2, 1, (launch_p1<Cfg2, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
-        B2G_DISPATCH(1, 3, 0, (launch_p1<Cfg3, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
-        B2G_DISPATCH(1, 3, 1, (launch_p1<Cfg3, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
-        B2G_DISPATCH(1, 4, 0, (launch_p1<Cfg4, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
-        B2G_DISPATCH(1, 4, 1, (launch_p1<Cfg4, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
-        B2G_DISPATCH(1, 5, 0, (launch_p1<Cfg5, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
-        B2G_DISPATCH(1, 5, 1, (launch_p1<Cfg5, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
-        B2G_DISPATCH(1, 6, 0, (launch_p1<Cfg6, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
-        B2G_DISPATCH(1, 6, 1, (launch_p1<Cfg6, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
-        B2G_DISPATCH(1, 7, 0, (launch_p1<Cfg7, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
-        B2G_DISPATCH(1, 7, 1, (launch_p1<Cfg7, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first)))
-        B2G_DISPATCH(2, 0, 0, (launch_p2<Cfg0, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
-        B2G_DISPATCH(2, 0, 1, (launch_p2<Cfg0, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
-        B2G_DISPATCH(2, 1, 0, (launch_p2<Cfg1, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
-        B2G_DISPATCH(2, 1, 1, (launch_p2<Cfg1, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
-        B2G_DISPATCH(2, 2, 0, (launch_p2<Cfg2, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
-        B2G_DISPATCH(2, 2, 1, (launch_p2<Cfg2, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
-        B2G_DISPATCH(2, 3, 0, (launch_p2<Cfg3, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
-        B2G_DISPATCH(2, 3, 1, (launch_p2<Cfg3, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
-        B2G_DISPATCH(2, 4, 0, (launch_p2<Cfg4, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
-        B2G_DISPATCH(2, 4, 1, (launch_p2<Cfg4, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
-        B2G_DISPATCH(2, 5, 0, (launch_p2<Cfg5, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
-        B2G_DISPATCH(2, 5, 1, (launch_p2<Cfg5, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
-        B2G_DISPATCH(2, 6, 0, (launch_p2<Cfg6, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
-        B2G_DISPATCH(2, 6, 1, (launch_p2<Cfg6, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
-        B2G_DISPATCH(2, 7, 0, (launch_p2<Cfg7, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
-        B2G_DISPATCH(2, 7, 1, (launch_p2<Cfg7, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first)))
+        B2G_DISPATCH(1, 0, 0, (launch_p1<Cfg0, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first, ind)))
+        B2G_DISPATCH(1, 0, 1, (launch_p1<Cfg0, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first, ind)))
+        B2G_DISPATCH(1, 1, 0, (launch_p1<Cfg1, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first, ind)))
+        B2G_DISPATCH(1, 1, 1, (launch_p1<Cfg1, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first, ind)))
+        B2G_DISPATCH(1, 2, 0, (launch_p1<Cfg2, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first, ind)))
+        B2G_DISPATCH(1, 2, 1, (launch_p1<Cfg2, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first, ind)))
+        B2G_DISPATCH(1, 3, 0, (launch_p1<Cfg3, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first, ind)))
+        B2G_DISPATCH(1, 3, 1, (launch_p1<Cfg3, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first, ind)))
+        B2G_DISPATCH(1, 4, 0, (launch_p1<Cfg4, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first, ind)))
+        B2G_DISPATCH(1, 4, 1, (launch_p1<Cfg4, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first, ind)))
+        B2G_DISPATCH(1, 5, 0, (launch_p1<Cfg5, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first, ind)))
+        B2G_DISPATCH(1, 5, 1, (launch_p1<Cfg5, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first, ind)))
+        B2G_DISPATCH(1, 6, 0, (launch_p1<Cfg6, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first, ind)))
+        B2G_DISPATCH(1, 6, 1, (launch_p1<Cfg6, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first, ind)))
+        B2G_DISPATCH(1, 7, 0, (launch_p1<Cfg7, false>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first, ind)))
+        B2G_DISPATCH(1, 7, 1, (launch_p1<Cfg7, true>(g, *tp, ctx, gs, counter, c_dev, pdl, wait_first, ind)))
+        B2G_DISPATCH(2, 0, 0, (launch_p2<Cfg0, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first, ind)))
+        B2G_DISPATCH(2, 0, 1, (launch_p2<Cfg0, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first, ind)))
+        B2G_DISPATCH(2, 1, 0, (launch_p2<Cfg1, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first, ind)))
+        B2G_DISPATCH(2, 1, 1, (launch_p2<Cfg1, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first, ind)))
+        B2G_DISPATCH(2, 2, 0, (launch_p2<Cfg2, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first, ind)))
+        B2G_DISPATCH(2, 2, 1, (launch_p2<Cfg2, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first, ind)))
+        B2G_DISPATCH(2, 3, 0, (launch_p2<Cfg3, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first, ind)))
+        B2G_DISPATCH(2, 3, 1, (launch_p2<Cfg3, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first, ind)))
+        B2G_DISPATCH(2, 4, 0, (launch_p2<Cfg4, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first, ind)))
+        B2G_DISPATCH(2, 4, 1, (launch_p2<Cfg4, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first, ind)))
+        B2G_DISPATCH(2, 5, 0, (launch_p2<Cfg5, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first, ind)))
+        B2G_DISPATCH(2, 5, 1, (launch_p2<Cfg5, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first, ind)))
+        B2G_DISPATCH(2, 6, 0, (launch_p2<Cfg6, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first, ind)))
+        B2G_DISPATCH(2, 6, 1, (launch_p2<Cfg6, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first, ind)))
+        B2G_DISPATCH(2, 7, 0, (launch_p2<Cfg7, true>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first, ind)))
+        B2G_DISPATCH(2, 7, 1, (launch_p2<Cfg7, false>(g, *tp, ctx, gs, counter, v_dev, scale, pdl, wait_first, ind)))
 #undef B2G_DISPATCH
         if (rc)
             return rc;
@@ -1191,12 +1266,36 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
             if (nt <= 0)
                 continue;
             reduce_kernel<<<std::min(nt * RED_SPLIT, ctx->sm_count * 16), 256, 0, ctx->stream>>>(
-                tp->d_tiles + rg.first, nt, tp->d_part_off, tp->d_win, tp->d_pbuf, v_dev, scale);
+                tp->d_tiles + rg.first, nt, tp->d_part_off, tp->d_win, tp->d_pbuf, v_dev, scale, ind);
             ctx->launches++;
         }
         if (end())
             return 1;
     }
+    return 0;
+    };
+    int body_rc = body();
+    if (capturing) {
+        const int64_t recorded = ctx->launches - launches_before;
+        bool replayed = false;
+        if (body_rc == 0)
+            replayed = finish_capture() == 0;
+        else { // a launch failed while recording: drop the capture
+            cudaGraph_t graph = nullptr;
+            cudaStreamEndCapture(ctx->stream, &graph);
+            if (graph)
+                cudaGraphDestroy(graph);
+            cudaGetLastError();
+            capturing = false, tp->graph_state = -1;
+        }
+        if (!replayed) { // no graph: this matvec runs eagerly, and so do the following ones
+            ctx->launches -= recorded;
+            ind = nullptr;
+            body_rc = body();
+        }
+    }
+    if (body_rc)
+        return body_rc;
     B2G_CUDA(cudaGetLastError());
     if (stats) {
         B2G_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -56,6 +56,12 @@ struct P2Seg {           // phase 2: one K-segment (= one distinct operator bloc
     int32_t col_lo, col_hi, pad; // panel columns the W panel covers: [col_lo, col_hi), zero outside
 };
 
+struct MatvecArgs {      // c, sigma and scale of a replay, read by the kernels of a captured CUDA graph
+    const double *c;
+    double *v;
+    double scale, pad;
+};
+
 struct Unit {            // one CTA-tile x K-chunk
     int32_t idx;         // phase 1: pair index; phase 2: window index
     int32_t row0, col0;  // origin of the tile inside the output matrix (elements)

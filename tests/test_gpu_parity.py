@@ -255,6 +255,36 @@ def test_bounded_w_workspace_gives_the_same_bits(b2g, ctx, monkeypatch):
         assert rel(one, sd.replay(d, nthreads=4)) < TOL
 
 
+def test_graph_replay_of_small_lists_takes_new_arguments(b2g, ctx, monkeypatch):
+    """Small lists replay a captured CUDA graph from the third call on (first call eager, second captured); c, sigma
+    and scale of every replay come through a device argument block.  Five calls with different c, different sigma
+    buffers and scales against the oracle, and bit for bit against the eager route (B2G_NO_GRAPH)."""
+    import torch
+    d = sd.load(os.path.join(GOLDEN, "n2_su2_m60_s4.b2seq"))
+    rng = np.random.default_rng(5)
+    cs = [rng.standard_normal(d.csize) for _ in range(5)]
+    scales = [1.0, -0.5, 2.0, 0.25, 1.0]
+    want = [sc * sd.replay(d, c=c, nthreads=4) for c, sc in zip(cs, scales)]
+    outs = {}
+    for mode in ("graph", "eager"):
+        if mode == "eager":
+            monkeypatch.setenv("B2G_NO_GRAPH", "1")
+        plan = b2g.SeqPlan.from_seqfile(ctx, as_seqfile(b2g, d), d.arenas)
+        got = []
+        for c, sc in zip(cs, scales):
+            cd = torch.tensor(c, dtype=torch.float64, device="cuda")
+            vd = torch.zeros(d.vsize, dtype=torch.float64, device="cuda")  # a fresh sigma buffer every call
+            torch.cuda.synchronize()
+            plan.matvec_dev(cd.data_ptr(), vd.data_ptr(), sc)
+            ctx.synchronize()
+            got.append(vd.cpu().numpy())
+        plan.close()
+        outs[mode] = got
+    for k in range(5):
+        assert rel(outs["graph"][k], want[k]) < TOL, k
+        assert np.array_equal(outs["graph"][k], outs["eager"][k]), k
+
+
 def test_matvec_is_repeatable_on_one_plan(b2g, ctx):
     """A second replay on the same plan must rebuild the W panels, not add to them."""
     d = shared_operator_list(np.random.default_rng(34))
