@@ -1074,7 +1074,8 @@ int b2g_tiled_launch(b2g_plan *p, const double *c_dev, double *v_dev, double sca
         return 0;
     // ---- CUDA graph replay of small lists (B2G_NO_GRAPH: off)
     static const bool graphs_on = getenv("B2G_NO_GRAPH") == nullptr;
-    const bool small_list = 2.0 * (double)p->stats.nflop_mnk < 3e11 && tp->slab_doubles.size() <= 1;
+    // below 50 GFLOP per matvec (N2, H10, C2, chain ends): there the launches, not the kernels, set the pace
+    const bool small_list = 2.0 * (double)p->stats.nflop_mnk < 5e10 && tp->slab_doubles.size() <= 1;
     const MatvecArgs *ind = nullptr;
     bool capturing = false;
     if (graphs_on && small_list && stats == nullptr && tp->graph_state >= 0) {
