@@ -614,7 +614,7 @@ extern "C" int b2g_plan_create(b2g_context *ctx, const b2g_batch *b0, const b2g_
 // Host-side regrouping of a chained pair list into the two-phase tile plan, without a device (timing and
 // tests of the planner): seconds = wall time of the regrouping, units = CTA work units, launches = kernel launches.
 extern "C" int b2g_debug_tiled_plan(const b2g_batch *b0, const b2g_batch *b1, double *seconds, int64_t *units,
-                                    int64_t *launches) {
+                                    int64_t *launches, int64_t *fingerprint) {
     if (!b0 || !b1 || b0->count != b1->count) {
         b2g_set_error("b2g_debug_tiled_plan: bad argument");
         return 1;
@@ -645,6 +645,8 @@ extern "C" int b2g_debug_tiled_plan(const b2g_batch *b0, const b2g_batch *b1, do
         *units = p->stats.n_large;
     if (launches)
         *launches = p->stats.launches;
+    if (fingerprint)
+        *fingerprint = p->stats.arenas; // the host-only build leaves the fingerprint of the plan here
     b2g_tiled_destroy(p->tiled);
     delete p;
     return rc;

@@ -918,47 +918,13 @@ int b2g_tiled_build(b2g_plan *p) {
                     if (!units_of(sl, ph, c, lay).empty())
                         groups[std::make_tuple(sl, ph, c, lay)].swap(units_of(sl, ph, c, lay));
     lap("units");
-    if (ctx == nullptr) { // b2g_debug_tiled_plan: the host-side regrouping alone (no device)
-        int64_t nu = 0;
-        for (auto &kv : groups)
-            nu += (int64_t)kv.second.size();
-        p->stats.launches = (int64_t)groups.size(), p->stats.n_large = nu;
-        return 0;
-    }
-    // ---- 5. upload
-    auto upload = [&](const void *src, size_t bytes, void **dst) -> int {
-        if (b2g_dmalloc(ctx, dst, bytes))
-            return 1;
-        tp->to_free.push_back(*dst);
-        if (bytes)
-            B2G_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
-        return 0;
-    };
-    if (upload(p1g.data(), p1g.size() * sizeof(P1Group), (void **)&tp->d_p1g))
-        return 1;
-    if (upload(p1s.data(), p1s.size() * sizeof(P1Seg), (void **)&tp->d_p1s))
-        return 1;
-    if (upload(wins.data(), wins.size() * sizeof(P2Window), (void **)&tp->d_win))
-        return 1;
-    if (upload(segs.data(), segs.size() * sizeof(P2Seg), (void **)&tp->d_seg))
-        return 1;
-    if (b2g_dmalloc(ctx, (void **)&tp->d_wbuf, std::max<size_t>(tp->wbuf_doubles, 2) * sizeof(double)))
-        return 1;
-    tp->to_free.push_back(tp->d_wbuf);
-    // phase 1 overwrites the column range of every group on every matvec; what no group covers must read as zero
-    B2G_CUDA(cudaMemsetAsync(tp->d_wbuf, 0, std::max<size_t>(tp->wbuf_doubles, 2) * sizeof(double), ctx->stream));
+    // ---- 5. sigma tiles, partial slots, unit order (host)
     // deterministic sigma accumulation: one partial slot per phase-2 unit, grouped by sigma tile
     // (a tile collects partials from both operand layouts), slots in K-chunk order
     const char *env_atomic = getenv("B2G_ATOMIC_SIGMA");
     std::vector<OutTile> tiles;
     std::vector<int64_t> part_off;
     if (!(env_atomic && env_atomic[0] == '1')) {
-        std::map<std::tuple<int, int, int>, std::vector<std::pair<int, HostUnit *>>> by_tile; // (panel,row0,col0)
-        for (auto &kv : groups)
-            if (std::get<1>(kv.first) == 2)
-                for (HostUnit &hu : kv.second)
-                    by_tile[std::make_tuple(hu.u.idx, hu.u.row0, hu.u.col0)].push_back(
-                        std::make_pair(std::get<2>(kv.first), &hu));
         // colour the panels so that panels sharing sigma elements never share a launch
         std::vector<int> colour(wins.size(), 0);
         {
@@ -987,45 +953,63 @@ int b2g_tiled_build(b2g_plan *p) {
                 active.swap(keep_a);
             }
         }
-        std::vector<std::pair<int, std::tuple<int, int, int>>> tile_order;
-        for (auto &kv : by_tile)
-            tile_order.push_back(std::make_pair(colour[std::get<0>(kv.first)], kv.first));
-        std::stable_sort(tile_order.begin(), tile_order.end(),
-                         [](const std::pair<int, std::tuple<int, int, int>> &x,
-                            const std::pair<int, std::tuple<int, int, int>> &y) { return x.first < y.first; });
+        // phase-2 units by (colour of the panel, panel, row0, col0), the partials of a tile in K-chunk order
+        // (= segment order; the segment ranges of the two operand layouts are disjoint)
+        struct TileRef {
+            int colour, panel, row0, col0, seg_begin, cfg;
+            uint32_t seq;
+            HostUnit *hu;
+        };
+        std::vector<TileRef> refs;
+        {
+            size_t n2 = 0;
+            for (auto &kv : groups)
+                if (std::get<1>(kv.first) == 2)
+                    n2 += kv.second.size();
+            refs.reserve(n2);
+            for (auto &kv : groups)
+                if (std::get<1>(kv.first) == 2)
+                    for (HostUnit &hu : kv.second)
+                        refs.push_back(TileRef{colour[hu.u.idx], hu.u.idx, hu.u.row0, hu.u.col0, hu.u.seg_begin,
+                                               std::get<2>(kv.first), (uint32_t)refs.size(), &hu});
+        }
+        std::sort(refs.begin(), refs.end(), [](const TileRef &x, const TileRef &y) {
+            if (x.colour != y.colour)
+                return x.colour < y.colour;
+            if (x.panel != y.panel)
+                return x.panel < y.panel;
+            if (x.row0 != y.row0)
+                return x.row0 < y.row0;
+            if (x.col0 != y.col0)
+                return x.col0 < y.col0;
+            if (x.seg_begin != y.seg_begin)
+                return x.seg_begin < y.seg_begin;
+            return x.seq < y.seq;
+        });
         size_t poff = 0;
-        for (auto &to : tile_order) {
-            auto kvit = by_tile.find(to.second);
-            auto &kv = *kvit;
-            while ((int)tp->tile_ranges.size() <= to.first)
+        for (size_t a = 0; a < refs.size();) {
+            size_t b = a + 1;
+            while (b < refs.size() && refs[b].panel == refs[a].panel && refs[b].row0 == refs[a].row0 &&
+                   refs[b].col0 == refs[a].col0)
+                b++;
+            const int col = refs[a].colour;
+            while ((int)tp->tile_ranges.size() <= col)
                 tp->tile_ranges.push_back(std::make_pair((int)tiles.size(), (int)tiles.size()));
-            auto &lst = kv.second;
-            std::stable_sort(lst.begin(), lst.end(),
-                             [](const std::pair<int, HostUnit *> &x, const std::pair<int, HostUnit *> &y) {
-                                 return x.second->u.seg_begin < y.second->u.seg_begin;
-                             });
-            const int c = lst[0].first;
-            OutTile ot{std::get<0>(kv.first), std::get<1>(kv.first), std::get<2>(kv.first), kCfg[c].bm, kCfg[c].bn,
-                       (int)part_off.size(), 0, 0};
-            for (auto &pr : lst) {
-                pr.second->u.poff = (int64_t)poff;
+            const int c = refs[a].cfg;
+            OutTile ot{refs[a].panel, refs[a].row0, refs[a].col0, kCfg[c].bm, kCfg[c].bn, (int)part_off.size(), 0, 0};
+            for (size_t z = a; z < b; z++) {
+                refs[z].hu->u.poff = (int64_t)poff;
                 part_off.push_back((int64_t)poff);
                 poff += (size_t)kCfg[c].bm * kCfg[c].bn;
             }
             ot.part_end = (int)part_off.size();
             tiles.push_back(ot);
-            tp->tile_ranges[to.first].second = (int)tiles.size();
+            tp->tile_ranges[col].second = (int)tiles.size();
+            a = b;
         }
         tp->pbuf_doubles = poff;
         p->stats.workspace_doubles = (int64_t)(tp->wbuf_doubles + tp->pbuf_doubles);
         tp->n_tiles = (int)tiles.size();
-        if (upload(tiles.data(), tiles.size() * sizeof(OutTile), (void **)&tp->d_tiles))
-            return 1;
-        if (upload(part_off.data(), part_off.size() * sizeof(int64_t), (void **)&tp->d_part_off))
-            return 1;
-        if (b2g_dmalloc(ctx, (void **)&tp->d_pbuf, std::max<size_t>(poff, 2) * sizeof(double)))
-            return 1;
-        tp->to_free.push_back(tp->d_pbuf);
     }
     std::vector<std::vector<Unit>> keep; // host copies must outlive the async copies
     for (auto &kv : groups) {
@@ -1042,10 +1026,69 @@ int b2g_tiled_build(b2g_plan *p) {
         g.n_units = (int)hu.size();
         for (const HostUnit &x : hu)
             g.flops += x.flops;
-        if (upload(keep.back().data(), hu.size() * sizeof(Unit), (void **)&g.d_units))
-            return 1;
         tp->groups.push_back(g);
     }
+    lap("tiles");
+    if (ctx == nullptr) { // b2g_debug_tiled_plan: the host-side regrouping alone (no device)
+        int64_t nu = 0;
+        for (auto &kv : groups)
+            nu += (int64_t)kv.second.size();
+        p->stats.launches = (int64_t)tp->groups.size(), p->stats.n_large = nu;
+        // fingerprint of everything the device would get (planner changes must not change it): FNV-1a over the
+        // unit lists with their partial-slot offsets, the sigma tiles and the slot table
+        uint64_t h = 1469598103934665603ull;
+        auto mix = [&h](const void *ptr, size_t bytes) {
+            const unsigned char *q = (const unsigned char *)ptr;
+            for (size_t i = 0; i < bytes; i++)
+                h = (h ^ q[i]) * 1099511628211ull;
+        };
+        for (auto &k : keep)
+            for (const Unit &u : k) { // field by field: the struct has padding
+                mix(&u.idx, 4), mix(&u.row0, 4), mix(&u.col0, 4), mix(&u.seg_begin, 4), mix(&u.seg_end, 4);
+                mix(&u.pad, 4), mix(&u.poff, 8);
+            }
+        for (const OutTile &t : tiles)
+            mix(&t, sizeof(OutTile));
+        mix(part_off.data(), part_off.size() * sizeof(int64_t));
+        for (const P2Seg &g : segs)
+            mix(&g.w_off, 8), mix(&g.klen, 4), mix(&g.col_lo, 4), mix(&g.col_hi, 4);
+        p->stats.arenas = (int64_t)(h >> 1); // debug entry only: reported as the fingerprint
+        return 0;
+    }
+    // ---- 6. upload
+    auto upload = [&](const void *src, size_t bytes, void **dst) -> int {
+        if (b2g_dmalloc(ctx, dst, bytes))
+            return 1;
+        tp->to_free.push_back(*dst);
+        if (bytes)
+            B2G_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return 0;
+    };
+    if (upload(p1g.data(), p1g.size() * sizeof(P1Group), (void **)&tp->d_p1g))
+        return 1;
+    if (upload(p1s.data(), p1s.size() * sizeof(P1Seg), (void **)&tp->d_p1s))
+        return 1;
+    if (upload(wins.data(), wins.size() * sizeof(P2Window), (void **)&tp->d_win))
+        return 1;
+    if (upload(segs.data(), segs.size() * sizeof(P2Seg), (void **)&tp->d_seg))
+        return 1;
+    if (b2g_dmalloc(ctx, (void **)&tp->d_wbuf, std::max<size_t>(tp->wbuf_doubles, 2) * sizeof(double)))
+        return 1;
+    tp->to_free.push_back(tp->d_wbuf);
+    // phase 1 overwrites the column range of every group on every matvec; what no group covers must read as zero
+    B2G_CUDA(cudaMemsetAsync(tp->d_wbuf, 0, std::max<size_t>(tp->wbuf_doubles, 2) * sizeof(double), ctx->stream));
+    if (!tiles.empty() || tp->pbuf_doubles != 0 || !part_off.empty()) {
+        if (upload(tiles.data(), tiles.size() * sizeof(OutTile), (void **)&tp->d_tiles))
+            return 1;
+        if (upload(part_off.data(), part_off.size() * sizeof(int64_t), (void **)&tp->d_part_off))
+            return 1;
+        if (b2g_dmalloc(ctx, (void **)&tp->d_pbuf, std::max<size_t>(tp->pbuf_doubles, 2) * sizeof(double)))
+            return 1;
+        tp->to_free.push_back(tp->d_pbuf);
+    }
+    for (size_t gi = 0; gi < tp->groups.size(); gi++) // keep[gi] belongs to groups[gi] (not yet reordered)
+        if (upload(keep[gi].data(), keep[gi].size() * sizeof(Unit), (void **)&tp->groups[gi].d_units))
+            return 1;
     std::stable_sort(tp->groups.begin(), tp->groups.end(), [](const LaunchGroup &a, const LaunchGroup &b) {
         return a.slab != b.slab ? a.slab < b.slab : a.phase < b.phase;
     });

@@ -103,9 +103,11 @@ int b2g_context_synchronize(b2g_context *ctx);
  * variable B2G_PROF): seconds and calls accumulated per label.  b2g_prof_record adds to a label (the
  * reference-side binding uses it for its own sections), b2g_prof_dump writes one JSON object to `path`
  * (NULL or "-": stderr) and returns 0; both are no-ops when the profile is off. */
-/* Host-side regrouping of a chained pair list into the two-phase tile plan, without a device (planner timing). */
+/* Host-side regrouping of a chained pair list into the two-phase tile plan, without a device (planner timing and
+ * tests): work units, launches, and a fingerprint (FNV-1a) of everything the device would receive - unit lists with
+ * their partial-slot offsets, sigma tiles, slot table, W offsets. */
 int b2g_debug_tiled_plan(const b2g_batch *batch0, const b2g_batch *batch1, double *seconds, int64_t *units,
-                         int64_t *launches);
+                         int64_t *launches, int64_t *fingerprint);
 int b2g_prof_enabled(void);
 void b2g_prof_record(const char *label, double seconds);
 int b2g_prof_dump(const char *path);

@@ -49,10 +49,10 @@ def test_tile_plan_regrouping_runs_on_the_host(b2g, name):
     (b0, b1), keep = b2g._make_batches(d0, d1)
     got = []
     for _ in range(2):
-        sec, units, launches = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+        sec, units, launches, fp = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
         rc = b2g.lib().b2g_debug_tiled_plan(ctypes.byref(b0), ctypes.byref(b1), ctypes.byref(sec), ctypes.byref(units),
-                                            ctypes.byref(launches))
+                                            ctypes.byref(launches), ctypes.byref(fp))
         assert rc == 0
-        got.append((units.value, launches.value))
+        got.append((units.value, launches.value, fp.value))
     assert got[0] == got[1]
     assert got[0][0] >= 2 and 2 <= got[0][1] <= 32  # at least one unit per phase; at most 8 shapes x 2 layouts x 2 phases

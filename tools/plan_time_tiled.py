@@ -17,11 +17,11 @@ for path in paths:
     d0, d1 = sf.as_batches(1 << 40)
     (b0, b1), keep = b2g._make_batches(d0, d1)
     for it in range(3):
-        sec, units, launches = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+        sec, units, launches, fp = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
         rc = L.b2g_debug_tiled_plan(ctypes.byref(b0), ctypes.byref(b1), ctypes.byref(sec), ctypes.byref(units),
-                                    ctypes.byref(launches))
+                                    ctypes.byref(launches), ctypes.byref(fp))
         assert rc == 0, L.b2g_last_error()
-        print("%s: pairs %d units %d launches %d plan %.1f ms" % (os.path.basename(path), sf.npairs, units.value,
-                                                                 launches.value, sec.value * 1e3))
+        print("%s: pairs %d units %d launches %d plan %.1f ms fingerprint %016x" % (
+            os.path.basename(path), sf.npairs, units.value, launches.value, sec.value * 1e3, fp.value & (2**64 - 1)))
 if os.environ.get("B2G_PROF"):
     L.b2g_prof_dump(None)
