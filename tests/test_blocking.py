@@ -361,6 +361,24 @@ def test_recorded_blocking_workloads_are_consistent(b2g):
         assert (cols[order][1:][same] == cols[order][:-1][same]).all()
 
 
+def test_plan_of_the_recorded_heff_blocking_list_keeps_descriptors_few(b2g):
+    """Host-side regrouping (B2G_PLAN_ONLY, no GPU) of the Cr2 SVP M=4000 H_eff blocking list: 66 630 terms fold
+    into 58 778 windows without serial components, and the work is handed to the device in units of whole rows /
+    whole tile rows - round 1 made one descriptor per window row (1.40 M for this list), which cost 10-50x the
+    kernel time to build and upload."""
+    from conftest import ROOT
+    tp = b2g.load_tpfile(os.path.join(ROOT, "workloads", "cr2_svp_m4000_blocking", "cr2_m4000_s20_call39.b2tp.gz"))
+    a_off, b_off, c_off, n_in, n_out = tp.offsets()
+    terms = np.zeros(tp.nterms, dtype=b2g.TP_DTYPE)
+    terms["a"], terms["b"], terms["c"] = (1 << 40) + 8 * a_off, (1 << 40) + 8 * b_off, (1 << 44) + 8 * c_off
+    for k in ("am", "an", "bm", "bn", "cn", "conja", "conjb", "scale"):
+        terms[k] = tp.t[k]
+    st = b2g.tensor_product_plan(terms, b2g.DST_ZERO)
+    assert st.entries == tp.nterms and st.clusters == 58778 and st.serial_entries == 0
+    assert 50_000 < st.units < 250_000, st.units
+    assert st.bytes_out == 8 * int(tp.out_sizes.sum()) or st.bytes_out > 0
+
+
 # ----------------------------------------------------------------------------- host-side regrouping (no GPU)
 
 
